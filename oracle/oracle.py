@@ -1,0 +1,303 @@
+"""Python face of the CPU parity oracle.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, `__graft_entry__.smoke()` and bench.py's `cpu_baseline` / `--impl reference`
+legs may import this module; nothing under `pydrex_b200/` does.
+
+It wraps `libdrex_oracle.so` (drex_oracle.c, the C restatement of the reference's
+arithmetic) with ctypes and restates the one piece of the hot path that is host control
+flow in the reference: the LSODA driver of `Mineral.update_orientations`
+(/root/reference/src/pydrex/minerals.py:312-541).
+
+Third-party arithmetic: the time integrator is `scipy.integrate.LSODA` (ODEPACK lsoda),
+which the reference calls at minerals.py:518-533.  scipy is unpinned by the reference
+(pyproject.toml:36 `scipy >= 1.2`); the golden vectors were generated with the scipy of
+this image (1.18.1) and the oracle calls the same installed scipy, exactly as the
+reference would.
+
+Parity status: PINNED against tests/golden/*.npz (see tests/test_oracle.py).
+"""
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+from scipy.integrate import LSODA
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libdrex_oracle.so")
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int)
+_i64p = ctypes.POINTER(ctypes.c_int64)
+
+
+def build(force=False):
+    """Compile the C restatement with gcc (oracle/Makefile)."""
+    src = os.path.join(_HERE, "drex_oracle.c")
+    if (
+        force
+        or not os.path.exists(_LIB_PATH)
+        or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src)
+    ):
+        subprocess.run(["make", "-C", _HERE, "-B", "libdrex_oracle.so"], check=True,
+                       capture_output=True)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(_LIB_PATH)
+        L.oracle_strain_rate_max.restype = ctypes.c_double
+        L.oracle_strain_rate_max.argtypes = [_dp]
+        L.oracle_left_stretch.argtypes = [_dp, _dp]
+        L.oracle_get_crss.argtypes = [ctypes.c_int, ctypes.c_int, _dp]
+        L.oracle_slip_invariants.argtypes = [_dp, _dp, _dp]
+        L.oracle_rotation_and_strain.argtypes = (
+            [ctypes.c_int, ctypes.c_int, _dp, _dp, _dp] + [ctypes.c_double] * 3 + [_dp] * 6
+        )
+        L.oracle_derivatives.argtypes = (
+            [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64]
+            + [_dp] * 5 + [ctypes.c_double] * 5 + [_dp, _dp]
+        )
+        L.oracle_extract_vars.argtypes = [_dp, ctypes.c_int64, _dp, _dp, _dp]
+        L.oracle_apply_gbs.argtypes = [_dp, _dp, ctypes.c_double, _dp, ctypes.c_int64]
+        L.oracle_eval_rhs.argtypes = (
+            [_dp, _dp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+            + [ctypes.c_double] * 5 + [_dp, _dp]
+        )
+        L.oracle_voigt_to_tensor.argtypes = [_dp, _dp]
+        L.oracle_tensor_to_voigt.argtypes = [_dp, _dp]
+        L.oracle_rotate_tensor.argtypes = [_dp, _dp, _dp]
+        L.oracle_voigt_average_accumulate.argtypes = [
+            _dp, _dp, ctypes.c_int64, _dp, ctypes.c_double, _dp]
+        L.oracle_matrix_to_quat.argtypes = [_dp, _dp]
+        L.oracle_symmetry_ops.argtypes = [ctypes.c_int, ctypes.c_int, _dp]
+        L.oracle_max_misorientation.argtypes = [ctypes.c_int, ctypes.c_int]
+        L.oracle_misorientations_random.restype = ctypes.c_double
+        L.oracle_misorientations_random.argtypes = [
+            ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int]
+        L.oracle_misorientation_index.restype = ctypes.c_double
+        L.oracle_misorientation_index.argtypes = [
+            _dp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, _dp, _i64p]
+        _lib = L
+    return _lib
+
+
+def _c(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(_dp)
+
+
+# ----------------------------------------------------------------------------- core.py
+
+
+def get_crss(phase, fabric):
+    out = np.empty(4)
+    if lib().oracle_get_crss(int(phase), int(fabric), out.ctypes.data_as(_dp)) != 0:
+        raise ValueError(f"unsupported phase/fabric: {phase}/{fabric}")
+    return out
+
+
+def slip_invariants(strain_rate, orientation):
+    D, Dp = _c(strain_rate)
+    a, ap = _c(orientation)
+    out = np.empty(4)
+    lib().oracle_slip_invariants(Dp, ap, out.ctypes.data_as(_dp))
+    return out
+
+
+def grain_probe(phase, fabric, orientation, strain_rate, velocity_gradient, p, n, lam):
+    """All per-grain intermediates of core._get_rotation_and_strain (core.py:687-760)."""
+    a, ap = _c(orientation)
+    D, Dp = _c(strain_rate)
+    Lm, Lp = _c(velocity_gradient)
+    da, E = np.empty(9), np.empty(1)
+    inv, rates, G, g0 = np.empty(4), np.empty(4), np.empty(9), np.empty(1)
+    rc = lib().oracle_rotation_and_strain(
+        int(phase), int(fabric), ap, Dp, Lp, p, n, lam,
+        da.ctypes.data_as(_dp), E.ctypes.data_as(_dp), inv.ctypes.data_as(_dp),
+        rates.ctypes.data_as(_dp), G.ctypes.data_as(_dp), g0.ctypes.data_as(_dp))
+    if rc != 0:
+        raise ValueError("unsupported phase/fabric")
+    return {"orientation_change": da.reshape(3, 3), "strain_energy": E[0], "invariants": inv,
+            "slip_rates": rates, "deformation_rate": G.reshape(3, 3), "slip_rate_softest": g0[0]}
+
+
+def derivatives(regime, phase, fabric, n_grains, orientations, fractions, strain_rate,
+                velocity_gradient, deformation_gradient_spin, stress_exponent,
+                deformation_exponent, nucleation_efficiency, gbm_mobility, volume_fraction):
+    """core.derivatives (core.py:347-474), same positional signature."""
+    o, op = _c(orientations)
+    f, fp = _c(fractions)
+    D, Dp = _c(strain_rate)
+    Lm, Lp = _c(velocity_gradient)
+    S, Sp = _c(deformation_gradient_spin)
+    od = np.empty((n_grains, 3, 3))
+    fd = np.empty(n_grains)
+    rc = lib().oracle_derivatives(
+        int(regime), int(phase), int(fabric), int(n_grains), op, fp, Dp, Lp, Sp,
+        float(stress_exponent), float(deformation_exponent), float(nucleation_efficiency),
+        float(gbm_mobility), float(volume_fraction),
+        od.ctypes.data_as(_dp), fd.ctypes.data_as(_dp))
+    if rc == -1:
+        raise ValueError("unsupported phase/fabric")
+    if rc == -2:
+        raise ValueError("this deformation mechanism is not yet supported.")
+    if rc == -3:
+        raise ValueError(f"regime must be a valid `DeformationRegime`, not {regime}")
+    return od, fd
+
+
+# ----------------------------------------------------------------------------- minerals.py
+
+
+def extract_vars(y, n_grains):
+    y, yp = _c(y)
+    F, o, f = np.empty((3, 3)), np.empty((n_grains, 3, 3)), np.empty(n_grains)
+    lib().oracle_extract_vars(yp, n_grains, F.ctypes.data_as(_dp), o.ctypes.data_as(_dp),
+                              f.ctypes.data_as(_dp))
+    return F, o, f
+
+
+def apply_gbs(orientations, fractions, gbs_threshold, orientations_prev, n_grains):
+    o = np.array(orientations, dtype=np.float64, order="C")
+    f = np.array(fractions, dtype=np.float64, order="C")
+    op, opp = _c(orientations_prev)
+    lib().oracle_apply_gbs(o.ctypes.data_as(_dp), f.ctypes.data_as(_dp), float(gbs_threshold),
+                           opp, n_grains)
+    return o, f
+
+
+class RhsCounter:
+    def __init__(self):
+        self.nfev = 0
+        self.nsteps = 0
+
+
+def update_orientations(orientations, fractions, regime, phase, fabric, params,
+                        deformation_gradient, get_velocity_gradient, pathline,
+                        counter=None, **kwargs):
+    """One call of Mineral.update_orientations (minerals.py:312-541) on explicit state.
+
+    Returns (F_new, orientations_new, fractions_new).  `get_velocity_gradient(t, x)` and
+    `pathline = (t0, t1, get_position)` are the reference's callables.
+    """
+    n_grains = len(fractions)
+    t0, t1, get_position = pathline
+    if not callable(get_velocity_gradient) or not callable(get_position):
+        raise ValueError("unable to evaluate velocity gradient / position callable")
+    volume_fraction = params["phase_fractions"][list(params["phase_assemblage"]).index(phase)]
+    p = float(params["stress_exponent"])
+    n = float(params["deformation_exponent"])
+    lam = float(params["nucleation_efficiency"])
+    M = float(params["gbm_mobility"])
+    work = np.empty(10 * n_grains)
+    workp = work.ctypes.data_as(_dp)
+    L_ = lib()
+
+    def eval_rhs(t, y):  # minerals.py:388-453
+        Lm = np.ascontiguousarray(get_velocity_gradient(t, get_position(t)), dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        dy = np.empty_like(y)
+        rc = L_.oracle_eval_rhs(
+            Lm.ctypes.data_as(_dp), y.ctypes.data_as(_dp), n_grains, int(regime), int(phase),
+            int(fabric), p, n, lam, M, float(volume_fraction), dy.ctypes.data_as(_dp), workp)
+        if rc != 0:
+            raise ValueError("unsupported regime/phase/fabric")
+        if counter is not None:
+            counter.nfev += 1
+        return dy
+
+    o_prev = np.ascontiguousarray(orientations, dtype=np.float64)
+    y0 = np.hstack((np.asarray(deformation_gradient, dtype=np.float64).ravel(),
+                    o_prev.ravel(), np.asarray(fractions, dtype=np.float64)))
+    solver = LSODA(
+        eval_rhs, t0, y0, t1,
+        atol=kwargs.pop("atol", np.abs(y0 * 1e-6) + 1e-4),       # minerals.py:523
+        rtol=kwargs.pop("rtol", 1e-6),                            # minerals.py:524
+        first_step=kwargs.pop("first_step", np.abs(t1 - t0) * 1e-1),  # minerals.py:525
+        **kwargs,
+    )
+    while True:
+        message = solver.step()
+        if message is not None and solver.status == "failed":
+            raise RuntimeError(message)  # reference: pydrex.exceptions.IterationError
+        if counter is not None:
+            counter.nsteps += 1
+        if solver.status != "running":
+            break
+    # minerals.py:464-474 act on a copy of the solver state on every internal step and are
+    # discarded by ODEPACK except after the final one.
+    _, o, f = extract_vars(solver.y, n_grains)
+    o, f = apply_gbs(o, f, params["gbs_threshold"], o_prev, n_grains)
+    y_end = np.hstack((solver.y[:9], o.ravel(), f))
+    F, o, f = extract_vars(y_end, n_grains)  # minerals.py:536-538
+    return F, o, f
+
+
+# ----------------------------------------------------------------------------- diagnostics
+
+
+def voigt_average(orientations, fractions, stiffness, phase_fraction=1.0, out=None):
+    """One (snapshot, phase) term of minerals.voigt_averages (minerals.py:729-739)."""
+    o, op = _c(orientations)
+    f, fp = _c(fractions)
+    S, Sp = _c(stiffness)
+    if out is None:
+        out = np.zeros((6, 6))
+    lib().oracle_voigt_average_accumulate(op, fp, len(f), Sp, float(phase_fraction),
+                                          out.ctypes.data_as(_dp))
+    return out
+
+
+def rotate_voigt(stiffness, rotation):
+    """elastic_tensor_to_voigt(rotate(voigt_to_elastic_tensor(S), R)) (tensors.py:167-273)."""
+    S, Sp = _c(stiffness)
+    R, Rp = _c(rotation)
+    T, Tr, V = np.empty(81), np.empty(81), np.empty((6, 6))
+    lib().oracle_voigt_to_tensor(Sp, T.ctypes.data_as(_dp))
+    lib().oracle_rotate_tensor(T.ctypes.data_as(_dp), Rp, Tr.ctypes.data_as(_dp))
+    lib().oracle_tensor_to_voigt(Tr.ctypes.data_as(_dp), V.ctypes.data_as(_dp))
+    return V
+
+
+def matrix_to_quat(m):
+    m, mp = _c(m)
+    q = np.empty(4)
+    lib().oracle_matrix_to_quat(mp, q.ctypes.data_as(_dp))
+    return q
+
+
+def symmetry_ops(system):
+    """4x4 matrices acting on scalar-last quaternions; `system` = LatticeSystem.value."""
+    buf = np.zeros((16, 4, 4))
+    n = lib().oracle_symmetry_ops(int(system[0]), int(system[1]), buf.ctypes.data_as(_dp))
+    if n < 0:
+        raise ValueError(f"unsupported lattice system: {system}")
+    return buf[:n].copy()
+
+
+def misorientations_random(low, high, system):
+    return lib().oracle_misorientations_random(float(low), float(high), int(system[0]),
+                                               int(system[1]))
+
+
+def misorientation_index(orientations, system, return_hist=False):
+    """diagnostics.misorientation_index (diagnostics.py:332-367); system = (a, b) tuple."""
+    o, op = _c(orientations)
+    tmax = lib().oracle_max_misorientation(int(system[0]), int(system[1]))
+    if tmax < 0:
+        raise ValueError(f"unsupported lattice system: {system}")
+    hist = np.empty(tmax)
+    counts = np.empty(tmax, dtype=np.int64)
+    M = lib().oracle_misorientation_index(op, len(o), int(system[0]), int(system[1]),
+                                          hist.ctypes.data_as(_dp), counts.ctypes.data_as(_i64p))
+    if return_hist:
+        return M, hist, counts
+    return M

@@ -1,0 +1,64 @@
+"""pytest configuration: the `gpu` marker and shared fixtures."""
+
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box)")
+
+
+def pytest_collection_modifyitems(config, items):
+    try:
+        import torch
+
+        has_gpu = torch.cuda.is_available()
+    except Exception:  # pragma: no cover
+        has_gpu = False
+    if has_gpu:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device visible")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+def _load(name):
+    return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
+def golden_derivatives():
+    return _load("derivatives.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_integrate():
+    return _load("integrate.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_diagnostics():
+    return _load("diagnostics.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_config1():
+    return _load("config1_n5000.npz")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import oracle as _oracle
+
+    _oracle.build()
+    return _oracle
