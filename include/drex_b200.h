@@ -1,0 +1,224 @@
+/*
+ * drex_b200.h -- C ABI of libdrex_b200.so: the B200 (sm_100a) CUDA implementation of the
+ * PyDRex crystallographic-preferred-orientation (CPO) hot path.
+ *
+ * Every entry point replaces one reference interface (paths relative to the reference
+ * tree, src/pydrex/...).  The reference is pure Python (numba + SciPy); its "FFI" for this
+ * path is a ctypes binding, shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all array pointers are DEVICE pointers unless the
+ *    name ends in _host;
+ *  - the caller owns every buffer; the library allocates nothing that outlives a call and
+ *    keeps no pointer after returning; scratch comes from a caller-provided workspace
+ *    whose size is queried first (drex_integrate_workspace_bytes, ...);
+ *  - every function is stream-ordered on `stream` (a cudaStream_t passed as void*) and
+ *    returns immediately after enqueueing; 0 = ok, <0 = error (see DREX_E_*), message via
+ *    drex_last_error (thread-local);
+ *  - a "system" is one (particle, mineral phase) grain ensemble of N grains;
+ *  - orientations are stored SoA, component-major: o[system][c][grain], c = 3*row + col of
+ *    the 3x3 direction-cosine matrix (rows = crystal a, b, c axes) -- coalesced per-grain
+ *    loads; the reference's AoS [N][3][3] layout is converted by drex_pack_soa_f64;
+ *  - 3x3 matrices (L, F, D, ...) are row-major double[9].
+ */
+#ifndef DREX_B200_H
+#define DREX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DREX_VERSION_MAJOR 0
+#define DREX_VERSION_MINOR 1
+
+/* error codes */
+#define DREX_OK 0
+#define DREX_E_INVALID (-1)   /* bad argument (ValueError on the Python side) */
+#define DREX_E_UNSUPPORTED (-2) /* unsupported regime / phase / fabric (ValueError) */
+#define DREX_E_CUDA (-3)      /* CUDA runtime error */
+#define DREX_E_WORKSPACE (-4) /* workspace too small */
+#define DREX_E_NODEVICE (-5)  /* no sm_100 device */
+
+/* enums mirror core.MineralPhase / MineralFabric / DeformationRegime (core.py:35-118) */
+#define DREX_PHASE_OLIVINE 0
+#define DREX_PHASE_ENSTATITE 1
+#define DREX_REGIME_MIN_VISCOSITY 0
+#define DREX_REGIME_MATRIX_DIFFUSION 1
+#define DREX_REGIME_MATRIX_DISLOCATION 4
+#define DREX_REGIME_FRICTIONAL_YIELDING 6
+#define DREX_REGIME_MAX_VISCOSITY 7
+
+/* velocity-gradient providers for the integrator (replace the Python callables
+ * get_velocity_gradient(t, get_position(t)) of minerals.py:388-392) */
+#define DREX_L_CONSTANT 0  /* K = 1: L(t) = nodes[0] */
+#define DREX_L_LINEAR 1    /* K = 2: linear in time between L(t0) and L(t1) */
+#define DREX_L_CHEBYSHEV 2 /* K >= 2 Chebyshev-Lobatto nodes on [t0, t1], barycentric */
+#define DREX_L_PIECEWISE 3 /* K >= 2 uniform nodes on [t0, t1], piecewise linear */
+
+/* integrator status per system */
+#define DREX_STATUS_OK 0
+#define DREX_STATUS_MAX_STEPS 1
+#define DREX_STATUS_STEP_UNDERFLOW 2
+#define DREX_STATUS_NOT_FINITE 3
+
+/* ---- library ---------------------------------------------------------------------- */
+
+int drex_version(int *major, int *minor);
+/* copies the calling thread's last error message (NUL-terminated) into buf */
+int drex_last_error(char *buf, size_t n);
+/* sm count / compute capability of `device`; DREX_E_NODEVICE unless cc >= 10.0 */
+int drex_device_info(int device, int *sm_count, int *cc_major, int *cc_minor);
+
+/* ---- layout ----------------------------------------------------------------------- */
+
+/* AoS [S][N][9] (reference layout, minerals.py:221-222) -> SoA [S][9][N] and back */
+int drex_pack_soa_f64(const double *aos, double *soa, int64_t S, int64_t N, void *stream);
+int drex_unpack_soa_f64(const double *soa, double *aos, int64_t S, int64_t N, void *stream);
+
+/* ---- core.derivatives (core.py:347-474) ------------------------------------------- */
+
+/* Scalar parameters of the D-Rex model shared by all systems of a call
+ * (params dict of minerals.py:441-445, 470). */
+typedef struct drex_params {
+    double stress_exponent;       /* p */
+    double deformation_exponent;  /* n */
+    double nucleation_efficiency; /* lambda* */
+    double gbm_mobility;          /* M* */
+    double gbs_threshold;         /* chi; used by drex_integrate_f64 only */
+} drex_params_t;
+
+size_t drex_derivatives_workspace_bytes(int64_t S, int64_t N);
+
+/* Batched core.derivatives: for each system s of S,
+ *   (orientations_diff, fractions_diff) = derivatives(regime[s], phase[s], fabric[s], N,
+ *        o[s], f[s], D[s], L[s], spin[s], p, n, lambda, M, vol_frac[s]).
+ * o_soa/do_soa: [S][9][N]; f/df: [S][N]; D, L, spin: [S][9] (D, L already divided by the
+ * max strain rate as at minerals.py:438-439); regime/phase/fabric: int32 [S];
+ * vol_frac: [S].  Unsupported regimes (2, 3, 5) or (phase, fabric) pairs are rejected
+ * from the HOST copies regime_host/phase_host/fabric_host (int32 [S]) before launch. */
+int drex_derivatives_f64(const double *o_soa, const double *f, const double *D, const double *L,
+                         const double *spin, const int32_t *regime, const int32_t *phase,
+                         const int32_t *fabric, const double *vol_frac,
+                         const int32_t *regime_host, const int32_t *phase_host,
+                         const int32_t *fabric_host, const drex_params_t *params, int64_t S,
+                         int64_t N, double *do_soa, double *df, void *workspace,
+                         size_t workspace_bytes, void *stream);
+
+/* Per-grain intermediates of core._get_rotation_and_strain (core.py:687-760), i.e. what
+ * the reference's private helpers _get_slip_invariants (571-598), _get_slip_rates_olivine
+ * (541-568), _get_deformation_rate (477-501), _get_slip_rate_softest (504-538) and
+ * _get_strain_energy (645-684) return, for G grains of one (phase, fabric).
+ * o_aos: [G][9]; D, L: [9]; outputs (any may be NULL): invariants [G][4], slip_rates [G][4],
+ * deformation_rate [G][9], slip_rate_softest [G], strain_energy [G],
+ * orientation_change [G][9]. */
+int drex_grain_probe_f64(const double *o_aos, const double *D, const double *L, int phase,
+                         int fabric, const drex_params_t *params, int64_t G, double *invariants,
+                         double *slip_rates, double *deformation_rate, double *slip_rate_softest,
+                         double *strain_energy, double *orientation_change, void *stream);
+
+/* The reference's private per-grain helpers, callable on arbitrary inputs (the reference
+ * tests call them directly, tests/test_core.py:142-164,753-762).  One grain per call; all
+ * pointers are device pointers; `out` receives 4, 4, 9, 1, 9 or 1 doubles.
+ *   op 0  _get_slip_invariants(strain_rate=in0[9], orientation=in1[9])        core.py:571-598
+ *   op 1  _get_slip_rates_olivine(invariants=in0[4], slip_indices=idx[4],
+ *                                 crss=in1[4], deformation_exponent=s0)       core.py:541-568
+ *   op 2  _get_deformation_rate(orientation=in0[9], slip_rates=in1[4])        core.py:477-501
+ *   op 3  _get_slip_rate_softest(deformation_rate=in0[9], velocity_gradient=in1[9])  504-538
+ *   op 4  _get_orientation_change(orientation=in0[9], velocity_gradient=in1[9],
+ *                                 deformation_rate=in2[9], slip_rate_softest=s0)     601-642
+ *   op 5  _get_strain_energy(crss=in0[4], slip_rates=in1[4], slip_rate_softest=s0,
+ *                            stress_exponent=s1, deformation_exponent=s2,
+ *                            nucleation_efficiency=s3)                        core.py:645-684 */
+int drex_grain_helper_f64(int op, const double *in0, const double *in1, const double *in2,
+                          const int32_t *idx, double s0, double s1, double s2, double s3,
+                          double *out, void *stream);
+
+/* ---- Mineral.update_orientations (minerals.py:312-541) ---------------------------- */
+
+typedef struct drex_tolerances {
+    /* error weight of component i: atol_abs + (atol_rel + rtol) * max(|y_i|, |y_new_i|);
+     * reference default (minerals.py:523-524): rtol 1e-6, atol 1e-4 + 1e-6 |y0_i|;
+     * weighted MAX norm as in ODEPACK lsoda */
+    double rtol;
+    double atol_abs;
+    double atol_rel;
+    double first_step_frac; /* first trial step = frac * |t1 - t0| when h_io is NULL or <= 0;
+                               0 selects the whole interval */
+    double max_step_frac;   /* cap on the step as a fraction of |t1 - t0| (<= 0: none) */
+    int32_t max_steps;      /* attempted steps per system before DREX_STATUS_MAX_STEPS */
+    int32_t method;         /* 0: Bogacki-Shampine 3(2) with FSAL */
+} drex_tolerances_t;
+
+size_t drex_integrate_workspace_bytes(int64_t S, int64_t N, int device);
+
+/* Advance S systems from t0 to t1 (per particle) with per-system adaptive steps, then
+ * apply grain-boundary sliding once against the interval-start orientations
+ * (minerals.py:464-474, utils.apply_gbs utils.py:159-180) and the final clip/renormalise
+ * (utils.extract_vars utils.py:183-190).
+ *
+ * sys_particle [S]  index into the per-particle arrays t0/t1/L_nodes
+ * sys_phase/sys_fabric/sys_regime [S]  int32; *_host copies are validated before launch
+ * sys_vol_frac [S]  phase volume fraction (minerals.py:412-415)
+ * F [S][9]          deformation gradient, in/out (each phase integrates it, minerals.py:426)
+ * o_in/f_in         state at t0; o_out/f_out state at t1 (may alias the inputs)
+ * L_kind, K, L_nodes [P][K][9]  velocity-gradient provider (DREX_L_*)
+ * h_io [S]          in: first trial step (<= 0: use first_step_frac); out: next suggested
+ *                   step; may be NULL
+ * status, n_rhs, n_accept, n_reject  int32 [S] outputs (n_* may be NULL)
+ */
+int drex_integrate_f64(int64_t S, int64_t P, int64_t N, const int32_t *sys_particle,
+                       const int32_t *sys_phase, const int32_t *sys_fabric,
+                       const int32_t *sys_regime, const double *sys_vol_frac,
+                       const int32_t *sys_phase_host, const int32_t *sys_fabric_host,
+                       const int32_t *sys_regime_host, double *F, const double *o_in,
+                       const double *f_in, double *o_out, double *f_out, const double *t0,
+                       const double *t1, int L_kind, int K, const double *L_nodes,
+                       const drex_params_t *params, const drex_tolerances_t *tol, double *h_io,
+                       int32_t *status, int32_t *n_rhs, int32_t *n_accept, int32_t *n_reject,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- minerals.voigt_averages (minerals.py:688-740) -------------------------------- */
+
+/* Cbar[s] (+)= phase_fraction[s] * sum_g f[s][g] * voigt(rotate(C(stiffness[s]), o[s][g]^T))
+ * with tensors.rotate / elastic_tensor_to_voigt semantics (tensors.py:187-273).
+ * stiffness: [S][36] 6x6 Voigt matrices (GPa); Cbar: [S][36]; accumulate != 0 adds to Cbar. */
+int drex_voigt_average_f64(const double *o_soa, const double *f, const double *stiffness,
+                           const double *phase_fraction, int64_t S, int64_t N, double *Cbar,
+                           int accumulate, void *stream);
+
+/* ---- diagnostics.misorientation_index (diagnostics.py:332-367) -------------------- */
+
+size_t drex_mindex_workspace_bytes(int64_t S, int64_t N, int system_a, int system_b);
+
+/* Closed-form random-texture density per 1-degree bin (stats.misorientations_random,
+ * stats.py:130-200), host-side; theory_host: [theta_max].  Returns theta_max or <0. */
+int drex_mindex_theory_host(int system_a, int system_b, double *theory_host);
+/* stats.misorientations_random(low, high, system) for arbitrary bin edges in degrees;
+ * DREX_E_INVALID for bad bounds, DREX_E_UNSUPPORTED where the reference asserts. */
+int drex_misorientations_random_host(double low, double high, int system_a, int system_b,
+                                     double *density_host);
+
+/* M-index of S textures of N grains each.  (system_a, system_b) = LatticeSystem.value
+ * (geometry.py:29-34).  o_soa: [S][9][N] float64.  M: [S] float64.  counts (optional):
+ * [S][theta_max] int64 histogram of pair misorientation angles in 1-degree bins.
+ * Quaternions are float32 and the symmetry operations are applied exactly as
+ * stats.misorientation_hist does (stats.py:105-123), including utils.quat_product's
+ * missing cross term (utils.py:365-371). */
+int drex_mindex_f32(const double *o_soa, int64_t S, int64_t N, int system_a, int system_b,
+                    double *M, int64_t *counts, void *workspace, size_t workspace_bytes,
+                    void *stream);
+
+/* ---- measurement helper ----------------------------------------------------------- */
+
+/* Runs a dependent-DFMA loop that saturates the FP64 pipe and returns the measured FP64
+ * rate in FLOP/s (2 per DFMA) in *flops_host -- the denominator for the FP64 roofline,
+ * which MEASURED_PEAKS.json does not carry. */
+int drex_fp64_peak_probe(int device, double *flops_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DREX_B200_H */

@@ -1,0 +1,546 @@
+// drex_capi.cu -- the C ABI of libdrex_b200.so (declared in include/drex_b200.h).
+//
+// Host-side argument checking and kernel launches only; every numeric result comes from
+// the sm_100a kernels in the .cuh files next to this one.  There is no CPU fallback: a
+// call without a usable device returns DREX_E_CUDA / DREX_E_NODEVICE.
+#include "../../include/drex_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "drex_derivatives.cuh"
+#include "drex_diagnostics.cuh"
+#include "drex_integrate.cuh"
+
+namespace {
+
+thread_local char g_error[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define DREX_CUDA_CHECK(expr)                                                              \
+    do {                                                                                   \
+        cudaError_t e_ = (expr);                                                           \
+        if (e_ != cudaSuccess)                                                             \
+            return fail(DREX_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_));      \
+    } while (0)
+
+// core.get_crss (core.py:315-342)
+bool crss_for(int phase, int fabric, double *crss) {
+    static const double table[6][4] = {{1, 2, 3, INFINITY}, {3, 2, 1, INFINITY},
+                                       {3, 2, INFINITY, 1}, {1, 1, 3, INFINITY},
+                                       {3, 1, 2, INFINITY}, {INFINITY, INFINITY, INFINITY, 1}};
+    const bool ok = (phase == 0 && fabric >= 0 && fabric <= 4) || (phase == 1 && fabric == 5);
+    if (ok) memcpy(crss, table[fabric], 4 * sizeof(double));
+    return ok;
+}
+
+drex::FabricConsts make_fabric_consts(int fabric, const drex_params_t &p) {
+    drex::FabricConsts fc;
+    memset(&fc, 0, sizeof(fc));
+    const int phase = (fabric == 5) ? 1 : 0;
+    double crss[4];
+    crss_for(phase, fabric, crss);
+    for (int i = 0; i < 4; ++i) {
+        fc.crss[i] = crss[i];
+        fc.inv_crss[i] = 1.0 / crss[i];
+    }
+    for (int i = 0; i < 3; ++i)  // core.py:675-676
+        fc.rho_pref[i] = std::pow(1.0 / crss[i], p.deformation_exponent - p.stress_exponent);
+    fc.n_minus_1 = p.deformation_exponent - 1.0;
+    fc.p = p.stress_exponent;
+    fc.p_over_n = p.stress_exponent / p.deformation_exponent;
+    fc.lambda = p.nucleation_efficiency;
+    fc.phase = phase;
+    fc.default_exponents = (p.stress_exponent == 1.5 && p.deformation_exponent == 3.5) ? 1 : 0;
+    return fc;
+}
+
+drex::FabricTable make_fabric_table(const drex_params_t &p) {
+    drex::FabricTable t;
+    for (int fab = 0; fab < 6; ++fab) t.fab[fab] = make_fabric_consts(fab, p);
+    return t;
+}
+
+int validate_systems(int64_t S, const int32_t *regime, const int32_t *phase, const int32_t *fabric) {
+    for (int64_t s = 0; s < S; ++s) {
+        const int r = regime[s];
+        if (r == 2 || r == 3 || r == 5)  // core.py:406-413,437-438
+            return fail(DREX_E_UNSUPPORTED, "this deformation mechanism is not yet supported.");
+        if (r < 0 || r > 7)  // core.py:473-474
+            return fail(DREX_E_INVALID, "regime must be a valid `DeformationRegime`, not %d", r);
+        double crss[4];
+        if (!crss_for(phase[s], fabric[s], crss)) {
+            if (phase[s] == 0)
+                return fail(DREX_E_UNSUPPORTED, "unsupported olivine fabric: %d", fabric[s]);
+            if (phase[s] == 1)
+                return fail(DREX_E_UNSUPPORTED, "unsupported enstatite fabric: %d", fabric[s]);
+            return fail(DREX_E_UNSUPPORTED, "phase must be a valid `MineralPhase`, not %d", phase[s]);
+        }
+    }
+    return DREX_OK;
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int integrate_slots(int device) {
+    int sms = 0, per_sm = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, drex::integrate_kernel,
+                                                      drex::INT_BLOCK, 0) != cudaSuccess)
+        return -1;
+    if (per_sm < 1) per_sm = 1;
+    return sms * per_sm;
+}
+
+}  // namespace
+
+extern "C" {
+
+int drex_version(int *major, int *minor) {
+    if (major) *major = DREX_VERSION_MAJOR;
+    if (minor) *minor = DREX_VERSION_MINOR;
+    return DREX_OK;
+}
+
+int drex_last_error(char *buf, size_t n) {
+    if (!buf || n == 0) return DREX_E_INVALID;
+    strncpy(buf, g_error, n - 1);
+    buf[n - 1] = '\0';
+    return DREX_OK;
+}
+
+int drex_device_info(int device, int *sm_count, int *cc_major, int *cc_minor) {
+    cudaDeviceProp prop;
+    DREX_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    if (prop.major < 10)
+        return fail(DREX_E_NODEVICE, "device %d is sm_%d%d; this library is built for sm_100a",
+                    device, prop.major, prop.minor);
+    return DREX_OK;
+}
+
+int drex_pack_soa_f64(const double *aos, double *soa, int64_t S, int64_t N, void *stream) {
+    if (S <= 0 || N <= 0) return DREX_OK;
+    if (!aos || !soa) return fail(DREX_E_INVALID, "drex_pack_soa_f64: null pointer");
+    dim3 grid((unsigned)((N + 255) / 256), (unsigned)S);
+    drex::pack_soa_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(aos, soa, S, N);
+    DREX_CUDA_CHECK(cudaGetLastError());
+    return DREX_OK;
+}
+
+int drex_unpack_soa_f64(const double *soa, double *aos, int64_t S, int64_t N, void *stream) {
+    if (S <= 0 || N <= 0) return DREX_OK;
+    if (!aos || !soa) return fail(DREX_E_INVALID, "drex_unpack_soa_f64: null pointer");
+    dim3 grid((unsigned)((N + 255) / 256), (unsigned)S);
+    drex::unpack_soa_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(soa, aos, S, N);
+    DREX_CUDA_CHECK(cudaGetLastError());
+    return DREX_OK;
+}
+
+size_t drex_derivatives_workspace_bytes(int64_t S, int64_t N) {
+    return (size_t)(S > 0 ? S : 0) * (size_t)(N > 0 ? N : 0) * sizeof(double);
+}
+
+int drex_derivatives_f64(const double *o_soa, const double *f, const double *D, const double *L,
+                         const double *spin, const int32_t *regime, const int32_t *phase,
+                         const int32_t *fabric, const double *vol_frac,
+                         const int32_t *regime_host, const int32_t *phase_host,
+                         const int32_t *fabric_host, const drex_params_t *params, int64_t S,
+                         int64_t N, double *do_soa, double *df, void *workspace,
+                         size_t workspace_bytes, void *stream) {
+    if (S < 0 || N < 0) return fail(DREX_E_INVALID, "negative size");
+    if (!params || !regime_host || !phase_host || !fabric_host)
+        return fail(DREX_E_INVALID, "drex_derivatives_f64: null host argument");
+    int rc = validate_systems(S, regime_host, phase_host, fabric_host);
+    if (rc != DREX_OK) return rc;
+    if (S == 0 || N == 0) return DREX_OK;
+    if (!o_soa || !f || !D || !L || !spin || !regime || !phase || !fabric || !vol_frac || !do_soa || !df)
+        return fail(DREX_E_INVALID, "drex_derivatives_f64: null device pointer");
+    if (workspace_bytes < drex_derivatives_workspace_bytes(S, N) || !workspace)
+        return fail(DREX_E_WORKSPACE, "drex_derivatives_f64: workspace too small (%zu < %zu)",
+                    workspace_bytes, drex_derivatives_workspace_bytes(S, N));
+    drex::DerivArgs A;
+    A.o = o_soa; A.f = f; A.D = D; A.L = L; A.spin = spin; A.vol_frac = vol_frac;
+    A.regime = regime; A.phase = phase; A.fabric = fabric;
+    A.d_o = do_soa; A.d_f = df; A.energy = (double *)workspace;
+    A.gbm_mobility = params->gbm_mobility;
+    A.S = S; A.N = N;
+    const drex::FabricTable T = make_fabric_table(*params);
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((unsigned)((N + drex::DERIV_BLOCK - 1) / drex::DERIV_BLOCK), (unsigned)S);
+    drex::derivatives_grain_kernel<<<grid, drex::DERIV_BLOCK, 0, st>>>(A, T);
+    DREX_CUDA_CHECK(cudaGetLastError());
+    drex::derivatives_gbm_kernel<<<(unsigned)S, drex::GBM_BLOCK, 0, st>>>(A);
+    DREX_CUDA_CHECK(cudaGetLastError());
+    return DREX_OK;
+}
+
+int drex_grain_probe_f64(const double *o_aos, const double *D, const double *L, int phase,
+                         int fabric, const drex_params_t *params, int64_t G, double *invariants,
+                         double *slip_rates, double *deformation_rate, double *slip_rate_softest,
+                         double *strain_energy, double *orientation_change, void *stream) {
+    if (!params) return fail(DREX_E_INVALID, "drex_grain_probe_f64: null params");
+    double crss[4];
+    if (!crss_for(phase, fabric, crss))
+        return fail(DREX_E_UNSUPPORTED, "unsupported phase/fabric: %d/%d", phase, fabric);
+    if (G <= 0) return DREX_OK;
+    if (!o_aos || !D || !L) return fail(DREX_E_INVALID, "drex_grain_probe_f64: null pointer");
+    drex::ProbeArgs A;
+    A.o_aos = o_aos; A.D = D; A.L = L;
+    A.inv = invariants; A.rates = slip_rates; A.G = deformation_rate;
+    A.gamma0 = slip_rate_softest; A.energy = strain_energy; A.da = orientation_change;
+    A.n = G;
+    const drex::FabricConsts fc = make_fabric_consts(fabric, *params);
+    drex::grain_probe_kernel<<<(unsigned)((G + 127) / 128), 128, 0, (cudaStream_t)stream>>>(A, fc);
+    DREX_CUDA_CHECK(cudaGetLastError());
+    return DREX_OK;
+}
+
+int drex_grain_helper_f64(int op, const double *in0, const double *in1, const double *in2,
+                          const int32_t *idx, double s0, double s1, double s2, double s3,
+                          double *out, void *stream) {
+    if (op < 0 || op > 5) return fail(DREX_E_INVALID, "drex_grain_helper_f64: unknown op %d", op);
+    if (!in0 || !in1 || !out || (op == 4 && !in2) || (op == 1 && !idx))
+        return fail(DREX_E_INVALID, "drex_grain_helper_f64: null pointer");
+    drex::HelperArgs A;
+    A.op = op; A.in0 = in0; A.in1 = in1; A.in2 = in2; A.idx = idx;
+    A.s0 = s0; A.s1 = s1; A.s2 = s2; A.s3 = s3; A.out = out;
+    drex::grain_helper_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(A);
+    DREX_CUDA_CHECK(cudaGetLastError());
+    return DREX_OK;
+}
+
+size_t drex_integrate_workspace_bytes(int64_t S, int64_t N, int device) {
+    if (S <= 0 || N <= 0) return 256;
+    int slots = integrate_slots(device);
+    if (slots < 1) slots = 1;
+    if ((int64_t)slots > S) slots = (int)S;
+    const size_t slot_bytes = align_up((size_t)drex::SLOT_ARRAYS * (size_t)N * sizeof(double), 256);
+    return 256 + (size_t)slots * slot_bytes;
+}
+
+int drex_integrate_f64(int64_t S, int64_t P, int64_t N, const int32_t *sys_particle,
+                       const int32_t *sys_phase, const int32_t *sys_fabric,
+                       const int32_t *sys_regime, const double *sys_vol_frac,
+                       const int32_t *sys_phase_host, const int32_t *sys_fabric_host,
+                       const int32_t *sys_regime_host, double *F, const double *o_in,
+                       const double *f_in, double *o_out, double *f_out, const double *t0,
+                       const double *t1, int L_kind, int K, const double *L_nodes,
+                       const drex_params_t *params, const drex_tolerances_t *tol, double *h_io,
+                       int32_t *status, int32_t *n_rhs, int32_t *n_accept, int32_t *n_reject,
+                       void *workspace, size_t workspace_bytes, void *stream) {
+    if (S < 0 || P < 0 || N < 0) return fail(DREX_E_INVALID, "negative size");
+    if (!params || !tol || !sys_phase_host || !sys_fabric_host || !sys_regime_host)
+        return fail(DREX_E_INVALID, "drex_integrate_f64: null host argument");
+    int rc = validate_systems(S, sys_regime_host, sys_phase_host, sys_fabric_host);
+    if (rc != DREX_OK) return rc;
+    if (L_kind < 0 || L_kind > 3) return fail(DREX_E_INVALID, "unknown L_kind %d", L_kind);
+    if (K < 1 || (L_kind != DREX_L_CONSTANT && K < 2) || (L_kind == DREX_L_LINEAR && K != 2))
+        return fail(DREX_E_INVALID, "L_kind %d needs a different node count than K = %d", L_kind, K);
+    if (!(tol->rtol >= 0.0) || !(tol->atol_abs >= 0.0) || !(tol->atol_rel >= 0.0) ||
+        !(tol->rtol + tol->atol_abs + tol->atol_rel > 0.0))
+        return fail(DREX_E_INVALID, "tolerances must be non-negative and not all zero");
+    if (tol->method != 0) return fail(DREX_E_INVALID, "unknown integration method %d", tol->method);
+    if (S == 0 || N == 0) return DREX_OK;
+    if (!sys_particle || !sys_phase || !sys_fabric || !sys_regime || !sys_vol_frac || !F || !o_in ||
+        !f_in || !o_out || !f_out || !t0 || !t1 || !L_nodes || !status)
+        return fail(DREX_E_INVALID, "drex_integrate_f64: null device pointer");
+    int device = 0;
+    DREX_CUDA_CHECK(cudaGetDevice(&device));
+    int slots = integrate_slots(device);
+    if (slots < 1) return fail(DREX_E_CUDA, "could not query occupancy of the integrator kernel");
+    if ((int64_t)slots > S) slots = (int)S;
+    const size_t slot_bytes = align_up((size_t)drex::SLOT_ARRAYS * (size_t)N * sizeof(double), 256);
+    const size_t need = 256 + (size_t)slots * slot_bytes;
+    if (!workspace || workspace_bytes < need)
+        return fail(DREX_E_WORKSPACE, "drex_integrate_f64: workspace too small (%zu < %zu)",
+                    workspace_bytes, need);
+    cudaStream_t st = (cudaStream_t)stream;
+    drex::IntegrateArgs A;
+    A.S = S; A.P = P; A.N = N;
+    A.sys_particle = sys_particle; A.sys_phase = sys_phase; A.sys_fabric = sys_fabric;
+    A.sys_regime = sys_regime; A.sys_vol_frac = sys_vol_frac;
+    A.F = F; A.o_in = o_in; A.f_in = f_in; A.o_out = o_out; A.f_out = f_out;
+    A.t0 = t0; A.t1 = t1; A.L_kind = L_kind; A.K = K; A.L_nodes = L_nodes;
+    A.gbm_mobility = params->gbm_mobility;
+    A.gbs_threshold = params->gbs_threshold;
+    A.tol.rtol = tol->rtol; A.tol.atol_abs = tol->atol_abs; A.tol.atol_rel = tol->atol_rel;
+    A.tol.first_step_frac = tol->first_step_frac; A.tol.max_step_frac = tol->max_step_frac;
+    A.tol.max_steps = tol->max_steps > 0 ? tol->max_steps : 100000;
+    A.tol.method = tol->method;
+    A.h_io = h_io; A.status = status; A.n_rhs = n_rhs; A.n_accept = n_accept; A.n_reject = n_reject;
+    A.queue = (int *)workspace;
+    A.scratch = (double *)((char *)workspace + 256);
+    A.slot_doubles = (int64_t)(slot_bytes / sizeof(double));
+    DREX_CUDA_CHECK(cudaMemsetAsync(workspace, 0, 256, st));
+    const drex::FabricTable T = make_fabric_table(*params);
+    drex::integrate_kernel<<<(unsigned)slots, drex::INT_BLOCK, 0, st>>>(A, T);
+    DREX_CUDA_CHECK(cudaGetLastError());
+    return DREX_OK;
+}
+
+int drex_voigt_average_f64(const double *o_soa, const double *f, const double *stiffness,
+                           const double *phase_fraction, int64_t S, int64_t N, double *Cbar,
+                           int accumulate, void *stream) {
+    if (S < 0 || N < 0) return fail(DREX_E_INVALID, "negative size");
+    if (S == 0) return DREX_OK;
+    if (!o_soa || !f || !stiffness || !phase_fraction || !Cbar)
+        return fail(DREX_E_INVALID, "drex_voigt_average_f64: null pointer");
+    drex::voigt_average_kernel<<<(unsigned)S, drex::VOIGT_BLOCK, 0, (cudaStream_t)stream>>>(
+        o_soa, f, stiffness, phase_fraction, N, Cbar, accumulate);
+    DREX_CUDA_CHECK(cudaGetLastError());
+    return DREX_OK;
+}
+
+// ---- M-index ---------------------------------------------------------------------------
+
+static int max_misorientation(int a, int b) {  // stats.py:203-215
+    if ((a == 2 && b == 4) || (a == 3 && b == 6)) return 120;
+    if ((a == 4 && b == 8) || (a == 6 && b == 12)) return 90;
+    if ((a == 1 && b == 1) || (a == 2 && b == 2)) return 180;
+    return -1;
+}
+
+// stats.misorientations_random (stats.py:130-200), Grimmer (1979)
+static double misorientations_random(double low, double high, int Ms, int Ns, bool *ok) {
+    const double pi = 3.14159265358979323846, deg = pi / 180.0;
+    const double a = std::tan(deg * 90.0 / Ms);
+    const double b = 2.0 * std::atan(std::sqrt(1.0 + a * a)) / deg;
+    const double c = std::round(2.0 * std::atan(std::sqrt(1.0 + 2.0 * a * a)) / deg);
+    double counts[2] = {0.0, 0.0};
+    const double edges[2] = {low, high};
+    for (int i = 0; i < 2; ++i) {
+        const double e = edges[i], d = e * deg;
+        if (0 <= e && e <= 180.0 / Ms) {
+            counts[i] += (Ns / 180.0) * (1 - std::cos(d));
+        } else if (180.0 / Ms <= e && e <= 180.0 * Ms / Ns) {
+            counts[i] += (Ns / 180.0) * a * std::sin(d);
+        } else if (90 <= e && e <= b) {
+            counts[i] += (Ms / 90.0) * ((Ms + a) * std::sin(d) - Ms * (1 - std::cos(d)));
+        } else if (b <= e && e <= c) {
+            const double nu = std::pow(std::tan(deg * e / 2.0), 2.0);
+            counts[i] =
+                (Ms / 90.0) *
+                ((Ms + a) * std::sin(d) - Ms * (1 - std::cos(d)) +
+                 (Ms / 180.0) *
+                     ((1 - std::cos(d)) *
+                          (std::acos((1 - nu * std::cos(deg * 180.0 / Ms)) / (nu - 1)) / deg +
+                           2.0 * std::acos(a / (std::sqrt(nu - a * a) * std::sqrt(nu - 1))) / deg) -
+                      2.0 * std::sin(d) *
+                          (2.0 * std::acos(a / std::sqrt(nu - 1)) / deg +
+                           a * std::acos(1.0 / std::sqrt(nu - a * a)) / deg)));
+        } else {
+            *ok = false;  // the reference hits `assert False` here (stats.py:198)
+            return NAN;
+        }
+    }
+    return (counts[0] + counts[1]) / 2.0;
+}
+
+// symmetry operations as 4x4 matrices on scalar-last quaternions (geometry.py:121-182
+// applied as at stats.py:118-123 through utils.quat_product, utils.py:365-371, which has
+// no cross term: q -> [w_s v + w v_s, w_s w - v_s.v])
+static int build_symops(int a, int b, drex::SymOps *ops) {
+    int n = 0;
+    auto push_quat = [&](double x, double y, double z, double w) {
+        double *m = ops->m[n++];
+        memset(m, 0, 16 * sizeof(double));
+        const double v[3] = {x, y, z};
+        for (int i = 0; i < 3; ++i) {
+            m[4 * i + i] = w;
+            m[4 * i + 3] = v[i];
+            m[12 + i] = -v[i];
+        }
+        m[15] = w;
+    };
+    auto push_diag = [&](double d0, double d1, double d2, double d3) {
+        double *m = ops->m[n++];
+        memset(m, 0, 16 * sizeof(double));
+        m[0] = d0; m[5] = d1; m[10] = d2; m[15] = d3;
+    };
+    const double pi = 3.14159265358979323846;
+    static const double AX[3][3] = {{0, 0, 1}, {0, 1, 0}, {1, 0, 0}};  // z, y, x
+    auto push_rots = [&](double unit, int i0, int i1, int step) {
+        for (int k = 0; k < 3; ++k)
+            for (int i = i0; i <= i1; i += step) {
+                const double h = 0.5 * i * unit, s = std::sin(h), c = std::cos(h);
+                push_quat(AX[k][0] * s, AX[k][1] * s, AX[k][2] * s, c);
+            }
+    };
+    push_quat(0, 0, 0, 1);
+    if (a == 1 && b == 1) {
+    } else if (a == 2 && (b == 2 || b == 4)) {
+        push_rots(pi, 1, 1, 1);
+        push_diag(1, -1, -1, 1);
+        push_diag(1, -1, 1, -1);
+        push_diag(1, 1, -1, -1);
+    } else if (a == 3 && b == 6) {
+        push_rots(pi / 3, 1, 2, 1);
+    } else if (a == 4 && b == 8) {
+        push_rots(pi / 2, 1, 3, 1);
+    } else if (a == 6 && b == 12) {
+        push_rots(pi / 3, 1, 2, 1);
+        push_rots(pi / 6, 1, 5, 2);
+    } else {
+        return -1;
+    }
+    ops->n = n;
+    return n;
+}
+
+int drex_mindex_theory_host(int system_a, int system_b, double *theory_host) {
+    const int tmax = max_misorientation(system_a, system_b);
+    if (tmax < 0) return fail(DREX_E_UNSUPPORTED, "unsupported lattice system: (%d, %d)", system_a, system_b);
+    if (!theory_host) return fail(DREX_E_INVALID, "null pointer");
+    bool ok = true;
+    for (int i = 0; i < tmax; ++i)
+        theory_host[i] = misorientations_random((double)i, (double)(i + 1), system_a, system_b, &ok);
+    if (!ok)
+        return fail(DREX_E_UNSUPPORTED,
+                    "random-texture misorientation density undefined for lattice system (%d, %d)",
+                    system_a, system_b);
+    return tmax;
+}
+
+int drex_misorientations_random_host(double low, double high, int system_a, int system_b,
+                                     double *density_host) {
+    const int tmax = max_misorientation(system_a, system_b);
+    if (tmax < 0) return fail(DREX_E_UNSUPPORTED, "unsupported lattice system: (%d, %d)", system_a, system_b);
+    if (!density_host) return fail(DREX_E_INVALID, "null pointer");
+    if (!(0 <= low && low <= high && high <= tmax))
+        return fail(DREX_E_INVALID, "bounds must obey 0 <= low <= high <= %d", tmax);
+    bool ok = true;
+    *density_host = misorientations_random(low, high, system_a, system_b, &ok);
+    if (!ok)
+        return fail(DREX_E_UNSUPPORTED,
+                    "random-texture misorientation density undefined for lattice system (%d, %d)",
+                    system_a, system_b);
+    return DREX_OK;
+}
+
+static size_t mindex_ws_layout(int64_t S, int64_t N, int n_ops, int tmax, size_t *off_counts,
+                               size_t *off_theory) {
+    size_t quats = align_up((size_t)S * (size_t)N * (size_t)n_ops * sizeof(float4), 256);
+    *off_counts = quats;
+    size_t counts = align_up((size_t)S * (size_t)tmax * sizeof(unsigned long long), 256);
+    *off_theory = quats + counts;
+    return quats + counts + align_up((size_t)tmax * sizeof(double), 256);
+}
+
+size_t drex_mindex_workspace_bytes(int64_t S, int64_t N, int system_a, int system_b) {
+    drex::SymOps ops;
+    const int n_ops = build_symops(system_a, system_b, &ops);
+    const int tmax = max_misorientation(system_a, system_b);
+    if (n_ops < 0 || tmax < 0 || S <= 0 || N <= 0) return 256;
+    size_t a, b;
+    return mindex_ws_layout(S, N, n_ops, tmax, &a, &b);
+}
+
+int drex_mindex_f32(const double *o_soa, int64_t S, int64_t N, int system_a, int system_b,
+                    double *M, int64_t *counts, void *workspace, size_t workspace_bytes,
+                    void *stream) {
+    drex::SymOps ops;
+    const int n_ops = build_symops(system_a, system_b, &ops);
+    const int tmax = max_misorientation(system_a, system_b);
+    if (n_ops < 0 || tmax < 0)
+        return fail(DREX_E_UNSUPPORTED, "unsupported lattice system: (%d, %d)", system_a, system_b);
+    double theory_host[drex::MAX_THETA];
+    int rc = drex_mindex_theory_host(system_a, system_b, theory_host);
+    if (rc < 0) return rc;
+    if (S < 0 || N < 0) return fail(DREX_E_INVALID, "negative size");
+    if (S == 0) return DREX_OK;
+    if (!o_soa || !M) return fail(DREX_E_INVALID, "drex_mindex_f32: null pointer");
+    size_t off_counts, off_theory;
+    const size_t need = mindex_ws_layout(S, N, n_ops, tmax, &off_counts, &off_theory);
+    if (!workspace || workspace_bytes < need)
+        return fail(DREX_E_WORKSPACE, "drex_mindex_f32: workspace too small (%zu < %zu)",
+                    workspace_bytes, need);
+    cudaStream_t st = (cudaStream_t)stream;
+    float4 *quats = (float4 *)workspace;
+    unsigned long long *cnt = (unsigned long long *)((char *)workspace + off_counts);
+    double *theory = (double *)((char *)workspace + off_theory);
+    DREX_CUDA_CHECK(cudaMemsetAsync(cnt, 0, (size_t)S * tmax * sizeof(unsigned long long), st));
+    DREX_CUDA_CHECK(cudaMemcpyAsync(theory, theory_host, tmax * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (N > 0) {
+        dim3 gq((unsigned)((N + 127) / 128), (unsigned)S);
+        drex::mindex_quats_kernel<<<gq, 128, 0, st>>>(o_soa, N, quats, ops);
+        DREX_CUDA_CHECK(cudaGetLastError());
+        const int n_tiles = (int)((N + drex::MINDEX_TILE - 1) / drex::MINDEX_TILE);
+        dim3 gp((unsigned)((int64_t)n_tiles * (n_tiles + 1) / 2), (unsigned)S);
+        switch (n_ops) {
+        case 1: drex::mindex_pairs_kernel<1><<<gp, drex::MINDEX_TILE, 0, st>>>(quats, N, n_tiles, tmax, cnt); break;
+        case 7: drex::mindex_pairs_kernel<7><<<gp, drex::MINDEX_TILE, 0, st>>>(quats, N, n_tiles, tmax, cnt); break;
+        case 10: drex::mindex_pairs_kernel<10><<<gp, drex::MINDEX_TILE, 0, st>>>(quats, N, n_tiles, tmax, cnt); break;
+        case 16: drex::mindex_pairs_kernel<16><<<gp, drex::MINDEX_TILE, 0, st>>>(quats, N, n_tiles, tmax, cnt); break;
+        default: return fail(DREX_E_INVALID, "unexpected symmetry operator count %d", n_ops);
+        }
+        DREX_CUDA_CHECK(cudaGetLastError());
+    }
+    drex::mindex_finalize_kernel<<<(unsigned)S, 32, 0, st>>>(cnt, theory, tmax, M);
+    DREX_CUDA_CHECK(cudaGetLastError());
+    if (counts)
+        DREX_CUDA_CHECK(cudaMemcpyAsync(counts, cnt, (size_t)S * tmax * sizeof(unsigned long long),
+                                        cudaMemcpyDeviceToDevice, st));
+    return DREX_OK;
+}
+
+// ---- FP64 peak probe -----------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters) {
+    double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
+    double a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999999, c = 1e-12;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+int drex_fp64_peak_probe(int device, double *flops_host) {
+    if (!flops_host) return fail(DREX_E_INVALID, "null pointer");
+    DREX_CUDA_CHECK(cudaSetDevice(device));
+    int sms = 0;
+    DREX_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int blocks = sms * 8, threads = 256, iters = 1 << 16;
+    double *buf = nullptr;
+    DREX_CUDA_CHECK(cudaMalloc(&buf, (size_t)blocks * threads * sizeof(double)));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0);
+        fp64_peak_kernel<<<blocks, threads>>>(buf, iters);
+        cudaEventRecord(e1);
+        cudaError_t e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) {
+            cudaFree(buf);
+            return fail(DREX_E_CUDA, "fp64 probe failed: %s", cudaGetErrorString(e));
+        }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3);
+        if (rep > 0 && flops > best) best = flops;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    *flops_host = best;
+    return DREX_OK;
+}
+
+}  // extern "C"

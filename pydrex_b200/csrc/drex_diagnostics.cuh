@@ -1,0 +1,269 @@
+// drex_diagnostics.cuh -- post-step texture reductions on device (sm_100a).
+//
+//  voigt_average_kernel   minerals.voigt_averages (src/pydrex/minerals.py:688-740):
+//      per grain the rotated stiffness is P S P^T with P the 6x6 matrix of products of
+//      direction cosines (equivalent to tensors.rotate + elastic_tensor_to_voigt,
+//      tensors.py:187-273, for tensors with the minor symmetries voigt_to_elastic_tensor
+//      builds), ~400 FMA instead of the reference's 3^8-term loop; one CTA per system,
+//      21 accumulators per thread, fixed-order block reduction.
+//  mindex_*               diagnostics.misorientation_index (diagnostics.py:332-367) with
+//      stats.misorientation_hist (stats.py:83-127) and geometry.misorientation_angles
+//      (geometry.py:74-118): all pairs x all symmetry-operator pairs, tiled on chip; the
+//      [C(N,2), 7, 4] float32 pair arrays of the reference (7.7 GB at N = 5000) never
+//      exist.  Arithmetic mirrors the reference: float32 transformed quaternions, float32
+//      products and sums without contraction, min over operator pairs == acos of the
+//      largest |dot| (acos is monotone).
+#pragma once
+#include "drex_common.cuh"
+
+namespace drex {
+
+// ------------------------------------------------------------------ Voigt average
+
+constexpr int VOIGT_BLOCK = 256;
+
+// canonical (p, q) of Voigt index I: inverse of tensors.py:174-175
+__host__ __device__ constexpr int voigt_p(int I) { return I < 3 ? I : (I == 3 ? 1 : 0); }
+__host__ __device__ constexpr int voigt_q(int I) { return I < 3 ? I : (I == 5 ? 1 : 2); }
+
+__global__ void __launch_bounds__(VOIGT_BLOCK)
+voigt_average_kernel(const double *__restrict__ o_soa, const double *__restrict__ f,
+                     const double *__restrict__ stiffness, const double *__restrict__ phase_fraction,
+                     int64_t N, double *__restrict__ Cbar, int accumulate) {
+    __shared__ double Ssym[36];
+    __shared__ double red[21][VOIGT_BLOCK / 32];
+    const int64_t s = blockIdx.x;
+    const int tid = threadIdx.x;
+    if (tid < 36) {
+        const int i = tid / 6, j = tid % 6;
+        // (M + M^T)/2 commutes with the congruence P . P^T (tensors.py:203)
+        Ssym[tid] = 0.5 * (stiffness[s * 36 + 6 * i + j] + stiffness[s * 36 + 6 * j + i]);
+    }
+    __syncthreads();
+    double acc[21];
+#pragma unroll
+    for (int i = 0; i < 21; ++i) acc[i] = 0.0;
+    const double *o = o_soa + s * 9 * N;
+    for (int64_t g = tid; g < N; g += VOIGT_BLOCK) {
+        double a[9];
+#pragma unroll
+        for (int c = 0; c < 9; ++c) a[c] = o[c * N + g];
+        const double w = f[s * N + g];
+        // rotation R = a^T (minerals.py:735): R[i][k] = a[k][i]
+        double Pm[6][6];
+#pragma unroll
+        for (int I = 0; I < 6; ++I) {
+            const int p = voigt_p(I), q = voigt_q(I);
+#pragma unroll
+            for (int A = 0; A < 6; ++A) {
+                const int k = voigt_p(A), l = voigt_q(A);
+                const double rpk = a[3 * k + p], rql = a[3 * l + q];
+                Pm[I][A] = (A < 3) ? rpk * rql : rpk * rql + a[3 * l + p] * a[3 * k + q];
+            }
+        }
+        double Q[6][6];
+#pragma unroll
+        for (int I = 0; I < 6; ++I)
+#pragma unroll
+            for (int B = 0; B < 6; ++B) {
+                double t = 0.0;
+#pragma unroll
+                for (int A = 0; A < 6; ++A) t += Pm[I][A] * Ssym[6 * A + B];
+                Q[I][B] = t;
+            }
+        int idx = 0;
+#pragma unroll
+        for (int I = 0; I < 6; ++I)
+#pragma unroll
+            for (int J = I; J < 6; ++J) {
+                double t = 0.0;
+#pragma unroll
+                for (int B = 0; B < 6; ++B) t += Q[I][B] * Pm[J][B];
+                acc[idx++] += w * t;
+            }
+    }
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int i = 0; i < 21; ++i) {
+        const double v = warp_sum(acc[i]);
+        if (lane == 0) red[i][warp] = v;
+    }
+    __syncthreads();
+    if (tid < 21) {
+        double t = 0.0;
+        for (int w = 0; w < VOIGT_BLOCK / 32; ++w) t += red[tid][w];
+        t *= phase_fraction[s];
+        // unpack upper-triangular index
+        int I = 0, rem = tid;
+        while (rem >= 6 - I) {
+            rem -= 6 - I;
+            ++I;
+        }
+        const int J = I + rem;
+        double *out = Cbar + s * 36;
+        if (accumulate) {
+            out[6 * I + J] += t;
+            if (I != J) out[6 * J + I] += t;
+        } else {
+            out[6 * I + J] = t;
+            if (I != J) out[6 * J + I] = t;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ M-index
+
+constexpr int MAX_SYMOPS = 16;
+constexpr int MINDEX_TILE = 128;  // grains per tile side == threads per CTA
+constexpr int MAX_THETA = 180;
+
+struct SymOps {
+    double m[MAX_SYMOPS][16];  // 4x4 matrices acting on scalar-last quaternions
+    int n;
+};
+
+// scipy Rotation.from_matrix(...).as_quat() (third-party; scipy 1.18.1
+// spatial/transform/_rotation_xp.py:51-157): nearest rotation for non-orthogonal input,
+// then the largest-of-diagonal-and-trace branch and normalisation.
+__device__ inline void matrix_to_quat(const double *M_in, double *q) {
+    double X[9];
+    for (int i = 0; i < 9; ++i) X[i] = M_in[i];
+    for (int it = 0; it < 40; ++it) {  // X <- (X + X^-T)/2 converges to the polar factor
+        const double c0[3] = {X[4] * X[8] - X[5] * X[7], X[5] * X[6] - X[3] * X[8], X[3] * X[7] - X[4] * X[6]};
+        const double c1[3] = {X[7] * X[2] - X[8] * X[1], X[8] * X[0] - X[6] * X[2], X[6] * X[1] - X[7] * X[0]};
+        const double c2[3] = {X[1] * X[5] - X[2] * X[4], X[2] * X[3] - X[0] * X[5], X[0] * X[4] - X[1] * X[3]};
+        const double det = X[0] * c0[0] + X[1] * c0[1] + X[2] * c0[2];
+        const double inv_t[9] = {c0[0] / det, c0[1] / det, c0[2] / det, c1[0] / det, c1[1] / det,
+                                 c1[2] / det, c2[0] / det, c2[1] / det, c2[2] / det};
+        double delta = 0.0;
+        for (int i = 0; i < 9; ++i) {
+            const double nx = 0.5 * (X[i] + inv_t[i]);
+            delta = fmax(delta, fabs(nx - X[i]));
+            X[i] = nx;
+        }
+        if (delta < 1e-16) break;
+    }
+    const double tr = X[0] + X[4] + X[8];
+    int choice = 0;
+    double best = X[0];
+    if (X[4] > best) { best = X[4]; choice = 1; }
+    if (X[8] > best) { best = X[8]; choice = 2; }
+    if (tr > best) { choice = 3; }
+    if (choice == 3) {
+        q[0] = X[7] - X[5];
+        q[1] = X[2] - X[6];
+        q[2] = X[3] - X[1];
+        q[3] = 1.0 + tr;
+    } else {
+        const int i = choice, j = (i + 1) % 3, k = (j + 1) % 3;
+        q[i] = 1.0 - tr + 2.0 * X[4 * i];
+        q[j] = X[3 * j + i] + X[3 * i + j];
+        q[k] = X[3 * k + i] + X[3 * i + k];
+        q[3] = X[3 * k + j] - X[3 * j + k];
+    }
+    const double nrm = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    for (int i = 0; i < 4; ++i) q[i] /= nrm;
+}
+
+// K1: transformed float32 quaternions, layout [S][N][n_ops] float4
+__global__ void __launch_bounds__(128)
+mindex_quats_kernel(const double *__restrict__ o_soa, int64_t N, float4 *__restrict__ quats,
+                    const __grid_constant__ SymOps ops) {
+    const int64_t s = blockIdx.y;
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= N) return;
+    double a[9], q[4];
+    for (int c = 0; c < 9; ++c) a[c] = o_soa[s * 9 * N + c * N + g];
+    matrix_to_quat(a, q);
+    float4 *dst = quats + (s * N + g) * ops.n;
+    for (int k = 0; k < ops.n; ++k) {
+        double r[4];
+        for (int i = 0; i < 4; ++i) {
+            double t = 0.0;
+            for (int j = 0; j < 4; ++j) t += ops.m[k][4 * i + j] * q[j];  // stats.py:119-123
+            r[i] = t;
+        }
+        dst[k] = make_float4((float)r[0], (float)r[1], (float)r[2], (float)r[3]);  // stats.py:105-112
+    }
+}
+
+// K2: pair tiles.  grid.x enumerates tile pairs (ti <= tj), grid.y = system.
+template <int NOPS>
+__global__ void __launch_bounds__(MINDEX_TILE)
+mindex_pairs_kernel(const float4 *__restrict__ quats, int64_t N, int n_tiles, int theta_max,
+                    unsigned long long *__restrict__ counts) {
+    __shared__ float4 qj[MINDEX_TILE * NOPS];
+    __shared__ unsigned int hist[MAX_THETA];
+    const int64_t s = blockIdx.y;
+    // decode (ti, tj), ti <= tj, from the linear upper-triangular index
+    int ti = 0, rem = blockIdx.x;
+    while (rem >= n_tiles - ti) {
+        rem -= n_tiles - ti;
+        ++ti;
+    }
+    const int tj = ti + rem;
+    const int tid = threadIdx.x;
+    for (int b = tid; b < theta_max; b += MINDEX_TILE) hist[b] = 0u;
+    const float4 *base = quats + s * N * NOPS;
+    const int64_t j0 = (int64_t)tj * MINDEX_TILE;
+    const int nj = (int)min((int64_t)MINDEX_TILE, N - j0);
+    for (int e = tid; e < nj * NOPS; e += MINDEX_TILE) qj[e] = base[j0 * NOPS + e];
+    const int64_t i = (int64_t)ti * MINDEX_TILE + tid;
+    float4 qi[NOPS];
+    if (i < N) {
+#pragma unroll
+        for (int k = 0; k < NOPS; ++k) qi[k] = base[i * NOPS + k];
+    }
+    __syncthreads();
+    if (i < N) {
+        const float rad2deg_f = 57.29577951308232f;
+        int jstart = (ti == tj) ? tid + 1 : 0;  // pairs (i, j) with i < j only (stats.py:113-115)
+        for (int jj = jstart; jj < nj; ++jj) {
+            float best = 0.0f;  // max |dot| over operator pairs == min angle (geometry.py:102-118)
+#pragma unroll
+            for (int a = 0; a < NOPS; ++a) {
+#pragma unroll
+                for (int b = 0; b < NOPS; ++b) {
+                    const float4 v = qj[jj * NOPS + b];
+                    // float32 products and left-to-right float32 sum, no contraction
+                    float d = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(qi[a].x, v.x), __fmul_rn(qi[a].y, v.y)),
+                                                  __fmul_rn(qi[a].z, v.z)),
+                                        __fmul_rn(qi[a].w, v.w));
+                    d = fminf(1.0f, fmaxf(-1.0f, d));
+                    best = fmaxf(best, fabsf(d));
+                }
+            }
+            // correctly rounded float32 acos, float32 rad2deg, then 2 * (float64)
+            const float half_deg = __fmul_rn((float)acos((double)best), rad2deg_f);
+            const double ang = 2.0 * (double)half_deg;
+            if (ang >= 0.0 && ang <= (double)theta_max) {
+                int bin = (int)ang;
+                if (bin >= theta_max) bin = theta_max - 1;
+                atomicAdd(&hist[bin], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int b = tid; b < theta_max; b += MINDEX_TILE)
+        if (hist[b]) atomicAdd(&counts[s * theta_max + b], (unsigned long long)hist[b]);
+}
+
+// K3: M = theta_max / (2 nbins) * sum_b |theory_b - density_b| (diagnostics.py:365-367)
+__global__ void __launch_bounds__(32)
+mindex_finalize_kernel(const unsigned long long *__restrict__ counts, const double *__restrict__ theory,
+                       int theta_max, double *__restrict__ M) {
+    const int64_t s = blockIdx.x;
+    const int lane = threadIdx.x;
+    double total = 0.0;
+    for (int b = lane; b < theta_max; b += 32) total += (double)counts[s * theta_max + b];
+    total = warp_sum(total);
+    double acc = 0.0;
+    for (int b = lane; b < theta_max; b += 32) {
+        const double density = (double)counts[s * theta_max + b] / total;  // bin width 1 degree
+        acc += fabs(theory[b] - density);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) M[s] = ((double)theta_max / (2.0 * (double)theta_max)) * acc;
+}
+
+}  // namespace drex

@@ -1,0 +1,237 @@
+"""Batched pathline-particle ensembles: the fast path the B200 kernels are built for.
+
+The reference parallelises over particles with one OS process each
+(`Pool.imap(run, final_locations)`, examples/standalone/cornerflow_simple.py:129-151, or
+Ray on a PBS cluster).  Here a whole cloud of particles, each carrying one grain ensemble
+per mineral phase, stays resident in HBM in SoA layout and advances with ONE launch of
+the persistent integrator per outer time step.  Particles are independent, so multi-GPU
+runs shard particle index ranges over ranks with no data-path collective; only results
+are gathered at the end (`gather_to_rank0`).
+
+A "system" is one (particle, phase) grain ensemble; system index s = particle * n_phases +
+phase_slot.
+"""
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from . import core as _core
+from . import exceptions as _err
+from .minerals import StiffnessTensors
+
+
+def shard_range(n_particles, rank, world_size):
+    """Contiguous particle range [lo, hi) owned by `rank` (sizes differ by at most one)."""
+    base, extra = divmod(int(n_particles), int(world_size))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def gather_to_rank0(local, n_particles, group=None):
+    """Gather per-particle result rows (a tensor [P_local, ...]) onto rank 0 in particle
+    order.  The only inter-rank traffic of a run; uses the default process group (NCCL for
+    CUDA tensors, gloo for CPU tensors).  Returns the full tensor on rank 0, None elsewhere.
+    """
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sizes = [shard_range(n_particles, r, world) for r in range(world)]
+    max_rows = max(hi - lo for lo, hi in sizes)
+    padded = torch.zeros((max_rows, *local.shape[1:]), dtype=local.dtype, device=local.device)
+    padded[: local.shape[0]] = local
+    bufs = [torch.empty_like(padded) for _ in range(world)] if rank == 0 else None
+    dist.gather(padded, bufs, dst=0, group=group)
+    if rank != 0:
+        return None
+    return torch.cat([b[: hi - lo] for b, (lo, hi) in zip(bufs, sizes)], dim=0)
+
+
+def random_orientations(n_systems, n_grains, seed, device):
+    """Haar-random rotation matrices [S, N, 3, 3] from normalised Gaussian quaternions,
+    generated on `device` (what scipy's Rotation.random does, minerals.py:261-263, but with
+    torch's generator: seeds are NOT interchangeable with the reference's)."""
+    import torch
+
+    gen = torch.Generator(device=device)
+    gen.manual_seed(int(seed))
+    q = torch.randn((n_systems, n_grains, 4), dtype=torch.float64, device=device, generator=gen)
+    q = q / q.norm(dim=-1, keepdim=True)
+    x, y, z, w = q.unbind(-1)
+    R = torch.stack([
+        1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+        2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+        2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], dim=-1)
+    return R.reshape(n_systems, n_grains, 3, 3)
+
+
+class ParticleEnsemble:
+    """P particles x len(phases) mineral phases x N grains, resident on one GPU.
+
+    - `phases`, `fabrics`, `regimes` — one entry per phase slot (MineralPhase / MineralFabric
+      / DeformationRegime ordinals)
+    - `params` — dict with the keys of `DefaultParams.as_dict()`; `phase_fractions` are
+      matched to `phases` through `phase_assemblage` exactly as minerals.py:412-415 does
+    - `orientations` — optional initial orientations [P, n_phases, N, 3, 3] (numpy or
+      torch); default Haar-random from `seed`
+    - `fractions` — optional initial fractions [P, n_phases, N]; default 1/N
+    """
+
+    def __init__(self, n_particles, n_grains, params, phases=(0, 1), fabrics=(0, 5),
+                 regimes=(4, 4), orientations=None, fractions=None, seed=8816, device=None):
+        torch = _lib.require_cuda()
+        self._torch = torch
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None \
+            else torch.device(device)
+        self.P, self.N, self.n_phases = int(n_particles), int(n_grains), len(phases)
+        self.S = self.P * self.n_phases
+        self.params = dict(params)
+        self.phases = [int(p) for p in phases]
+        self.fabrics = [int(f) for f in fabrics]
+        for ph, fab in zip(self.phases, self.fabrics):
+            _core.get_crss(ph, fab)  # ValueError for unsupported combinations
+        assemblage = list(self.params["phase_assemblage"])
+        vol = [float(self.params["phase_fractions"][assemblage.index(ph)]) for ph in self.phases]
+        f64, i32, dev = torch.float64, torch.int32, self.device
+        P, K, N, S = self.P, self.n_phases, self.N, self.S
+        meta = np.empty((4, S), dtype=np.int32)
+        meta[0] = np.repeat(np.arange(P, dtype=np.int32), K)
+        meta[1] = np.tile(np.asarray(self.phases, dtype=np.int32), P)
+        meta[2] = np.tile(np.asarray(self.fabrics, dtype=np.int32), P)
+        meta[3] = np.tile(np.asarray([int(r) for r in regimes], dtype=np.int32), P)
+        self.meta_host = meta
+        self.meta = torch.as_tensor(meta).to(dev)
+        self.vol_frac = torch.tensor(vol, dtype=f64, device=dev).repeat(P)
+        self.F = torch.eye(3, dtype=f64, device=dev).reshape(1, 9).repeat(S, 1).contiguous()
+        self.o = torch.empty((S, 9, N), dtype=f64, device=dev)  # SoA
+        if orientations is None:
+            o_aos = random_orientations(S, N, seed, dev)
+        else:
+            o_aos = torch.as_tensor(orientations).to(device=dev, dtype=f64)
+        self._pack(o_aos.reshape(S, N, 9).contiguous(), self.o)
+        if fractions is None:
+            self.f = torch.full((S, N), 1.0 / N, dtype=f64, device=dev)
+        else:
+            self.f = torch.as_tensor(fractions).to(device=dev, dtype=f64).reshape(S, N).contiguous()
+        self.h = torch.zeros(S, dtype=f64, device=dev)
+        self.stats = torch.zeros((4, S), dtype=i32, device=dev)  # status, n_rhs, n_accept, n_reject
+        self._ws = None
+        self.total_rhs = 0
+        self.total_steps = 0
+
+    # -- layout --------------------------------------------------------------------------
+    def _pack(self, aos, soa):
+        lib, torch = _lib.load(), self._torch
+        S, N = soa.shape[0], soa.shape[2]
+        _lib.check(lib.drex_pack_soa_f64(_lib.ptr(aos), _lib.ptr(soa), S, N, _lib.stream_ptr(torch)))
+
+    def orientations(self):
+        """Current orientations as [P, n_phases, N, 3, 3] (device tensor, AoS like the reference)."""
+        lib, torch = _lib.load(), self._torch
+        aos = torch.empty((self.S, self.N, 9), dtype=torch.float64, device=self.device)
+        _lib.check(lib.drex_unpack_soa_f64(_lib.ptr(self.o), _lib.ptr(aos), self.S, self.N,
+                                           _lib.stream_ptr(torch)))
+        return aos.reshape(self.P, self.n_phases, self.N, 3, 3)
+
+    def fractions(self):
+        return self.f.reshape(self.P, self.n_phases, self.N)
+
+    def deformation_gradients(self):
+        """F per particle (the last phase's, as update_all returns it, minerals.py:684)."""
+        return self.F.reshape(self.P, self.n_phases, 3, 3)[:, -1]
+
+    # -- integration -----------------------------------------------------------------------
+    def tolerances(self, rtol=1e-6, atol_abs=1e-4, atol_rel=1e-6, first_step_frac=0.0,
+                   max_step_frac=0.0, max_steps=100000):
+        tol = _lib.DrexTolerances()
+        tol.rtol, tol.atol_abs, tol.atol_rel = rtol, atol_abs, atol_rel
+        tol.first_step_frac, tol.max_step_frac = first_step_frac, max_step_frac
+        tol.max_steps, tol.method = max_steps, 0
+        return tol
+
+    def update(self, t0, t1, L_nodes, kind=_lib.L_CONSTANT, tol=None, check=True):
+        """Advance every particle from t0[p] to t1[p] (device tensors [P] or floats).
+
+        `L_nodes` is a device tensor [P, K, 3, 3] (or [P, 3, 3] for a constant L) holding the
+        velocity-gradient table of each particle for this interval; `kind` one of
+        `_lib.L_CONSTANT / L_LINEAR / L_CHEBYSHEV / L_PIECEWISE`.
+        One kernel launch; returns the per-system status tensor (raises `IterationError`
+        on failure when `check`, which synchronises).
+        """
+        lib, torch = _lib.load(), self._torch
+        dev, f64 = self.device, torch.float64
+        if not torch.is_tensor(t0):
+            t0 = torch.full((self.P,), float(t0), dtype=f64, device=dev)
+        if not torch.is_tensor(t1):
+            t1 = torch.full((self.P,), float(t1), dtype=f64, device=dev)
+        L_nodes = L_nodes.to(device=dev, dtype=f64)
+        if L_nodes.dim() == 3:
+            L_nodes = L_nodes[:, None]
+        K = int(L_nodes.shape[1])
+        L_nodes = L_nodes.reshape(self.P, K, 9).contiguous()
+        if tol is None:
+            tol = self.tolerances()
+        p = self.params
+        prm = _lib.DrexParams(float(p["stress_exponent"]), float(p["deformation_exponent"]),
+                              float(p["nucleation_efficiency"]), float(p["gbm_mobility"]),
+                              float(p["gbs_threshold"]))
+        if self._ws is None:
+            nbytes = lib.drex_integrate_workspace_bytes(self.S, self.N, dev.index or 0)
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        Pp = _lib.ptr
+        m, mh = self.meta, self.meta_host
+        _lib.check(lib.drex_integrate_f64(
+            self.S, self.P, self.N, Pp(m[0]), Pp(m[1]), Pp(m[2]), Pp(m[3]), Pp(self.vol_frac),
+            Pp(mh[1]), Pp(mh[2]), Pp(mh[3]), Pp(self.F), Pp(self.o), Pp(self.f), Pp(self.o),
+            Pp(self.f), Pp(t0), Pp(t1), int(kind), K, Pp(L_nodes), ctypes.byref(prm),
+            ctypes.byref(tol), Pp(self.h), Pp(self.stats[0]), Pp(self.stats[1]),
+            Pp(self.stats[2]), Pp(self.stats[3]), Pp(self._ws), self._ws.numel(),
+            _lib.stream_ptr(torch)))
+        if check:
+            stats = self.stats.cpu().numpy()
+            bad = np.nonzero(stats[0])[0]
+            if bad.size:
+                s = int(bad[0])
+                raise _err.IterationError(
+                    f"{bad.size} system(s) failed; first: particle {s // self.n_phases}, phase slot "
+                    f"{s % self.n_phases}: {_lib.STATUS_MESSAGES.get(int(stats[0, s]))}")
+            self.total_rhs += int(stats[1].sum())
+            self.total_steps += int(stats[2].sum())
+        return self.stats[0]
+
+    # -- diagnostics -----------------------------------------------------------------------
+    def voigt_averages(self, elastic_tensors=None):
+        """Voigt-averaged stiffness per particle, [P, 6, 6] (minerals.voigt_averages for the
+        current snapshot of every particle)."""
+        lib, torch = _lib.load(), self._torch
+        dev, f64 = self.device, torch.float64
+        tensors = list(elastic_tensors if elastic_tensors is not None else StiffnessTensors())
+        assemblage = list(self.params["phase_assemblage"])
+        stiff = np.stack([np.asarray(tensors[assemblage.index(ph)], dtype=np.float64).reshape(36)
+                          for ph in self.phases])
+        stiff_d = torch.as_tensor(np.tile(stiff, (self.P, 1))).to(dev)
+        Cbar = torch.empty((self.S, 36), dtype=f64, device=dev)
+        _lib.check(lib.drex_voigt_average_f64(_lib.ptr(self.o), _lib.ptr(self.f), _lib.ptr(stiff_d),
+                                              _lib.ptr(self.vol_frac), self.S, self.N,
+                                              _lib.ptr(Cbar), 0, _lib.stream_ptr(torch)))
+        return Cbar.reshape(self.P, self.n_phases, 6, 6).sum(dim=1)
+
+    def misorientation_indices(self, system, phase_slot=0, batch=256):
+        """M-index of every particle's texture for one phase slot, [P] (device tensor)."""
+        lib, torch = _lib.load(), self._torch
+        a, b = system.value
+        o = self.o.reshape(self.P, self.n_phases, 9, self.N)[:, phase_slot]
+        out = torch.empty(self.P, dtype=torch.float64, device=self.device)
+        for lo in range(0, self.P, batch):
+            chunk = o[lo:lo + batch].contiguous()
+            T = chunk.shape[0]
+            nbytes = lib.drex_mindex_workspace_bytes(T, self.N, a, b)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            rc = lib.drex_mindex_f32(_lib.ptr(chunk), T, self.N, a, b, _lib.ptr(out[lo:lo + T]),
+                                     None, _lib.ptr(ws), nbytes, _lib.stream_ptr(torch))
+            _lib.check(rc)
+        return out

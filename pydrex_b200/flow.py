@@ -1,0 +1,84 @@
+"""Host-side tabulation of the velocity gradient L(t) along a pathline.
+
+The reference evaluates two Python callables inside every right-hand side,
+`get_velocity_gradient(t, get_position(t))` (minerals.py:391-392).  Python cannot run on
+the device, so each outer interval [t0, t1] is tabulated once on the host and the kernel
+interpolates (include/drex_b200.h DREX_L_*):
+
+  constant   all samples equal                        -> 1 node
+  linear     Fluidity-style linear-in-time L          -> 2 nodes
+  Chebyshev  K = 2^m + 1 Chebyshev-Lobatto nodes, barycentric interpolation; K doubles
+             (the node sets nest, so no sample is wasted) until the interpolant
+             reproduces the new samples to `rtol`.
+"""
+
+import numpy as np
+
+from . import _lib
+
+
+def chebyshev_lobatto(K):
+    """Nodes on [0, 1], ascending: x_j = (1 - cos(pi j / (K - 1))) / 2."""
+    if K == 1:
+        return np.zeros(1)
+    return 0.5 * (1.0 - np.cos(np.pi * np.arange(K) / (K - 1)))
+
+
+def barycentric_interpolate(values, x):
+    """Evaluate the Chebyshev-Lobatto interpolant of `values[K, ...]` at x in [0, 1].
+
+    Host mirror of `eval_L` in csrc/drex_integrate.cuh, used to decide K.
+    """
+    values = np.asarray(values, dtype=np.float64)
+    K = values.shape[0]
+    nodes = chebyshev_lobatto(K)
+    d = x - nodes
+    hit = np.abs(d) < 1e-15
+    if hit.any():
+        return values[int(np.argmax(hit))]
+    w = np.where(np.arange(K) % 2 == 1, -1.0, 1.0)
+    w[0] *= 0.5
+    w[-1] *= 0.5
+    w = w / d
+    return np.tensordot(w, values, axes=(0, 0)) / w.sum()
+
+
+def tabulate_velocity_gradient(get_velocity_gradient, get_position, t0, t1, rtol=1e-10,
+                               max_nodes=129):
+    """Sample L(t) = get_velocity_gradient(t, get_position(t)) on [t0, t1].
+
+    Returns `(kind, nodes)` with nodes of shape [K, 3, 3].
+    """
+
+    def L_at(x):
+        t = t0 + (t1 - t0) * x
+        return np.asarray(get_velocity_gradient(t, get_position(t)), dtype=np.float64).reshape(3, 3)
+
+    K = 5
+    xs = chebyshev_lobatto(K)
+    vals = {float(x): L_at(x) for x in xs}
+    samples = np.stack([vals[float(x)] for x in xs])
+    scale = np.abs(samples).max()
+    if not np.isfinite(scale):
+        raise ValueError("velocity gradient is not finite on the requested interval")
+    tol = rtol * scale
+    if np.abs(samples - samples[0]).max() <= tol:
+        return _lib.L_CONSTANT, samples[:1].copy()
+    lin = samples[0][None] + xs[:, None, None] * (samples[-1] - samples[0])[None]
+    if np.abs(samples - lin).max() <= tol:
+        return _lib.L_LINEAR, np.stack([samples[0], samples[-1]])
+    while True:
+        K2 = 2 * (K - 1) + 1
+        xs2 = chebyshev_lobatto(K2)
+        err = 0.0
+        for j, x in enumerate(xs2):
+            if j % 2 == 0:  # node of the coarser set
+                vals.setdefault(float(x), samples[j // 2])
+                continue
+            v = L_at(x)
+            vals[float(x)] = v
+            err = max(err, np.abs(v - barycentric_interpolate(samples, x)).max())
+        samples2 = np.stack([vals[float(x)] for x in xs2])
+        if err <= tol or K2 >= max_nodes:
+            return _lib.L_CHEBYSHEV, samples2
+        K, samples = K2, samples2
