@@ -1,0 +1,528 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the CPO-integration hot path on B200 (and the CPU baseline).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU arm (oracle port)
+
+Workload (BASELINE.json configs[3]'s per-GPU share, weak scaling): each GPU holds
+`--particles` pathline particles (default 1250 = 10^4 / 8), each carrying an olivine A-type
+and an enstatite ensemble of `--grains` (5000) grains, GBM and GBS enabled (M* = 125,
+chi = 0.3), advanced through outer CPO intervals along synthetic pathlines:
+  simple_shear  every particle sees a randomly oriented simple shear with its own strain
+                rate, strain increment 0.02-0.08 per outer step;
+  corner_flow   particles ride 2-D corner-flow pathlines (analytic Batchelor solution,
+                plate speed 2 cm/yr, exit depths spread over the domain); L(t) is
+                tabulated per outer interval at 9 Chebyshev nodes.
+
+A "step" is one outer CPO interval of every particle: ONE launch of the persistent
+integrator kernel.  metric "grain-steps/s" = grains x outer intervals advanced per second
+(the integrator-independent unit of useful work); grain-derivative evaluations/s and
+internal integrator steps/s are reported next to it and feed the roofline.
+
+value  : inputs resident in HBM, device-timed with CUDA events (max over ranks)
+e2e    : the same through the host-buffer API -- every step copies the particles' state
+         (orientations + fractions + F, reference AoS layout) and velocity-gradient tables
+         from pinned host memory, converts layout on device, integrates, and copies the new
+         state and the per-system counters back.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+F_ALG = 254.0  # FP64 flop per grain-derivative evaluation
+B_ALG_DERIV = 160.0  # bytes per evaluation of the standalone derivative kernel
+PARAMS = {"phase_assemblage": (0, 1), "phase_fractions": (0.7, 0.3), "stress_exponent": 1.5,
+          "deformation_exponent": 3.5, "gbm_mobility": 125, "gbs_threshold": 0.3,
+          "nucleation_efficiency": 5.0}
+
+
+# ----------------------------------------------------------------------------- workloads
+
+
+def simple_shear_tables(P, n_steps, seed):
+    """Per-particle constant velocity gradients: a simple shear of rate r_p in a random
+    frame.  Returns (kind, L[n_steps][P,1,3,3], (t_lo[n_steps][P], t_hi[n_steps][P]))."""
+    rng = np.random.default_rng(seed)
+    from scipy.spatial.transform import Rotation
+
+    R = Rotation.random(P, random_state=seed).as_matrix()
+    rate = rng.uniform(0.5, 2.0, size=P)
+    L0 = np.zeros((3, 3))
+    L0[1, 0] = 2.0
+    L = np.einsum("pij,jk,plk->pil", R, L0, R) * rate[:, None, None]
+    dt = 0.04
+    t_edges = np.arange(n_steps + 1)[:, None] * dt * np.ones(P)[None]
+    return 0, [L[:, None].copy() for _ in range(n_steps)], (t_edges[:-1], t_edges[1:])
+
+
+def corner_flow_tables(P, n_steps, seed, K=9, n_path_steps=50):
+    """2-D corner-flow pathlines (config 3/4): particles exit at x = 1e6 m, depths spread
+    over 5-95 % of the 200 km box, plate speed 2 cm/yr (geometry of the reference's
+    tests/test_corner_flow_2d.py:107-113; velocity field = the analytic Batchelor corner
+    solution of velocity._corner_2d*).  Each pathline is traced backwards with a vectorised
+    RK4 (host, numpy) until it leaves the box (strain target 10 is never reached first),
+    cut into 50 equal-time outer intervals like `get_pathline(..., regular_steps=50)`
+    (pathlines.py:113-116), and L(t) = grad v(x(t)) is tabulated at K Chebyshev-Lobatto
+    nodes per interval.  Strain per outer interval ranges from 0.004 to 0.5: strongly
+    different work per particle.  Bench step k uses interval k mod 50."""
+    U = 2.0 / (100 * 365 * 86400)
+    H, W = 2e5, 1e6
+    z_exit = -np.linspace(0.05, 0.95, P) * H
+
+    def vel(x, z):
+        r2 = x * x + z * z
+        pre = 2 * U / np.pi
+        return pre * (np.arctan2(x, -z) + x * z / r2), pre * z * z / r2
+
+    def grad(x, z):
+        pre = 4 * U / (np.pi * (x * x + z * z) ** 2)
+        L = np.zeros(x.shape + (3, 3))
+        L[..., 0, 0] = -pre * x * x * z
+        L[..., 0, 2] = pre * x**3
+        L[..., 2, 0] = -pre * x * z * z
+        L[..., 2, 2] = pre * x * x * z
+        return L
+
+    def strain_rate(x, z):
+        pre = 4 * U / (np.pi * (x * x + z * z) ** 2)
+        return np.hypot(pre * x * x * z, 0.5 * pre * (x**3 - x * z * z))
+
+    n_fine, d_eps = 4000, 10.0 / 4000
+    x, z, t = np.full(P, W), z_exit.copy(), np.zeros(P)
+    alive = np.ones(P, dtype=bool)
+    T, X, Z = [t.copy()], [x.copy()], [z.copy()]
+    for _ in range(n_fine):
+        vx, vz = vel(x, z)
+        dt = -np.minimum(d_eps / strain_rate(x, z), 2e3 / np.hypot(vx, vz))
+        k1 = (vx, vz)
+        k2 = vel(x + 0.5 * dt * k1[0], z + 0.5 * dt * k1[1])
+        k3 = vel(x + 0.5 * dt * k2[0], z + 0.5 * dt * k2[1])
+        k4 = vel(x + dt * k3[0], z + dt * k3[1])
+        xn = x + dt / 6 * (k1[0] + 2 * k2[0] + 2 * k3[0] + k4[0])
+        zn = z + dt / 6 * (k1[1] + 2 * k2[1] + 2 * k3[1] + k4[1])
+        alive &= (xn > 0) & (zn > -H) & (zn < 0)
+        x, z, t = np.where(alive, xn, x), np.where(alive, zn, z), np.where(alive, t + dt, t)
+        T.append(t.copy())
+        X.append(x.copy())
+        Z.append(z.copy())
+    T, X, Z = np.array(T)[::-1], np.array(X)[::-1], np.array(Z)[::-1]  # forward in time
+    cheb = 0.5 * (1 - np.cos(np.pi * np.arange(K) / (K - 1)))
+    edges = T[0][None] + np.linspace(0.0, 1.0, n_path_steps + 1)[:, None] * (0.0 - T[0])[None]
+    t_nodes = edges[:-1, None, :] + cheb[None, :, None] * np.diff(edges, axis=0)[:, None, :]
+    L_path = np.empty((n_path_steps, P, K, 3, 3))
+    for p in range(P):
+        keep = np.concatenate([[True], np.diff(T[:, p]) > 0])  # frozen tail after leaving
+        xp = np.interp(t_nodes[:, :, p], T[keep, p], X[keep, p])
+        zp = np.interp(t_nodes[:, :, p], T[keep, p], Z[keep, p])
+        L_path[:, p] = grad(xp, zp)
+    tables = [L_path[k % n_path_steps] for k in range(n_steps)]
+    t_lo = np.stack([edges[k % n_path_steps] for k in range(n_steps)])
+    t_hi = np.stack([edges[k % n_path_steps + 1] for k in range(n_steps)])
+    return 2, tables, (t_lo, t_hi)
+
+
+
+def make_workload(name, P, n_steps, seed):
+    if name == "simple_shear":
+        return simple_shear_tables(P, n_steps, seed)
+    if name == "corner_flow":
+        return corner_flow_tables(P, n_steps, seed)
+    raise SystemExit(f"unknown workload {name}")
+
+
+# ----------------------------------------------------------------------------- clocks
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-i", str(self.index), "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax = float(parts[2])
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    import pydrex_b200 as drex
+    from pydrex_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    P, N, K, W = args.particles, args.grains, args.steps, args.warmup
+    n_total = K + W
+    kind, tables, t_edges = make_workload(args.workload, P, n_total, seed=1000 + rank)
+    L_dev = [torch.as_tensor(np.ascontiguousarray(t)).to(dev) for t in tables]
+    t_lo, t_hi = (torch.as_tensor(np.ascontiguousarray(t)).to(dev) for t in t_edges)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---------------- resident-state arm: `value` and the roofline -----------------------
+    ens = drex.ParticleEnsemble(P, N, PARAMS, seed=8816 + rank, device=dev)
+    tol = ens.tolerances()  # the reference's default tolerances
+    S = ens.S
+    # state + scratch exceed L2 (126 MB) by far, so consecutive steps cannot hit in L2
+    state_bytes = S * N * 10 * 8
+    for k in range(W):
+        ens.update(t_lo[k], t_hi[k], L_dev[k], kind, tol, check=False)
+    counters = torch.zeros((3,), dtype=torch.int64, device=dev)
+    step_ms = []
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    ev[0].record()
+    for k in range(W, n_total):
+        ens.update(t_lo[k], t_hi[k], L_dev[k], kind, tol, check=False)
+        counters += ens.stats[1:4].sum(dim=1)  # n_rhs, n_accept, n_reject (torch, tiny)
+        ev[k - W + 1].record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = max_over_ranks(ev[0].elapsed_time(ev[K]))
+    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(K)]
+    status_bad = int((ens.stats[0] != 0).sum().item())
+    n_rhs, n_acc, n_rej = (int(c) for c in counters.cpu())
+    evals = sum_over_ranks(n_rhs * N)
+    internal = sum_over_ranks(n_acc * N)
+    outer = float(world * S * N * K)
+    secs = total_ms * 1e-3
+    value = outer / secs
+
+    # kernel-only duration: the integrator launch is the whole step on the stream, so the
+    # per-step CUDA-event time IS the kernel's launch duration (plus a 256 B memset)
+    kernel_ms = float(np.mean(step_ms))
+    evals_per_launch = n_rhs * N / K
+    fp64_peak = None
+    if rank == 0:
+        import ctypes
+
+        flops = ctypes.c_double()
+        _lib.check(_lib.load().drex_fp64_peak_probe(local_rank, ctypes.byref(flops)))
+        fp64_peak = flops.value / 1e12
+    barrier()
+
+    # ---------------- host-buffer arm: `e2e` ------------------------------------------------
+    e2e = run_e2e(args, drex, _lib, torch, dev, kind, tables, t_edges, barrier, max_over_ranks,
+                  world, rank)
+
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    achieved_tf = F_ALG * evals_per_launch / (kernel_ms * 1e-3) / 1e12
+    # bytes the integrator moves per grain per attempted step (csrc/drex_integrate.cuh):
+    # orientation + FSAL slope in, both out (4 x 72 B), 3 stage energies, 10 fraction-stage
+    # doubles for olivine; enstatite skips the fraction stages.  Averaged over both phases.
+    bytes_per_attempt = 288.0 + 0.5 * (24.0 + 10 * 8.0 * 2)
+    attempts = (n_acc + n_rej) * N / K
+    hbm_gbs = bytes_per_attempt * attempts / (kernel_ms * 1e-3) / 1e9
+    cpu = None if args.no_cpu_baseline else cpu_baseline(args)
+    line = {
+        "metric": "grain-steps/s", "value": value, "unit": "grain-steps/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {
+            "workload": f"{args.workload}: {P} particles/GPU x (olivine A + enstatite AB) x "
+                        f"{N} grains, GBM M*=125 + GBS chi=0.3, reference default tolerances",
+            "step": "one outer CPO interval of every particle = one integrator launch",
+            "particles_per_gpu": P, "grains": N, "phases": 2,
+            "cache": f"inputs larger than L2: {state_bytes / 1e6:.0f} MB state + "
+                     f"{ens._ws.numel() / 1e6:.0f} MB scratch per GPU vs 126 MB L2",
+            "parallelism": f"particles sharded over {world} GPU(s), no data-path collective",
+        },
+        "grain_evals_per_s": evals / secs,
+        "grain_internal_steps_per_s": internal / secs,
+        "rhs_per_outer_step": n_rhs / (S * K), "rejected_steps": n_rej,
+        "failed_systems": status_bad,
+        "gpu_launches": K,
+        "e2e": e2e,
+        "roofline": {
+            "kernel": "drex::integrate_kernel", "bound": "fp64",
+            "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+            "frac": achieved_tf / fp64_peak if fp64_peak else None,
+            "peak_source": "measured here: drex_fp64_peak_probe (DFMA loop); MEASURED_PEAKS.json "
+                           "has no FP64 entry",
+            "algorithmic_flop_per_eval": F_ALG, "evals_per_launch": evals_per_launch,
+            "launch_ms": kernel_ms,
+            "hbm": {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": hbm_gbs / hbm_peak, "bytes_per_grain_attempt": bytes_per_attempt,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)"
+                    if peaks else "fallback 6650 GB/s"},
+            "traffic": None,
+        },
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+
+
+def run_e2e(args, drex, _lib, torch, dev, kind, tables, t_edges, barrier, max_over_ranks, world,
+            rank):
+    """Host-buffer path: state lives in pinned host memory in the reference's AoS layout and
+    round-trips every step, as a geodynamics code calling once per model time step would."""
+    import ctypes
+
+    P, N, K, W = args.particles, args.grains, args.steps, args.warmup
+    ens = drex.ParticleEnsemble(P, N, PARAMS, seed=8816 + rank, device=dev)
+    S = ens.S
+    tol = ens.tolerances()
+    f64 = torch.float64
+    h_o = ens.orientations().reshape(S, N, 9).cpu().pin_memory()  # AoS like Mineral.orientations
+    h_f = ens.f.cpu().pin_memory()
+    h_F = ens.F.cpu().pin_memory()
+    h_stats = torch.zeros((4, S), dtype=torch.int32).pin_memory()
+    h_L = [torch.as_tensor(np.ascontiguousarray(t)).pin_memory() for t in tables]
+    h_lo, h_hi = (torch.as_tensor(np.ascontiguousarray(t)).pin_memory() for t in t_edges)
+    d_aos = torch.empty((S, N, 9), dtype=f64, device=dev)
+    lib = _lib.load()
+    st = _lib.stream_ptr(torch)
+
+    def step(k):
+        d_aos.copy_(h_o, non_blocking=True)
+        ens.f.copy_(h_f, non_blocking=True)
+        ens.F.copy_(h_F, non_blocking=True)
+        Lk = h_L[k].to(dev, non_blocking=True)
+        t0 = h_lo[k].to(dev, non_blocking=True)
+        t1 = h_hi[k].to(dev, non_blocking=True)
+        _lib.check(lib.drex_pack_soa_f64(_lib.ptr(d_aos), _lib.ptr(ens.o), S, N, st))
+        ens.update(t0, t1, Lk, kind, tol, check=False)
+        _lib.check(lib.drex_unpack_soa_f64(_lib.ptr(ens.o), _lib.ptr(d_aos), S, N, st))
+        h_o.copy_(d_aos, non_blocking=True)
+        h_f.copy_(ens.f, non_blocking=True)
+        h_F.copy_(ens.F, non_blocking=True)
+        h_stats.copy_(ens.stats, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller needs the result on the host
+
+    for k in range(W):
+        step(k)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall = time.perf_counter()
+    e0.record()
+    for k in range(W, W + K):
+        step(k)
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t_wall
+    ms = max_over_ranks(max(e0.elapsed_time(e1), wall * 1e3 * 0.0))
+    state = S * N * 10 * 8 + S * 9 * 8
+    h2d = state + h_L[0].numel() * 8 + 2 * P * 8
+    d2h = state + 4 * S * 4
+    return {"value": world * S * N * K / (ms * 1e-3), "unit": "grain-steps/s",
+            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "ms_per_step": ms / K, "gpu_launches_per_step": 3,
+            "note": "state (orientations AoS + fractions + F) and L tables copied from pinned "
+                    "host memory every step, new state and counters copied back"}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+
+
+def _cpu_worker(job):
+    """One particle, both phases, `n_steps` outer intervals with the oracle port
+    (C right-hand side + scipy LSODA), the structure of the reference's per-particle run."""
+    os.environ["OMP_NUM_THREADS"] = "1"
+    from scipy.spatial.transform import Rotation
+
+    from oracle import oracle
+
+    seed, N, n_steps, kind, nodes, edges = job
+
+    def barycentric_interpolate(values, x):  # Chebyshev-Lobatto interpolant on [0, 1]
+        K = values.shape[0]
+        d = x - 0.5 * (1.0 - np.cos(np.pi * np.arange(K) / (K - 1)))
+        if (np.abs(d) < 1e-15).any():
+            return values[int(np.argmin(np.abs(d)))]
+        w = np.where(np.arange(K) % 2 == 1, -1.0, 1.0)
+        w[0] *= 0.5
+        w[-1] *= 0.5
+        w = w / d
+        return np.tensordot(w, values, axes=(0, 0)) / w.sum()
+
+    def make_get_L(k):
+        if kind == 0:
+            return lambda t, x: nodes[k][0]
+        t0, t1 = edges[0][k], edges[1][k]
+        return lambda t, x: barycentric_interpolate(nodes[k], (t - t0) / (t1 - t0))
+
+    states = []
+    for phase, fabric in ((0, 0), (1, 5)):
+        o = Rotation.random(N, random_state=seed + phase).as_matrix()
+        states.append([phase, fabric, o, np.full(N, 1.0 / N)])
+    counter = oracle.RhsCounter()
+    t_start = time.perf_counter()
+    F = np.eye(3)
+    for k in range(n_steps):
+        get_L = make_get_L(k)
+        for stt in states:  # update_all: every phase starts from the same F (minerals.py:674-684)
+            F_new, stt[2], stt[3] = oracle.update_orientations(
+                stt[2], stt[3], 4, stt[0], stt[1], PARAMS, F, get_L,
+                (edges[0][k], edges[1][k], lambda t: np.zeros(3)), counter=counter)
+        F = F_new
+    return time.perf_counter() - t_start, counter.nfev, counter.nsteps
+
+
+def cpu_run(args, n_particles, n_steps, cores):
+    """Time the CPU port on `cores` processes; returns (grain-steps/s, evals/s, info)."""
+    import multiprocessing as mp
+
+    from oracle import oracle
+
+    oracle.build()
+    N = args.grains
+    kind, tables, t_edges = make_workload(args.workload, n_particles, n_steps, seed=1000)
+    jobs = [(8816 + 2 * p, N, n_steps, kind, [t[p] for t in tables],
+             (t_edges[0][:, p], t_edges[1][:, p])) for p in range(n_particles)]
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        out = pool.map(_cpu_worker, jobs, chunksize=1)
+    wall = time.perf_counter() - t0
+    nfev = sum(o[1] for o in out)
+    nsteps = sum(o[2] for o in out)
+    grain_steps = n_particles * 2 * N * n_steps
+    return grain_steps / wall, nfev * N / wall, nsteps * N / wall, wall
+
+
+def cpu_baseline(args):
+    cores = len(os.sched_getaffinity(0))
+    n_particles = max(cores, 8)
+    n_steps = 2
+    v, evals, internal, wall = cpu_run(args, n_particles, n_steps, cores)
+    return {"value": v, "unit": "grain-steps/s", "cores": cores, "kind": "port",
+            "grain_evals_per_s": evals, "grain_internal_steps_per_s": internal,
+            "sample": f"{n_particles} particles x 2 phases x {args.grains} grains x {n_steps} outer "
+                      f"steps of the {args.workload} workload, oracle port (C RHS + scipy LSODA, "
+                      f"reference tolerances), multiprocessing Pool({cores}); {wall:.1f} s"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    K, W = args.steps, args.warmup
+    n_particles = max(cores, 8)
+    # bounded sample: each "step" advances n_particles particles through one outer interval
+    if W > 0:
+        cpu_run(args, n_particles, min(W, 1), cores)
+    n_steps = min(K, 3)
+    v, evals, internal, wall = cpu_run(args, n_particles, n_steps, cores)
+    sample = (f"{n_particles} particles x 2 phases x {args.grains} grains x {n_steps} outer steps "
+              f"per timed run (bounded sample of the GPU arm's workload), oracle port "
+              f"(C restatement of core.derivatives + scipy LSODA), Pool({cores})")
+    line = {
+        "impl": "reference", "metric": "grain-steps/s", "value": v, "unit": "grain-steps/s",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": K, "warmup": W,
+        "ms_per_step": wall * 1e3 / n_steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: bounded CPU sample, {sample}"},
+        "grain_evals_per_s": evals, "grain_internal_steps_per_s": internal,
+        "cpu_baseline": {"value": v, "unit": "grain-steps/s", "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": v, "unit": "grain-steps/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--particles", type=int, default=1250, help="particles per GPU")
+    ap.add_argument("--grains", type=int, default=5000)
+    ap.add_argument("--workload", default="corner_flow", choices=["simple_shear", "corner_flow"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -9,7 +9,9 @@ interpolates (include/drex_b200.h DREX_L_*):
   linear     Fluidity-style linear-in-time L          -> 2 nodes
   Chebyshev  K = 2^m + 1 Chebyshev-Lobatto nodes, barycentric interpolation; K doubles
              (the node sets nest, so no sample is wasted) until the interpolant
-             reproduces the new samples to `rtol`.
+             reproduces the new samples to `rtol`;
+  piecewise  dense uniform table, linear between nodes, when L(t) is not smooth on the
+             interval (the Chebyshev refinement did not converge).
 """
 
 import numpy as np
@@ -51,7 +53,11 @@ def tabulate_velocity_gradient(get_velocity_gradient, get_position, t0, t1, rtol
     """
 
     def L_at(x):
-        t = t0 + (t1 - t0) * x
+        # The right end is sampled just inside the interval: callers commonly switch flows
+        # with `L1 if t < t_switch else L2` at an outer time stamp, and the right-hand
+        # sides that matter all lie at t < t1 (only the error estimate of the last step
+        # touches t1 itself).
+        t = t0 + (t1 - t0) * min(x, 1.0 - 1e-12)
         return np.asarray(get_velocity_gradient(t, get_position(t)), dtype=np.float64).reshape(3, 3)
 
     K = 5
@@ -79,6 +85,12 @@ def tabulate_velocity_gradient(get_velocity_gradient, get_position, t0, t1, rtol
             vals[float(x)] = v
             err = max(err, np.abs(v - barycentric_interpolate(samples, x)).max())
         samples2 = np.stack([vals[float(x)] for x in xs2])
-        if err <= tol or K2 >= max_nodes:
+        if err <= tol:
             return _lib.L_CHEBYSHEV, samples2
+        if K2 >= max_nodes:
+            # not smooth on this interval (e.g. a flow switch inside it): polynomial
+            # interpolation would ring, so hand the kernel a dense piecewise-linear table
+            # and let the step-size control find the kink
+            xs_u = np.linspace(0.0, 1.0, 2 * max_nodes - 1)
+            return _lib.L_PIECEWISE, np.stack([L_at(x) for x in xs_u])
         K, samples = K2, samples2
