@@ -222,6 +222,10 @@ def update_orientations(orientations, fractions, regime, phase, fabric, params,
         atol=kwargs.pop("atol", np.abs(y0 * 1e-6) + 1e-4),       # minerals.py:523
         rtol=kwargs.pop("rtol", 1e-6),                            # minerals.py:524
         first_step=kwargs.pop("first_step", np.abs(t1 - t0) * 1e-1),  # minerals.py:525
+        # banded-Jacobian switch of Mineral.__post_init__ (minerals.py:264-275): without it
+        # ODEPACK's n^2 work array overflows for N > 4632; no Jacobian is ever formed
+        lband=kwargs.pop("lband", 6000 if n_grains > 4632 else None),
+        uband=kwargs.pop("uband", 6000 if n_grains > 4632 else None),
         **kwargs,
     )
     while True:

@@ -63,6 +63,9 @@ drex::FabricConsts make_fabric_consts(int fabric, const drex_params_t &p) {
     fc.lambda = p.nucleation_efficiency;
     fc.phase = phase;
     fc.default_exponents = (p.stress_exponent == 1.5 && p.deformation_exponent == 3.5) ? 1 : 0;
+    fc.inf_index = 3;
+    for (int i = 0; i < 4; ++i)
+        if (std::isinf(crss[i]) && phase == 0) fc.inf_index = i;
     return fc;
 }
 
@@ -93,14 +96,27 @@ int validate_systems(int64_t S, const int32_t *regime, const int32_t *phase, con
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// The integrator runs one CTA per SM (255 registers x 256 threads fill the register file).
 int integrate_slots(int device) {
-    int sms = 0, per_sm = 0;
+    int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, drex::integrate_kernel,
-                                                      drex::INT_BLOCK, 0) != cudaSuccess)
-        return -1;
-    if (per_sm < 1) per_sm = 1;
-    return sms * per_sm;
+    return sms;
+}
+
+// Dynamic shared memory of the integrator: the per-warp TMA stages plus as many of the four
+// fraction-stage arrays as fit under the opt-in limit.
+size_t integrate_smem_bytes(int device, int64_t N, int *smem_arrays) {
+    int optin = 0;
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    const size_t stage_bytes = (size_t)drex::INT_WARPS * drex::STAGE_DOUBLES * sizeof(double);
+    const size_t static_bytes = sizeof(drex::StepShared) + 256;
+    const size_t array_bytes = (size_t)((N + 31) / 32 * 32) * sizeof(double);
+    size_t avail = (size_t)optin > stage_bytes + static_bytes ? (size_t)optin - stage_bytes - static_bytes : 0;
+    int n = (int)(avail / array_bytes);
+    if (n > 4) n = 4;
+    if (n < 0) n = 0;
+    *smem_arrays = n;
+    return stage_bytes + (size_t)n * array_bytes;
 }
 
 }  // namespace
@@ -285,9 +301,16 @@ int drex_integrate_f64(int64_t S, int64_t P, int64_t N, const int32_t *sys_parti
     A.queue = (int *)workspace;
     A.scratch = (double *)((char *)workspace + 256);
     A.slot_doubles = (int64_t)(slot_bytes / sizeof(double));
+    int smem_arrays = 0;
+    const size_t dyn_smem = integrate_smem_bytes(device, N, &smem_arrays);
+    A.smem_arrays = smem_arrays;
+    // TMA bulk copies need 16 B aligned rows: even N and 16 B aligned base pointers
+    A.bulk_ok = (N % 2 == 0) && ((uintptr_t)o_in % 16 == 0) && ((uintptr_t)workspace % 16 == 0);
+    DREX_CUDA_CHECK(cudaFuncSetAttribute(drex::integrate_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
     DREX_CUDA_CHECK(cudaMemsetAsync(workspace, 0, 256, st));
     const drex::FabricTable T = make_fabric_table(*params);
-    drex::integrate_kernel<<<(unsigned)slots, drex::INT_BLOCK, 0, st>>>(A, T);
+    drex::integrate_kernel<<<(unsigned)slots, drex::INT_BLOCK, dyn_smem, st>>>(A, T);
     DREX_CUDA_CHECK(cudaGetLastError());
     return DREX_OK;
 }

@@ -5,8 +5,12 @@
 // core._get_rotation_and_strain and its helpers (src/pydrex/core.py:477-760), restated
 // for registers:
 //   * the four slip invariants share three matrix-vector products D.a_r;
-//   * the 4-element argsort is a stable insertion network on (key, value) tuples, so no
-//     dynamically indexed local arrays exist;
+//   * every supported fabric has exactly one slip system with infinite CRSS
+//     (core.py:324-342).  Its sort key |I/inf| is 0, so in the reference's 4-way argsort
+//     it (or another system whose invariant is exactly 0) takes the "inactive" slot and
+//     in every case ends with slip rate 0.  The argsort therefore reduces to ranking the
+//     THREE finite systems -- three comparisons and no data movement -- with identical
+//     results for all finite inputs (and NaN where the reference yields NaN);
 //   * the Schmid tensor is two outer products; the 81-term permutation-symbol sum is a
 //     cross product;
 //   * |gamma_k * gamma0|^(p/n) is factored as |r_k|^p * |gamma0|^(p/n) because
@@ -21,7 +25,7 @@ namespace drex {
 
 // Per-(phase, fabric) constants, built on the host (drex_capi.cu: make_fabric_consts).
 struct FabricConsts {
-    double crss[4];      // core.get_crss (core.py:315-342); +inf for inactive systems
+    double crss[4];      // core.get_crss (core.py:315-342); +inf for the inactive system
     double inv_crss[4];  // 1/crss (0 for inf)
     double rho_pref[3];  // (1/crss_i)^(n-p), i = 0..2 (core.py:675-676)
     double n_minus_1;    // deformation_exponent - 1
@@ -30,6 +34,8 @@ struct FabricConsts {
     double lambda;       // nucleation_efficiency
     int phase;           // 0 olivine, 1 enstatite
     int default_exponents;  // p == 1.5 && n == 3.5: powers via sqrt
+    int inf_index;       // olivine: index of the infinite-CRSS system (2 for C-type, else 3)
+    int pad_;
 };
 
 // x^y for x >= 0 with C pow() conventions at 0; exp(y log x) is accurate to
@@ -47,13 +53,6 @@ struct GrainOut {
 struct GrainProbe {  // optional intermediates for drex_grain_probe_f64
     double inv[4], rates[4], G[9], gamma0;
 };
-
-#define DREX_SWAP_IF(cond, x, y) \
-    do {                         \
-        double t_ = (cond) ? (y) : (x); \
-        (y) = (cond) ? (x) : (y);       \
-        (x) = t_;                       \
-    } while (0)
 
 // a: orientation (already clipped by the caller where the reference clips),
 // D: symmetric strain rate (D/smax), L: velocity gradient (L/smax).
@@ -84,59 +83,44 @@ __device__ __forceinline__ void grain_rhs(const double (&a)[9], const double (&D
     const bool all_zero = (I0 == 0.0) & (I1 == 0.0) & (I2 == 0.0) & (I3 == 0.0);
 
     if (fc.phase == 0) {
-        // stable insertion argsort of |I/crss| carrying (I, 1/crss, crss, system id)
-        double k0 = fabs(I0 * fc.inv_crss[0]), k1 = fabs(I1 * fc.inv_crss[1]);
-        double k2 = fabs(I2 * fc.inv_crss[2]), k3 = fabs(I3 * fc.inv_crss[3]);
-        double v0 = I0, v1 = I1, v2 = I2, v3 = I3;
-        double r0 = fc.inv_crss[0], r1 = fc.inv_crss[1], r2 = fc.inv_crss[2], r3 = fc.inv_crss[3];
-        double c0 = fc.crss[0], c1 = fc.crss[1], c2 = fc.crss[2], c3 = fc.crss[3];
-        double s0 = 0.0, s1 = 1.0, s2 = 2.0, s3 = 3.0;
-#define DREX_CSWAP(i, j)                      \
-    do {                                      \
-        const bool sw_ = k##i > k##j;         \
-        DREX_SWAP_IF(sw_, k##i, k##j);        \
-        DREX_SWAP_IF(sw_, v##i, v##j);        \
-        DREX_SWAP_IF(sw_, r##i, r##j);        \
-        DREX_SWAP_IF(sw_, c##i, c##j);        \
-        DREX_SWAP_IF(sw_, s##i, s##j);        \
-    } while (0)
-        // insertion sort as adjacent compare-exchanges (strict >, hence stable)
-        DREX_CSWAP(0, 1);
-        DREX_CSWAP(1, 2);
-        DREX_CSWAP(0, 1);
-        DREX_CSWAP(2, 3);
-        DREX_CSWAP(1, 2);
-        DREX_CSWAP(0, 1);
-#undef DREX_CSWAP
-        // sorted: 0 = inactive, 1 = min, 2 = int, 3 = max (core.py:556-567)
-        const double pre = c3 / v3;
-        const double q_min = pre * v1 * r1;
-        const double q_int = pre * v2 * r2;
-        double rate_min, rate_int, wp_min, wp_int;
-        const double am = fabs(q_min), ai = fabs(q_int);
+        // the three finite-CRSS systems (x, y, z); z is natural index 2 or 3 (CTA-uniform)
+        const bool inf3 = fc.inf_index == 3;
+        const double vz = inf3 ? I2 : I3;
+        const double rz = inf3 ? fc.inv_crss[2] : fc.inv_crss[3];
+        const double cz = inf3 ? fc.crss[2] : fc.crss[3];
+        const double ux = I0 * fc.inv_crss[0], uy = I1 * fc.inv_crss[1], uz = vz * rz;  // I/crss
+        const double kx = fabs(ux), ky = fabs(uy), kz = fabs(uz);
+        // stable ranks (ties keep index order, like the reference's insertion argsort)
+        const bool xy = kx <= ky, xz = kx <= kz, yz = ky <= kz;
+        const bool x_max = !xy && !xz;  // rank 2
+        const bool y_max = xy && !yz;
+        const bool z_max = xz && yz;
+        const double I_max = z_max ? vz : (y_max ? I1 : I0);
+        const double c_max = z_max ? cz : (y_max ? fc.crss[1] : fc.crss[0]);
+        const double pre = c_max / I_max;  // core.py:560
+        const double qx = pre * ux, qy = pre * uy, qz = pre * uz;
+        const double ax = fabs(qx), ay = fabs(qy), az = fabs(qz);
+        double rx, ry, rz_, px, py, pz;  // q|q|^(n-1) and |q|^p
         if (fc.default_exponents) {
-            const double sm = sqrt(am), si = sqrt(ai);
-            rate_min = q_min * (am * am * sm);  // q |q|^2.5
-            rate_int = q_int * (ai * ai * si);
-            wp_min = am * sm;                   // |q|^1.5
-            wp_int = ai * si;
+            const double sx = sqrt(ax), sy = sqrt(ay), sz = sqrt(az);
+            rx = qx * (ax * ax * sx); ry = qy * (ay * ay * sy); rz_ = qz * (az * az * sz);
+            px = ax * sx; py = ay * sy; pz = az * sz;
         } else {
-            rate_min = q_min * pow_nonneg(am, fc.n_minus_1);
-            rate_int = q_int * pow_nonneg(ai, fc.n_minus_1);
-            wp_min = pow_nonneg(am, fc.p);
-            wp_int = pow_nonneg(ai, fc.p);
+            rx = qx * pow_nonneg(ax, fc.n_minus_1);
+            ry = qy * pow_nonneg(ay, fc.n_minus_1);
+            rz_ = qz * pow_nonneg(az, fc.n_minus_1);
+            px = pow_nonneg(ax, fc.p); py = pow_nonneg(ay, fc.p); pz = pow_nonneg(az, fc.p);
         }
-        // scatter back to natural slip-system order
-#define DREX_PICK(id, field_min, field_int, field_max) \
-    ((s1 == (id)) ? (field_min) : ((s2 == (id)) ? (field_int) : ((s3 == (id)) ? (field_max) : 0.0)))
-        g0 = DREX_PICK(0.0, rate_min, rate_int, 1.0);
-        g1 = DREX_PICK(1.0, rate_min, rate_int, 1.0);
-        g2 = DREX_PICK(2.0, rate_min, rate_int, 1.0);
-        g3 = DREX_PICK(3.0, rate_min, rate_int, 1.0);
-        w0 = DREX_PICK(0.0, wp_min, wp_int, 1.0);
-        w1 = DREX_PICK(1.0, wp_min, wp_int, 1.0);
-        w2 = DREX_PICK(2.0, wp_min, wp_int, 1.0);
-#undef DREX_PICK
+        // the softest system slips at rate exactly 1 (core.py:567)
+        g0 = x_max ? 1.0 : rx;
+        g1 = y_max ? 1.0 : ry;
+        const double gz = z_max ? 1.0 : rz_;
+        w0 = x_max ? 1.0 : px;
+        w1 = y_max ? 1.0 : py;
+        const double wz = z_max ? 1.0 : pz;
+        g2 = inf3 ? gz : 0.0;
+        g3 = inf3 ? 0.0 : gz;
+        w2 = inf3 ? wz : 0.0;  // C-type: natural index 2 is the infinite-CRSS system
     } else {
         // enstatite: only (100)[001] slips (core.py:731-739)
         g3 = (fabs(I3) > 1e-15) ? 1.0 : 0.0;
@@ -146,9 +130,8 @@ __device__ __forceinline__ void grain_rhs(const double (&a)[9], const double (&D
     // u = g0 a1 + g1 a2, v = g2 a1 + g3 a0 (core.py:492-501)
     double G[9];
     {
-        const double u0 = g0 * a[3] + g1 * a[6], u1 = g0 * a[4] + g1 * a[7], u2 = g0 * a[5] + g1 * a[8];
-        const double t0 = g2 * a[3] + g3 * a[0], t1 = g2 * a[4] + g3 * a[1], t2 = g2 * a[5] + g3 * a[2];
-        const double u[3] = {u0, u1, u2}, v[3] = {t0, t1, t2};
+        const double u[3] = {g0 * a[3] + g1 * a[6], g0 * a[4] + g1 * a[7], g0 * a[5] + g1 * a[8]};
+        const double v[3] = {g2 * a[3] + g3 * a[0], g2 * a[4] + g3 * a[1], g2 * a[5] + g3 * a[2]};
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -190,9 +173,11 @@ __device__ __forceinline__ void grain_rhs(const double (&a)[9], const double (&D
         const double gp = pow_nonneg(fabs(gamma0), fc.p_over_n);
         const double rho0 = fc.rho_pref[0] * (w0 * gp);
         const double rho1 = fc.rho_pref[1] * (w1 * gp);
-        const double rho2 = fc.rho_pref[2] * (w2 * gp);
-        energy = rho0 * exp(-fc.lambda * rho0 * rho0) + rho1 * exp(-fc.lambda * rho1 * rho1) +
-                 rho2 * exp(-fc.lambda * rho2 * rho2);
+        energy = rho0 * exp(-fc.lambda * rho0 * rho0) + rho1 * exp(-fc.lambda * rho1 * rho1);
+        if (fc.inf_index == 3) {  // otherwise rho_2 = (1/inf)^(n-p) * ... = 0 contributes 0
+            const double rho2 = fc.rho_pref[2] * (w2 * gp);
+            energy += rho2 * exp(-fc.lambda * rho2 * rho2);
+        }
     }
     if (all_zero) {  // core.py:721-722
 #pragma unroll

@@ -7,10 +7,10 @@
 // (minerals.py:464-474).
 //
 // Design (B200-first, not a translation of LSODA):
-//  * persistent kernel; one CTA owns one system (particle, phase) from t0 to t1 and walks
-//    its own accepted/rejected steps with no host round trip; CTAs pull systems from an
-//    atomic queue, so particles with 9 or 106 right-hand sides per interval balance
-//    themselves (per-particle step control);
+//  * persistent kernel, one CTA per SM; a CTA owns one system (particle, phase) from t0 to
+//    t1 and walks its own accepted/rejected steps with no host round trip; CTAs pull
+//    systems from an atomic queue, so particles with 9 or 106 right-hand sides per
+//    interval balance themselves (per-particle step control);
 //  * Bogacki-Shampine 3(2) with FSAL: LSODA never leaves its non-stiff Adams branch on
 //    this problem, and at the reference tolerance (1e-4 absolute)
 //    a third-order pair needs the fewest right-hand sides;
@@ -19,7 +19,11 @@
 //    Phase 1 therefore takes each grain through ALL THREE stages in registers with no
 //    synchronisation (one HBM/L2 round trip of the orientation per STEP, not per stage),
 //    recording the strain energy at each stage; phase 2 runs the cheap coupled fraction
-//    stages with four fixed-order block reductions;
+//    stages out of shared memory with four fixed-order block reductions;
+//  * each warp streams its grains in chunks of 32: the chunk's orientation and FSAL slope
+//    (18 rows x 256 B of the SoA arrays) are fetched by TMA bulk copies
+//    (cp.async.bulk -> mbarrier) into a per-warp shared-memory stage while the warp is
+//    still computing the previous chunk, so HBM latency never reaches the FP64 pipe;
 //  * FP64 throughout; clip/renormalise inside every right-hand side as
 //    utils.extract_vars does (utils.py:183-190).
 #pragma once
@@ -30,6 +34,8 @@
 namespace drex {
 
 constexpr int INT_BLOCK = 256;
+constexpr int INT_WARPS = INT_BLOCK / 32;
+constexpr int STAGE_DOUBLES = 18 * 32;  // per warp: 9 orientation rows + 9 slope rows x 32 grains
 
 struct TolArgs {
     double rtol, atol_abs, atol_rel, first_step_frac, max_step_frac;
@@ -53,13 +59,49 @@ struct IntegrateArgs {
     double *scratch;       // n_slots * slot_doubles
     int64_t slot_doubles;  // per-CTA scratch size in doubles
     int *queue;            // atomic work counter, zeroed before launch
+    int smem_arrays;       // how many of the 4 fraction-stage arrays live in shared memory
+    int bulk_ok;           // 1: SoA rows are 16 B aligned -> TMA bulk staging allowed
 };
 
-// per-CTA scratch layout, in units of N doubles
+// per-CTA global scratch layout, in units of N doubles
 constexpr int SLOT_OA = 0, SLOT_OB = 9, SLOT_KA = 18, SLOT_KB = 27;  // orientation ping-pong, FSAL k
-constexpr int SLOT_FA = 36, SLOT_FB = 37, SLOT_KFA = 38, SLOT_KFB = 39, SLOT_KF2 = 40;
-constexpr int SLOT_FS = 41, SLOT_ACCE = 42, SLOT_E2 = 43, SLOT_E3 = 44, SLOT_E4 = 45;
-constexpr int SLOT_ARRAYS = 46;
+constexpr int SLOT_FA = 36, SLOT_FB = 37, SLOT_KFA = 38, SLOT_KFB = 39;
+constexpr int SLOT_P2 = 40;  // 4 fraction-stage arrays when they do not fit in shared memory
+constexpr int SLOT_ARRAYS = 44;
+
+// ---- TMA bulk copy + mbarrier (sm_90+/sm_100a PTX) ------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0;
+    const uint32_t addr = smem_addr(bar);
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_global, uint32_t bytes,
+                                         uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_addr(dst_smem)),
+        "l"(src_global), "r"(bytes), "r"(smem_addr(bar))
+        : "memory");
+}
 
 // velocity gradient at time t for particle `ip` (the DREX_L_* providers)
 __device__ inline void eval_L(const IntegrateArgs &A, int64_t ip, double t, double ta, double tb,
@@ -120,6 +162,7 @@ struct StepShared {
     double errF;           // weighted error of the F block
     double t, h, tend;
     double red[64];
+    uint64_t mbar[INT_WARPS];
     int sys, flag;
 };
 
@@ -143,6 +186,26 @@ __device__ inline void fill_stage_flow(StageFlow &sf, const double *L) {
             sf.Ls[3 * i + j] = L[3 * i + j] / s;                           // minerals.py:439
             sf.D[3 * i + j] = (0.5 * (L[3 * i + j] + L[3 * j + i])) / s;   // minerals.py:421,438
         }
+}
+
+// |x| > 1 on the integer pipe (the FP64 pipe is the bottleneck; clipping almost never fires)
+__device__ __forceinline__ bool exceeds_one(double x) {
+    const uint32_t hi = (uint32_t)__double2hiint(x) & 0x7fffffffu;
+    return hi > 0x3ff00000u || (hi == 0x3ff00000u && __double2loint(x) != 0);
+}
+__device__ __forceinline__ bool not_finite(double x) {
+    return ((uint32_t)__double2hiint(x) & 0x7ff00000u) == 0x7ff00000u;
+}
+
+// clip the nine entries to [-1, 1] (utils.py:187) only when some entry needs it
+__device__ __forceinline__ void clip9(double (&a)[9]) {
+    bool any = false;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) any |= exceeds_one(a[c]);
+    if (any) {
+#pragma unroll
+        for (int c = 0; c < 9; ++c) a[c] = clip1(a[c]);
+    }
 }
 
 // Rotation rate (already multiplied by strain_rate_max, minerals.py:450) and strain
@@ -173,12 +236,36 @@ __device__ __forceinline__ void stage_rhs(const double (&a)[9], const StageFlow 
     }
 }
 
+// weighted error ratio in float32: only its magnitude relative to 1 steers the step size
+__device__ __forceinline__ float err_ratio(double err, double ynew, double atol_abs, double relw) {
+    return __fdividef((float)fabs(err), (float)(atol_abs + relw * fabs(ynew)));
+}
+
 __global__ void __launch_bounds__(INT_BLOCK, 1)
 integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
+    extern __shared__ __align__(128) double dyn_smem[];
     __shared__ StepShared sh;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t N = A.N;
+    const int64_t n_chunks = (N + 31) / 32;
     double *slot = A.scratch + (int64_t)blockIdx.x * A.slot_doubles;
+    double *stage = dyn_smem + warp * STAGE_DOUBLES;  // [18][32] doubles of this warp
+    double *p2_smem = dyn_smem + INT_WARPS * STAGE_DOUBLES;
+    const int64_t Npad = (N + 31) / 32 * 32;
+    // fraction-stage arrays: shared memory while they fit, global scratch otherwise
+    double *p2[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        p2[i] = (i < A.smem_arrays) ? p2_smem + i * Npad : slot + (SLOT_P2 + i) * N;
+    double *E2 = p2[0], *E3 = p2[1], *E4 = p2[2], *fs = p2[3];
+    // aliases by lifetime: E2 -> k2 of the fractions -> error accumulator; E3 -> new fractions
+    double *kf2 = E2, *acce = E2, *fnew_s = E3;
+
+    uint64_t *mbar = &sh.mbar[warp];
+    uint32_t mbar_parity = 0;
+    if (lane == 0) mbar_init(mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
 
     for (;;) {
         __syncthreads();
@@ -206,8 +293,6 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
         double *k_cur = slot + SLOT_KA * N, *k_nxt = slot + SLOT_KB * N;
         double *f_nxt = slot + SLOT_FA * N;
         double *kf_cur = slot + SLOT_KFA * N, *kf_nxt = slot + SLOT_KFB * N;
-        double *kf2 = slot + SLOT_KF2 * N, *fs = slot + SLOT_FS * N, *acce = slot + SLOT_ACCE * N;
-        double *E2 = slot + SLOT_E2 * N, *E3 = slot + SLOT_E3 * N, *E4 = slot + SLOT_E4 * N;
 
         // ---- initial slope at t0 (one right-hand side) --------------------------------
         if (tid == 0) {
@@ -229,40 +314,61 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
         __syncthreads();
         {
             double sumc = 0.0, sume = 0.0;
-            for (int64_t g = tid; g < N; g += INT_BLOCK) {
-                double a[9], k[9], e;
+            for (int64_t q = warp; q < n_chunks; q += INT_WARPS) {
+                const int64_t g = q * 32 + lane;
+                if (g < N) {
+                    double a[9], k[9], e;
 #pragma unroll
-                for (int c = 0; c < 9; ++c) a[c] = clip1(o_in[c * N + g]);
-                stage_rhs(a, sh.st[2], regime, fc, k, e);
+                    for (int c = 0; c < 9; ++c) a[c] = o_in[c * N + g];
+                    clip9(a);
+                    stage_rhs(a, sh.st[2], regime, fc, k, e);
 #pragma unroll
-                for (int c = 0; c < 9; ++c) k_cur[c * N + g] = k[c];
-                if (f_active) {
-                    const double xc = fmax(f_in[g], 0.0);
-                    E4[g] = e;
-                    fs[g] = xc;
-                    sumc += xc;
-                    sume += xc * e;
+                    for (int c = 0; c < 9; ++c) k_cur[c * N + g] = k[c];
+                    if (f_active) {
+                        const double xc = fmax(f_in[g], 0.0);
+                        E4[g] = e;
+                        fs[g] = xc;
+                        sumc += xc;
+                        sume += xc * e;
+                    }
                 }
             }
             if (f_active) {
                 block_sum2<INT_BLOCK>(sumc, sume, sh.red);
                 const double mean = sume / sumc;
                 const double pref = sh.st[2].s * gbm_scale;
-                for (int64_t g = tid; g < N; g += INT_BLOCK)
-                    kf_cur[g] = pref * (fs[g] / sumc) * (mean - E4[g]);
+                for (int64_t q = warp; q < n_chunks; q += INT_WARPS) {
+                    const int64_t g = q * 32 + lane;
+                    if (g < N) kf_cur[g] = pref * (fs[g] / sumc) * (mean - E4[g]);
+                }
             }
         }
         int n_rhs = 1, n_acc = 0, n_rej = 0, status = 0;
         bool done = (span == 0.0);
         bool last_rejected = false;
+        double h_carry = 0.0;
 
         // ---- adaptive steps -------------------------------------------------------------
         while (!done) {
-            __syncthreads();
+            __syncthreads();  // k_cur / kf_cur / o_cur of the previous step are complete
             if (n_acc + n_rej >= A.tol.max_steps) {
                 status = 1;  // DREX_STATUS_MAX_STEPS
                 break;
             }
+            // prefetch this warp's first chunk while the stage flows are being set up
+            const bool use_bulk = A.bulk_ok != 0;
+            auto issue_chunk = [&](int64_t q) {
+                // lanes 0..17 each fetch one 256 B row of the SoA arrays into the warp's stage
+                if (lane == 0) mbar_expect_tx(mbar, 18u * 256u);
+                __syncwarp();
+                if (lane < 18) {
+                    const double *src = (lane < 9) ? o_cur + (int64_t)lane * N + q * 32
+                                                   : k_cur + (int64_t)(lane - 9) * N + q * 32;
+                    bulk_g2s(stage + lane * 32, src, 256u, mbar);
+                }
+            };
+            if (use_bulk && warp < n_chunks && (int64_t)warp * 32 + 32 <= N) issue_chunk(warp);
+
             // stage flows at t + h/2, t + 3h/4, t + h (three lanes), then F by lane 0
             if (tid < 3) {
                 const double cfrac = (tid == 0) ? BS_A21 : ((tid == 1) ? BS_A32 : 1.0);
@@ -285,7 +391,7 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                 double em = 0.0;
                 for (int c = 0; c < 9; ++c) {
                     const double err = h * (BS_E1 * sh.kF[c] + BS_E2 * k2[c] + BS_E3 * k3[c] + BS_E4 * sh.kFnew[c]);
-                    const double sc = atol_abs + relw * fmax(fabs(sh.F[c]), fabs(sh.Fnew[c]));
+                    const double sc = atol_abs + relw * fabs(sh.Fnew[c]);
                     const double r = fabs(err) / sc;
                     em = (r != r) ? INFINITY : fmax(em, r);
                 }
@@ -298,72 +404,110 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
             }
             __syncthreads();
             const double h = sh.h;
-            double emax = 0.0;
+            float emax_f = 0.0f;
+            bool bad = false;
 
             // ---- phase 1: every grain through all three stages in registers -------------
-            for (int64_t g = tid; g < N; g += INT_BLOCK) {
-                double a[9], k[9], st[9], accy[9], acc_e[9], e;
+            for (int64_t q = warp; q < n_chunks; q += INT_WARPS) {
+                const int64_t g = q * 32 + lane;
+                const bool full = use_bulk && (q * 32 + 32 <= N);
+                const int64_t qn = q + INT_WARPS;
+                const bool next_full = use_bulk && qn < n_chunks && (qn * 32 + 32 <= N);
+                double k[9], st[9], accy[9], acc_e[9], e = 0.0;
+                if (full) {
+                    mbar_wait(mbar, mbar_parity);
+                    mbar_parity ^= 1u;
 #pragma unroll
-                for (int c = 0; c < 9; ++c) {
-                    a[c] = o_cur[c * N + g];
-                    k[c] = k_cur[c * N + g];
+                    for (int c = 0; c < 9; ++c) k[c] = stage[(9 + c) * 32 + lane];
+                } else if (g < N) {
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) {
+                        stage[c * 32 + lane] = o_cur[c * N + g];
+                        k[c] = k_cur[c * N + g];
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) {
+                        stage[c * 32 + lane] = 0.0;
+                        k[c] = 0.0;
+                    }
                 }
+                const bool live = g < N;
+                // the orientation stays in the warp's stage (read again for stage 3)
 #pragma unroll
                 for (int c = 0; c < 9; ++c) {
-                    accy[c] = a[c] + (h * BS_B1) * k[c];
+                    const double ac = stage[c * 32 + lane];
+                    accy[c] = ac + (h * BS_B1) * k[c];
                     acc_e[c] = BS_E1 * k[c];
-                    st[c] = clip1(a[c] + (h * BS_A21) * k[c]);
+                    st[c] = ac + (h * BS_A21) * k[c];
                 }
-                stage_rhs(st, sh.st[0], regime, fc, k, e);
-                if (f_active) E2[g] = e;
+                clip9(st);
+                if (live) stage_rhs(st, sh.st[0], regime, fc, k, e);
+                if (f_active && live) E2[g] = e;
 #pragma unroll
                 for (int c = 0; c < 9; ++c) {
                     accy[c] += (h * BS_B2) * k[c];
                     acc_e[c] += BS_E2 * k[c];
-                    st[c] = clip1(a[c] + (h * BS_A32) * k[c]);
+                    st[c] = stage[c * 32 + lane] + (h * BS_A32) * k[c];
                 }
-                stage_rhs(st, sh.st[1], regime, fc, k, e);
-                if (f_active) E3[g] = e;
+                // the stage buffer is free now: fetch this warp's next chunk behind stage 3/4
+                __syncwarp();
+                if (next_full) issue_chunk(qn);
+                clip9(st);
+                if (live) stage_rhs(st, sh.st[1], regime, fc, k, e);
+                if (f_active && live) E3[g] = e;
 #pragma unroll
                 for (int c = 0; c < 9; ++c) {
                     accy[c] += (h * BS_B3) * k[c];
                     acc_e[c] += BS_E3 * k[c];
-                    st[c] = clip1(accy[c]);
+                    st[c] = accy[c];
                 }
-                stage_rhs(st, sh.st[2], regime, fc, k, e);
-                if (f_active) E4[g] = e;
+                clip9(st);
+                if (live) stage_rhs(st, sh.st[2], regime, fc, k, e);
+                if (f_active && live) E4[g] = e;
+                if (live) {
 #pragma unroll
-                for (int c = 0; c < 9; ++c) {
-                    const double err = h * (acc_e[c] + BS_E4 * k[c]);
-                    const double sc = atol_abs + relw * fmax(fabs(a[c]), fabs(accy[c]));
-                    const double r = fabs(err) / sc;
-                    emax = (r != r) ? INFINITY : fmax(emax, r);
-                    o_nxt[c * N + g] = accy[c];
-                    k_nxt[c * N + g] = k[c];
+                    for (int c = 0; c < 9; ++c) {
+                        const double err = h * (acc_e[c] + BS_E4 * k[c]);
+                        emax_f = fmaxf(emax_f, err_ratio(err, accy[c], atol_abs, relw));
+                        bad |= not_finite(accy[c]) | not_finite(k[c]);
+                        o_nxt[c * N + g] = accy[c];
+                        k_nxt[c * N + g] = k[c];
+                    }
                 }
             }
             n_rhs += 3;
+            double emax = bad ? INFINITY : (double)emax_f;
 
             // ---- phase 2: coupled volume fractions (core.py:431-436) --------------------
             if (f_active) {
+                __syncthreads();  // E2..E4 of all warps written (same-thread ownership aside)
                 double sc_ = 0.0, se_ = 0.0;
-                for (int64_t g = tid; g < N; g += INT_BLOCK) {  // stage 2 state
-                    const double xc = fmax(f_cur[g] + (h * BS_A21) * kf_cur[g], 0.0);
-                    fs[g] = xc;
-                    sc_ += xc;
-                    se_ += xc * E2[g];
+#pragma unroll 4
+                for (int64_t q = warp; q < n_chunks; q += INT_WARPS) {  // stage 2 state
+                    const int64_t g = q * 32 + lane;
+                    if (g < N) {
+                        const double xc = fmax(f_cur[g] + (h * BS_A21) * kf_cur[g], 0.0);
+                        fs[g] = xc;
+                        sc_ += xc;
+                        se_ += xc * E2[g];
+                    }
                 }
                 block_sum2<INT_BLOCK>(sc_, se_, sh.red);
                 double sumc = sc_, mean = se_ / sc_, pref = sh.st[0].s * gbm_scale;
                 sc_ = 0.0;
                 se_ = 0.0;
-                for (int64_t g = tid; g < N; g += INT_BLOCK) {  // k2, stage 3 state
-                    const double k2 = pref * (fs[g] / sumc) * (mean - E2[g]);
-                    kf2[g] = k2;
-                    const double xc = fmax(f_cur[g] + (h * BS_A32) * k2, 0.0);
-                    fs[g] = xc;
-                    sc_ += xc;
-                    se_ += xc * E3[g];
+#pragma unroll 4
+                for (int64_t q = warp; q < n_chunks; q += INT_WARPS) {  // k2, stage 3 state
+                    const int64_t g = q * 32 + lane;
+                    if (g < N) {
+                        const double k2 = pref * (fs[g] / sumc) * (mean - E2[g]);
+                        kf2[g] = k2;  // E2[g] is dead from here
+                        const double xc = fmax(f_cur[g] + (h * BS_A32) * k2, 0.0);
+                        fs[g] = xc;
+                        sc_ += xc;
+                        se_ += xc * E3[g];
+                    }
                 }
                 block_sum2<INT_BLOCK>(sc_, se_, sh.red);
                 sumc = sc_;
@@ -371,29 +515,40 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                 pref = sh.st[1].s * gbm_scale;
                 sc_ = 0.0;
                 se_ = 0.0;
-                for (int64_t g = tid; g < N; g += INT_BLOCK) {  // k3, new state
-                    const double k1 = kf_cur[g], k2 = kf2[g];
-                    const double k3 = pref * (fs[g] / sumc) * (mean - E3[g]);
-                    const double fn = f_cur[g] + h * (BS_B1 * k1 + BS_B2 * k2 + BS_B3 * k3);
-                    f_nxt[g] = fn;
-                    acce[g] = BS_E1 * k1 + BS_E2 * k2 + BS_E3 * k3;
-                    const double xc = fmax(fn, 0.0);
-                    fs[g] = xc;
-                    sc_ += xc;
-                    se_ += xc * E4[g];
+#pragma unroll 4
+                for (int64_t q = warp; q < n_chunks; q += INT_WARPS) {  // k3, new state
+                    const int64_t g = q * 32 + lane;
+                    if (g < N) {
+                        const double k1 = kf_cur[g], k2 = kf2[g];
+                        const double k3 = pref * (fs[g] / sumc) * (mean - E3[g]);
+                        const double fn = f_cur[g] + h * (BS_B1 * k1 + BS_B2 * k2 + BS_B3 * k3);
+                        f_nxt[g] = fn;
+                        fnew_s[g] = fn;  // E3[g] is dead from here
+                        acce[g] = BS_E1 * k1 + BS_E2 * k2 + BS_E3 * k3;
+                        const double xc = fmax(fn, 0.0);
+                        fs[g] = xc;
+                        sc_ += xc;
+                        se_ += xc * E4[g];
+                    }
                 }
                 block_sum2<INT_BLOCK>(sc_, se_, sh.red);
                 sumc = sc_;
                 mean = se_ / sc_;
                 pref = sh.st[2].s * gbm_scale;
-                for (int64_t g = tid; g < N; g += INT_BLOCK) {  // k4 (FSAL), error
-                    const double k4 = pref * (fs[g] / sumc) * (mean - E4[g]);
-                    kf_nxt[g] = k4;
-                    const double err = h * (acce[g] + BS_E4 * k4);
-                    const double sc = atol_abs + relw * fmax(fabs(f_cur[g]), fabs(f_nxt[g]));
-                    const double r = fabs(err) / sc;
-                    emax = (r != r) ? INFINITY : fmax(emax, r);
+                float ef = 0.0f;
+                bool badf = false;
+#pragma unroll 4
+                for (int64_t q = warp; q < n_chunks; q += INT_WARPS) {  // k4 (FSAL), error
+                    const int64_t g = q * 32 + lane;
+                    if (g < N) {
+                        const double k4 = pref * (fs[g] / sumc) * (mean - E4[g]);
+                        kf_nxt[g] = k4;
+                        const double err = h * (acce[g] + BS_E4 * k4);
+                        ef = fmaxf(ef, err_ratio(err, fnew_s[g], atol_abs, relw));
+                        badf |= not_finite(k4) | not_finite(fnew_s[g]);
+                    }
                 }
+                emax = badf ? INFINITY : fmax(emax, (double)ef);
             }
             emax = block_max<INT_BLOCK>(emax, sh.red);
             emax = fmax(emax, sh.errF);
@@ -412,6 +567,7 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                 ++n_acc;
                 last_rejected = false;
                 t_now = t_now + h;
+                h_carry = h_next;
                 // swap ping-pong buffers
                 const double *o_old = o_cur;
                 o_cur = o_nxt;
@@ -444,6 +600,7 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
             } else {
                 ++n_rej;
                 last_rejected = true;
+                h_carry = h_next;
                 if (fabs(h_next) <= 1e-14 * fmax(fabs(t_now), fabs(span))) {
                     status = 2;  // DREX_STATUS_STEP_UNDERFLOW
                     break;
@@ -451,8 +608,7 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
             }
             if (tid == 0) {
                 sh.t = t_now;
-                if (!done) sh.h = h_next;
-                else sh.h = h_next;  // suggestion for the next interval
+                sh.h = done ? h_carry : h_next;  // when done: suggestion for the next interval
             }
         }
         __syncthreads();
