@@ -96,7 +96,7 @@ int validate_systems(int64_t S, const int32_t *regime, const int32_t *phase, con
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// The integrator runs one CTA per SM (255 registers x 256 threads fill the register file).
+// The integrator runs one CTA per SM (128 registers x 512 threads fill the register file).
 int integrate_slots(int device) {
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;

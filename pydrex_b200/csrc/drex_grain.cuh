@@ -40,9 +40,10 @@ struct FabricConsts {
 
 // x^y for x >= 0 with C pow() conventions at 0; exp(y log x) is accurate to
 // ~|y log x| * 2^-53 relative, far inside the 1e-10 parity bound.
+// log(0) = -inf makes x = 0 come out right for y != 0 without a per-thread branch; y is
+// a model exponent (uniform across the launch).
 __device__ __forceinline__ double pow_nonneg(double x, double y) {
-    if (x == 0.0) return (y == 0.0) ? 1.0 : (y > 0.0 ? 0.0 : INFINITY);
-    return exp(y * log(x));
+    return (y == 0.0) ? 1.0 : exp(y * log(x));
 }
 
 struct GrainOut {

@@ -33,9 +33,15 @@
 
 namespace drex {
 
-constexpr int INT_BLOCK = 256;
+constexpr int INT_BLOCK = 512;
 constexpr int INT_WARPS = INT_BLOCK / 32;
-constexpr int STAGE_DOUBLES = 18 * 32;  // per warp: 9 orientation rows + 9 slope rows x 32 grains
+// per-warp shared-memory stage, rows of 32 grains: 0-8 orientation and 9-17 FSAL slope (TMA
+// targets), 18-26 running new state, 27-35 running error combination.  Keeping the two
+// accumulators here instead of in registers is what lets 512 threads (4 warps per
+// scheduler) share the register file: the FP64 pipe needs that many warps to cover its
+// own dependent-issue latency.
+constexpr int STAGE_ROWS = 36;
+constexpr int STAGE_DOUBLES = STAGE_ROWS * 32;
 
 struct TolArgs {
     double rtol, atol_abs, atol_rel, first_step_frac, max_step_frac;
@@ -189,9 +195,8 @@ __device__ inline void fill_stage_flow(StageFlow &sf, const double *L) {
 }
 
 // |x| > 1 on the integer pipe (the FP64 pipe is the bottleneck; clipping almost never fires)
-__device__ __forceinline__ bool exceeds_one(double x) {
-    const uint32_t hi = (uint32_t)__double2hiint(x) & 0x7fffffffu;
-    return hi > 0x3ff00000u || (hi == 0x3ff00000u && __double2loint(x) != 0);
+__device__ __forceinline__ bool exceeds_one(double x) {  // |x| >= 1 (conservative, one compare)
+    return ((uint32_t)__double2hiint(x) & 0x7fffffffu) >= 0x3ff00000u;
 }
 __device__ __forceinline__ bool not_finite(double x) {
     return ((uint32_t)__double2hiint(x) & 0x7ff00000u) == 0x7ff00000u;
@@ -358,7 +363,7 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
             // prefetch this warp's first chunk while the stage flows are being set up
             const bool use_bulk = A.bulk_ok != 0;
             auto issue_chunk = [&](int64_t q) {
-                // lanes 0..17 each fetch one 256 B row of the SoA arrays into the warp's stage
+                // lanes 0..17 each fetch one 256 B row of the SoA arrays into rows 0-17
                 if (lane == 0) mbar_expect_tx(mbar, 18u * 256u);
                 __syncwarp();
                 if (lane < 18) {
@@ -407,71 +412,66 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
             float emax_f = 0.0f;
             bool bad = false;
 
-            // ---- phase 1: every grain through all three stages in registers -------------
+            // ---- phase 1: every grain through all three stages, no synchronisation --------
             for (int64_t q = warp; q < n_chunks; q += INT_WARPS) {
                 const int64_t g = q * 32 + lane;
                 const bool full = use_bulk && (q * 32 + 32 <= N);
                 const int64_t qn = q + INT_WARPS;
                 const bool next_full = use_bulk && qn < n_chunks && (qn * 32 + 32 <= N);
-                double k[9], st[9], accy[9], acc_e[9], e = 0.0;
+                const bool live = g < N;
+                double *sa = stage + lane, *sk = stage + 9 * 32 + lane;
+                double *sy = stage + 18 * 32 + lane, *se = stage + 27 * 32 + lane;
+                double k[9], st[9], e = 0.0;
                 if (full) {
                     mbar_wait(mbar, mbar_parity);
                     mbar_parity ^= 1u;
-#pragma unroll
-                    for (int c = 0; c < 9; ++c) k[c] = stage[(9 + c) * 32 + lane];
-                } else if (g < N) {
+                } else {  // ragged tail (or unaligned rows): plain loads; idle lanes get zeros
 #pragma unroll
                     for (int c = 0; c < 9; ++c) {
-                        stage[c * 32 + lane] = o_cur[c * N + g];
-                        k[c] = k_cur[c * N + g];
-                    }
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 9; ++c) {
-                        stage[c * 32 + lane] = 0.0;
-                        k[c] = 0.0;
+                        sa[c * 32] = live ? o_cur[c * N + g] : 0.0;
+                        sk[c * 32] = live ? k_cur[c * N + g] : 0.0;
                     }
                 }
-                const bool live = g < N;
-                // the orientation stays in the warp's stage (read again for stage 3)
 #pragma unroll
                 for (int c = 0; c < 9; ++c) {
-                    const double ac = stage[c * 32 + lane];
-                    accy[c] = ac + (h * BS_B1) * k[c];
-                    acc_e[c] = BS_E1 * k[c];
-                    st[c] = ac + (h * BS_A21) * k[c];
+                    const double ac = sa[c * 32], kc = sk[c * 32];
+                    sy[c * 32] = ac + (h * BS_B1) * kc;
+                    se[c * 32] = BS_E1 * kc;
+                    st[c] = ac + (h * BS_A21) * kc;
                 }
                 clip9(st);
-                if (live) stage_rhs(st, sh.st[0], regime, fc, k, e);
+                stage_rhs(st, sh.st[0], regime, fc, k, e);
                 if (f_active && live) E2[g] = e;
 #pragma unroll
                 for (int c = 0; c < 9; ++c) {
-                    accy[c] += (h * BS_B2) * k[c];
-                    acc_e[c] += BS_E2 * k[c];
-                    st[c] = stage[c * 32 + lane] + (h * BS_A32) * k[c];
+                    sy[c * 32] += (h * BS_B2) * k[c];
+                    se[c * 32] += BS_E2 * k[c];
+                    st[c] = sa[c * 32] + (h * BS_A32) * k[c];
                 }
-                // the stage buffer is free now: fetch this warp's next chunk behind stage 3/4
+                // rows 0-17 are free now: fetch this warp's next chunk behind stages 3 and 4
                 __syncwarp();
                 if (next_full) issue_chunk(qn);
                 clip9(st);
-                if (live) stage_rhs(st, sh.st[1], regime, fc, k, e);
+                stage_rhs(st, sh.st[1], regime, fc, k, e);
                 if (f_active && live) E3[g] = e;
 #pragma unroll
                 for (int c = 0; c < 9; ++c) {
-                    accy[c] += (h * BS_B3) * k[c];
-                    acc_e[c] += BS_E3 * k[c];
-                    st[c] = accy[c];
+                    const double yn = sy[c * 32] + (h * BS_B3) * k[c];
+                    sy[c * 32] = yn;
+                    se[c * 32] += BS_E3 * k[c];
+                    st[c] = yn;
                 }
                 clip9(st);
-                if (live) stage_rhs(st, sh.st[2], regime, fc, k, e);
+                stage_rhs(st, sh.st[2], regime, fc, k, e);
                 if (f_active && live) E4[g] = e;
                 if (live) {
 #pragma unroll
                     for (int c = 0; c < 9; ++c) {
-                        const double err = h * (acc_e[c] + BS_E4 * k[c]);
-                        emax_f = fmaxf(emax_f, err_ratio(err, accy[c], atol_abs, relw));
-                        bad |= not_finite(accy[c]) | not_finite(k[c]);
-                        o_nxt[c * N + g] = accy[c];
+                        const double yn = sy[c * 32];
+                        const double err = h * (se[c * 32] + BS_E4 * k[c]);
+                        emax_f = fmaxf(emax_f, err_ratio(err, yn, atol_abs, relw));
+                        bad |= not_finite(yn) | not_finite(k[c]);
+                        o_nxt[c * N + g] = yn;
                         k_nxt[c * N + g] = k[c];
                     }
                 }
