@@ -246,6 +246,10 @@ __device__ __forceinline__ float err_ratio(double err, double ynew, double atol_
     return __fdividef((float)fabs(err), (float)(atol_abs + relw * fabs(ynew)));
 }
 
+// Chunks of 32 grains a warp can keep in registers during the fraction stages and the
+// end-of-interval pass (fast path: N <= 32 * INT_WARPS * MAXQ = 5120 grains).
+constexpr int MAXQ = 10;
+
 __global__ void __launch_bounds__(INT_BLOCK, 1)
 integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
     extern __shared__ __align__(128) double dyn_smem[];
@@ -253,18 +257,18 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t N = A.N;
     const int64_t n_chunks = (N + 31) / 32;
+    const bool fast = n_chunks <= (int64_t)MAXQ * INT_WARPS;
     double *slot = A.scratch + (int64_t)blockIdx.x * A.slot_doubles;
-    double *stage = dyn_smem + warp * STAGE_DOUBLES;  // [18][32] doubles of this warp
+    double *stage = dyn_smem + warp * STAGE_DOUBLES;  // [STAGE_ROWS][32] doubles of this warp
     double *p2_smem = dyn_smem + INT_WARPS * STAGE_DOUBLES;
     const int64_t Npad = (N + 31) / 32 * 32;
-    // fraction-stage arrays: shared memory while they fit, global scratch otherwise
+    // stage energies (and the generic path's clipped fractions): shared memory while they
+    // fit, global scratch otherwise
     double *p2[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
         p2[i] = (i < A.smem_arrays) ? p2_smem + i * Npad : slot + (SLOT_P2 + i) * N;
     double *E2 = p2[0], *E3 = p2[1], *E4 = p2[2], *fs = p2[3];
-    // aliases by lifetime: E2 -> k2 of the fractions -> error accumulator; E3 -> new fractions
-    double *kf2 = E2, *acce = E2, *fnew_s = E3;
 
     uint64_t *mbar = &sh.mbar[warp];
     uint32_t mbar_parity = 0;
@@ -317,34 +321,64 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
             sh.h = h;
         }
         __syncthreads();
+        double sum_clip = 0.0;  // sum of max(f, 0) of the current state (utils.py:188-189)
         {
-            double sumc = 0.0, sume = 0.0;
+            // software-pipelined: the next chunk's loads are in flight during this chunk's math
+            double sumc = 0.0, sume = 0.0, an[9], fn = 0.0;
+            {
+                const int64_t g0 = (int64_t)warp * 32 + lane;
+                const bool ok = warp < n_chunks && g0 < N;
+#pragma unroll
+                for (int c = 0; c < 9; ++c) an[c] = ok ? o_in[c * N + g0] : 0.0;
+                fn = ok ? f_in[g0] : 0.0;
+            }
             for (int64_t q = warp; q < n_chunks; q += INT_WARPS) {
                 const int64_t g = q * 32 + lane;
-                if (g < N) {
-                    double a[9], k[9], e;
+                double a[9], k[9], e;
 #pragma unroll
-                    for (int c = 0; c < 9; ++c) a[c] = o_in[c * N + g];
-                    clip9(a);
-                    stage_rhs(a, sh.st[2], regime, fc, k, e);
+                for (int c = 0; c < 9; ++c) a[c] = an[c];
+                const double xc = fmax(fn, 0.0);
+                {
+                    const int64_t gn = (q + INT_WARPS) * 32 + lane;
+                    const bool ok = (q + INT_WARPS) < n_chunks && gn < N;
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) an[c] = ok ? o_in[c * N + gn] : 0.0;
+                    fn = ok ? f_in[gn] : 0.0;
+                }
+                clip9(a);
+                stage_rhs(a, sh.st[2], regime, fc, k, e);
+                if (g < N) {
 #pragma unroll
                     for (int c = 0; c < 9; ++c) k_cur[c * N + g] = k[c];
-                    if (f_active) {
-                        const double xc = fmax(f_in[g], 0.0);
-                        E4[g] = e;
-                        fs[g] = xc;
-                        sumc += xc;
-                        sume += xc * e;
-                    }
+                    if (f_active) E4[g] = e;
+                    sumc += xc;
+                    sume += xc * e;
                 }
             }
+            block_sum2<INT_BLOCK>(sumc, sume, sh.red);
+            sum_clip = sumc;
             if (f_active) {
-                block_sum2<INT_BLOCK>(sumc, sume, sh.red);
                 const double mean = sume / sumc;
                 const double pref = sh.st[2].s * gbm_scale;
-                for (int64_t q = warp; q < n_chunks; q += INT_WARPS) {
-                    const int64_t g = q * 32 + lane;
-                    if (g < N) kf_cur[g] = pref * (fs[g] / sumc) * (mean - E4[g]);
+                if (fast) {
+                    double fr[MAXQ], er[MAXQ];
+#pragma unroll
+                    for (int j = 0; j < MAXQ; ++j) {
+                        const int64_t g = ((int64_t)warp + j * INT_WARPS) * 32 + lane;
+                        const bool ok = g < N;
+                        fr[j] = ok ? f_in[g] : 0.0;
+                        er[j] = ok ? E4[g] : 0.0;
+                    }
+#pragma unroll
+                    for (int j = 0; j < MAXQ; ++j) {
+                        const int64_t g = ((int64_t)warp + j * INT_WARPS) * 32 + lane;
+                        if (g < N) kf_cur[g] = pref * (fmax(fr[j], 0.0) / sumc) * (mean - er[j]);
+                    }
+                } else {
+                    for (int64_t q = warp; q < n_chunks; q += INT_WARPS) {
+                        const int64_t g = q * 32 + lane;
+                        if (g < N) kf_cur[g] = pref * (fmax(f_in[g], 0.0) / sumc) * (mean - E4[g]);
+                    }
                 }
             }
         }
@@ -352,6 +386,7 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
         bool done = (span == 0.0);
         bool last_rejected = false;
         double h_carry = 0.0;
+        const bool use_bulk = A.bulk_ok != 0;
 
         // ---- adaptive steps -------------------------------------------------------------
         while (!done) {
@@ -360,8 +395,6 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                 status = 1;  // DREX_STATUS_MAX_STEPS
                 break;
             }
-            // prefetch this warp's first chunk while the stage flows are being set up
-            const bool use_bulk = A.bulk_ok != 0;
             auto issue_chunk = [&](int64_t q) {
                 // lanes 0..17 each fetch one 256 B row of the SoA arrays into rows 0-17
                 if (lane == 0) mbar_expect_tx(mbar, 18u * 256u);
@@ -372,6 +405,7 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                     bulk_g2s(stage + lane * 32, src, 256u, mbar);
                 }
             };
+            // prefetch this warp's first chunk while the stage flows are being set up
             if (use_bulk && warp < n_chunks && (int64_t)warp * 32 + 32 <= N) issue_chunk(warp);
 
             // stage flows at t + h/2, t + 3h/4, t + h (three lanes), then F by lane 0
@@ -478,12 +512,84 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
             }
             n_rhs += 3;
             double emax = bad ? INFINITY : (double)emax_f;
+            double sum_clip_new = sum_clip;
 
             // ---- phase 2: coupled volume fractions (core.py:431-436) --------------------
-            if (f_active) {
-                __syncthreads();  // E2..E4 of all warps written (same-thread ownership aside)
+            if (f_active && fast) {
+                // every per-grain value of this thread stays in registers across the four
+                // block reductions; loads are issued together, stores at the end
+                double fr[MAXQ], k1[MAXQ], xr[MAXQ], k2[MAXQ], e4[MAXQ];
+#pragma unroll
+                for (int j = 0; j < MAXQ; ++j) {
+                    const int64_t g = ((int64_t)warp + j * INT_WARPS) * 32 + lane;
+                    const bool ok = g < N;
+                    fr[j] = ok ? f_cur[g] : 0.0;
+                    k1[j] = ok ? kf_cur[g] : 0.0;
+                    e4[j] = ok ? E4[g] : 0.0;
+                }
                 double sc_ = 0.0, se_ = 0.0;
-#pragma unroll 4
+#pragma unroll
+                for (int j = 0; j < MAXQ; ++j) {  // stage 2 state
+                    const int64_t g = ((int64_t)warp + j * INT_WARPS) * 32 + lane;
+                    xr[j] = fmax(fr[j] + (h * BS_A21) * k1[j], 0.0);
+                    sc_ += xr[j];
+                    se_ += xr[j] * ((g < N) ? E2[g] : 0.0);
+                }
+                block_sum2<INT_BLOCK>(sc_, se_, sh.red);
+                double sumc = sc_, mean = se_ / sc_, pref = sh.st[0].s * gbm_scale;
+                sc_ = 0.0;
+                se_ = 0.0;
+#pragma unroll
+                for (int j = 0; j < MAXQ; ++j) {  // k2, stage 3 state
+                    const int64_t g = ((int64_t)warp + j * INT_WARPS) * 32 + lane;
+                    const bool ok = g < N;
+                    k2[j] = pref * (xr[j] / sumc) * (mean - (ok ? E2[g] : 0.0));
+                    xr[j] = fmax(fr[j] + (h * BS_A32) * k2[j], 0.0);
+                    sc_ += xr[j];
+                    se_ += xr[j] * (ok ? E3[g] : 0.0);
+                }
+                block_sum2<INT_BLOCK>(sc_, se_, sh.red);
+                sumc = sc_;
+                mean = se_ / sc_;
+                pref = sh.st[1].s * gbm_scale;
+                sc_ = 0.0;
+                se_ = 0.0;
+#pragma unroll
+                for (int j = 0; j < MAXQ; ++j) {  // k3, new state
+                    const int64_t g = ((int64_t)warp + j * INT_WARPS) * 32 + lane;
+                    const double k3 = pref * (xr[j] / sumc) * (mean - ((g < N) ? E3[g] : 0.0));
+                    const double fn = fr[j] + h * (BS_B1 * k1[j] + BS_B2 * k2[j] + BS_B3 * k3);
+                    k1[j] = BS_E1 * k1[j] + BS_E2 * k2[j] + BS_E3 * k3;  // error combination
+                    k2[j] = fn;                                           // new fraction
+                    xr[j] = fmax(fn, 0.0);
+                    sc_ += xr[j];
+                    se_ += xr[j] * e4[j];
+                }
+                block_sum2<INT_BLOCK>(sc_, se_, sh.red);
+                sumc = sc_;
+                sum_clip_new = sc_;
+                mean = se_ / sc_;
+                pref = sh.st[2].s * gbm_scale;
+                float ef = 0.0f;
+                bool badf = false;
+#pragma unroll
+                for (int j = 0; j < MAXQ; ++j) {  // k4 (FSAL), error
+                    const int64_t g = ((int64_t)warp + j * INT_WARPS) * 32 + lane;
+                    const double k4 = pref * (xr[j] / sumc) * (mean - e4[j]);
+                    if (g < N) {
+                        kf_nxt[g] = k4;
+                        f_nxt[g] = k2[j];
+                        const double err = h * (k1[j] + BS_E4 * k4);
+                        ef = fmaxf(ef, err_ratio(err, k2[j], atol_abs, relw));
+                        badf |= not_finite(k4) | not_finite(k2[j]);
+                    }
+                }
+                emax = badf ? INFINITY : fmax(emax, (double)ef);
+            } else if (f_active) {
+                // generic path for ensembles too large for the register path: the same four
+                // sweeps through memory (E2 -> k2 -> error combination, E3 -> new fraction)
+                double *kf2 = E2, *acce = E2, *fnew_s = E3;
+                double sc_ = 0.0, se_ = 0.0;
                 for (int64_t q = warp; q < n_chunks; q += INT_WARPS) {  // stage 2 state
                     const int64_t g = q * 32 + lane;
                     if (g < N) {
@@ -497,7 +603,6 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                 double sumc = sc_, mean = se_ / sc_, pref = sh.st[0].s * gbm_scale;
                 sc_ = 0.0;
                 se_ = 0.0;
-#pragma unroll 4
                 for (int64_t q = warp; q < n_chunks; q += INT_WARPS) {  // k2, stage 3 state
                     const int64_t g = q * 32 + lane;
                     if (g < N) {
@@ -515,7 +620,6 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                 pref = sh.st[1].s * gbm_scale;
                 sc_ = 0.0;
                 se_ = 0.0;
-#pragma unroll 4
                 for (int64_t q = warp; q < n_chunks; q += INT_WARPS) {  // k3, new state
                     const int64_t g = q * 32 + lane;
                     if (g < N) {
@@ -533,11 +637,11 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                 }
                 block_sum2<INT_BLOCK>(sc_, se_, sh.red);
                 sumc = sc_;
+                sum_clip_new = sc_;
                 mean = se_ / sc_;
                 pref = sh.st[2].s * gbm_scale;
                 float ef = 0.0f;
                 bool badf = false;
-#pragma unroll 4
                 for (int64_t q = warp; q < n_chunks; q += INT_WARPS) {  // k4 (FSAL), error
                     const int64_t g = q * 32 + lane;
                     if (g < N) {
@@ -568,6 +672,7 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                 last_rejected = false;
                 t_now = t_now + h;
                 h_carry = h_next;
+                sum_clip = sum_clip_new;
                 // swap ping-pong buffers
                 const double *o_old = o_cur;
                 o_cur = o_nxt;
@@ -618,33 +723,94 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
         double *o_out = A.o_out + s * 9 * N;
         double *f_out = A.f_out + s * N;
         const double floor_v = A.gbs_threshold / (double)N;
-        double s1 = 0.0, dummy = 0.0;
-        for (int64_t g = tid; g < N; g += INT_BLOCK) s1 += fmax(f_cur[g], 0.0);
-        block_sum2<INT_BLOCK>(s1, dummy, sh.red);
-        double s2 = 0.0;
-        dummy = 0.0;
-        for (int64_t g = tid; g < N; g += INT_BLOCK) {
-            double fa = fmax(f_cur[g], 0.0) / s1;
-            const bool slide = fa < floor_v;
-            double a[9];
+        const double s1 = sum_clip;  // sum of max(f, 0), carried from the last accepted step
+        if (fast) {
+            double fa[MAXQ];
+            uint32_t slide_mask = 0;
+            double s2 = 0.0, dummy = 0.0;
 #pragma unroll
-            for (int c = 0; c < 9; ++c) a[c] = slide ? o_in[c * N + g] : o_cur[c * N + g];
+            for (int j = 0; j < MAXQ; ++j) {
+                const int64_t g = ((int64_t)warp + j * INT_WARPS) * 32 + lane;
+                fa[j] = (g < N) ? f_cur[g] : 0.0;
+            }
 #pragma unroll
-            for (int c = 0; c < 9; ++c) o_out[c * N + g] = clip1(a[c]);
-            fa = slide ? floor_v : fa;
-            fs[g] = fa;
-            s2 += fa;
+            for (int j = 0; j < MAXQ; ++j) {
+                const int64_t g = ((int64_t)warp + j * INT_WARPS) * 32 + lane;
+                double v = fmax(fa[j], 0.0) / s1;
+                const bool slide = (g < N) && (v < floor_v);
+                slide_mask |= slide ? (1u << j) : 0u;
+                v = slide ? floor_v : v;
+                fa[j] = (g < N) ? v : 0.0;
+                s2 += fa[j];
+            }
+            block_sum2<INT_BLOCK>(s2, dummy, sh.red);
+            double s3 = 0.0;
+            dummy = 0.0;
+#pragma unroll
+            for (int j = 0; j < MAXQ; ++j) {
+                fa[j] = fmax(fa[j] / s2, 0.0);
+                s3 += fa[j];
+            }
+            block_sum2<INT_BLOCK>(s3, dummy, sh.red);
+#pragma unroll
+            for (int j = 0; j < MAXQ; ++j) {
+                const int64_t g = ((int64_t)warp + j * INT_WARPS) * 32 + lane;
+                if (g < N) f_out[g] = fa[j] / s3;
+            }
+            // orientations: sliding grains get the interval-start orientation back;
+            // pipelined so the next chunk's loads overlap this chunk's stores
+            double an[9];
+            {
+                const int64_t g0 = (int64_t)warp * 32 + lane;
+                const bool ok = warp < n_chunks && g0 < N;
+                const double *src = (slide_mask & 1u) ? o_in : o_cur;
+#pragma unroll
+                for (int c = 0; c < 9; ++c) an[c] = ok ? src[c * N + g0] : 0.0;
+            }
+            int j = 0;
+            for (int64_t q = warp; q < n_chunks; q += INT_WARPS, ++j) {
+                const int64_t g = q * 32 + lane;
+                double a[9];
+#pragma unroll
+                for (int c = 0; c < 9; ++c) a[c] = an[c];
+                {
+                    const int64_t gn = (q + INT_WARPS) * 32 + lane;
+                    const bool ok = (q + INT_WARPS) < n_chunks && gn < N;
+                    const double *src = ((slide_mask >> (j + 1)) & 1u) ? o_in : o_cur;
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) an[c] = ok ? src[c * N + gn] : 0.0;
+                }
+                clip9(a);
+                if (g < N) {
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) o_out[c * N + g] = a[c];
+                }
+            }
+        } else {
+            double s2 = 0.0, dummy = 0.0;
+            for (int64_t g = tid; g < N; g += INT_BLOCK) {
+                double fa = fmax(f_cur[g], 0.0) / s1;
+                const bool slide = fa < floor_v;
+                double a[9];
+#pragma unroll
+                for (int c = 0; c < 9; ++c) a[c] = slide ? o_in[c * N + g] : o_cur[c * N + g];
+#pragma unroll
+                for (int c = 0; c < 9; ++c) o_out[c * N + g] = clip1(a[c]);
+                fa = slide ? floor_v : fa;
+                fs[g] = fa;
+                s2 += fa;
+            }
+            block_sum2<INT_BLOCK>(s2, dummy, sh.red);
+            double s3 = 0.0;
+            dummy = 0.0;
+            for (int64_t g = tid; g < N; g += INT_BLOCK) {
+                const double fb = fmax(fs[g] / s2, 0.0);
+                fs[g] = fb;
+                s3 += fb;
+            }
+            block_sum2<INT_BLOCK>(s3, dummy, sh.red);
+            for (int64_t g = tid; g < N; g += INT_BLOCK) f_out[g] = fs[g] / s3;
         }
-        block_sum2<INT_BLOCK>(s2, dummy, sh.red);
-        double s3 = 0.0;
-        dummy = 0.0;
-        for (int64_t g = tid; g < N; g += INT_BLOCK) {
-            const double fb = fmax(fs[g] / s2, 0.0);
-            fs[g] = fb;
-            s3 += fb;
-        }
-        block_sum2<INT_BLOCK>(s3, dummy, sh.red);
-        for (int64_t g = tid; g < N; g += INT_BLOCK) f_out[g] = fs[g] / s3;
         if (tid == 0) {
             for (int c = 0; c < 9; ++c) A.F[s * 9 + c] = sh.F[c];
             if (A.h_io) A.h_io[s] = sh.h;
