@@ -167,6 +167,10 @@ size_t drex_integrate_workspace_bytes(int64_t S, int64_t N, int device);
  * L_kind, K, L_nodes [P][K][9]  velocity-gradient provider (DREX_L_*)
  * h_io [S]          in: first trial step (<= 0: use first_step_frac); out: next suggested
  *                   step; may be NULL
+ * order [S]         optional (may be NULL) permutation of 0..S-1: the order in which the
+ *                   persistent CTAs pull systems from the work queue.  Results do not
+ *                   depend on it; putting expensive systems first (longest-processing-
+ *                   time-first) shortens the tail of the launch.
  * status, n_rhs, n_accept, n_reject  int32 [S] outputs (n_* may be NULL)
  */
 int drex_integrate_f64(int64_t S, int64_t P, int64_t N, const int32_t *sys_particle,
@@ -177,8 +181,8 @@ int drex_integrate_f64(int64_t S, int64_t P, int64_t N, const int32_t *sys_parti
                        const double *f_in, double *o_out, double *f_out, const double *t0,
                        const double *t1, int L_kind, int K, const double *L_nodes,
                        const drex_params_t *params, const drex_tolerances_t *tol, double *h_io,
-                       int32_t *status, int32_t *n_rhs, int32_t *n_accept, int32_t *n_reject,
-                       void *workspace, size_t workspace_bytes, void *stream);
+                       const int32_t *order, int32_t *status, int32_t *n_rhs, int32_t *n_accept,
+                       int32_t *n_reject, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- minerals.voigt_averages (minerals.py:688-740) -------------------------------- */
 

@@ -126,7 +126,7 @@ def _declare(lib):
     lib.drex_integrate_workspace_bytes.argtypes = [i64, i64, i32]
     lib.drex_integrate_f64.argtypes = (
         [i64, i64, i64] + [vp] * 5 + [vp] * 3 + [vp] * 5 + [vp, vp, i32, i32, vp]
-        + [c.POINTER(DrexParams), c.POINTER(DrexTolerances)] + [vp] * 5 + [vp, szt, vp]
+        + [c.POINTER(DrexParams), c.POINTER(DrexTolerances)] + [vp] * 6 + [vp, szt, vp]
     )
     lib.drex_voigt_average_f64.argtypes = [vp, vp, vp, vp, i64, i64, vp, i32, vp]
     lib.drex_mindex_workspace_bytes.restype = szt

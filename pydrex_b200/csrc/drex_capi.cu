@@ -256,6 +256,7 @@ int drex_integrate_f64(int64_t S, int64_t P, int64_t N, const int32_t *sys_parti
                        const double *f_in, double *o_out, double *f_out, const double *t0,
                        const double *t1, int L_kind, int K, const double *L_nodes,
                        const drex_params_t *params, const drex_tolerances_t *tol, double *h_io,
+                       const int32_t *order,
                        int32_t *status, int32_t *n_rhs, int32_t *n_accept, int32_t *n_reject,
                        void *workspace, size_t workspace_bytes, void *stream) {
     if (S < 0 || P < 0 || N < 0) return fail(DREX_E_INVALID, "negative size");
@@ -297,7 +298,7 @@ int drex_integrate_f64(int64_t S, int64_t P, int64_t N, const int32_t *sys_parti
     A.tol.first_step_frac = tol->first_step_frac; A.tol.max_step_frac = tol->max_step_frac;
     A.tol.max_steps = tol->max_steps > 0 ? tol->max_steps : 100000;
     A.tol.method = tol->method;
-    A.h_io = h_io; A.status = status; A.n_rhs = n_rhs; A.n_accept = n_accept; A.n_reject = n_reject;
+    A.h_io = h_io; A.order = order; A.status = status; A.n_rhs = n_rhs; A.n_accept = n_accept; A.n_reject = n_reject;
     A.queue = (int *)workspace;
     A.scratch = (double *)((char *)workspace + 256);
     A.slot_doubles = (int64_t)(slot_bytes / sizeof(double));

@@ -102,13 +102,30 @@ __device__ inline void jacobi_eig3(const double *A_in, double *w, double *V) {
     w[2] = A[8];
 }
 
-// max |eigenvalue| of sym(L)  (scipy.linalg.eigvalsh call at minerals.py:421-422)
+// max |eigenvalue| of sym(L)  (scipy.linalg.eigvalsh call at minerals.py:421-422).
+// Closed form for a symmetric 3x3 (trigonometric solution of the characteristic cubic):
+// the extreme eigenvalues are q + 2p cos(phi) and q + 2p cos(phi + 2pi/3); absolute error
+// ~1 ulp of the spectral radius, the same class as LAPACK's.  This sits on the serial
+// per-step path of every CTA, so it must not iterate.
 __device__ inline double strain_rate_max(const double *L) {
-    double D[9], w[3], V[9];
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) D[3 * i + j] = 0.5 * (L[3 * i + j] + L[3 * j + i]);
-    jacobi_eig3(D, w, V);
-    return fmax(fabs(w[0]), fmax(fabs(w[1]), fabs(w[2])));
+    const double d00 = L[0], d11 = L[4], d22 = L[8];
+    const double d01 = 0.5 * (L[1] + L[3]), d02 = 0.5 * (L[2] + L[6]), d12 = 0.5 * (L[5] + L[7]);
+    const double p1 = d01 * d01 + d02 * d02 + d12 * d12;
+    const double q = (d00 + d11 + d22) / 3.0;
+    const double b00 = d00 - q, b11 = d11 - q, b22 = d22 - q;
+    const double p2 = b00 * b00 + b11 * b11 + b22 * b22 + 2.0 * p1;
+    const double p = sqrt(p2 / 6.0);
+    if (!(p > 0.0)) return fabs(q);  // multiple of the identity (or NaN, which propagates)
+    const double ip = 1.0 / p;
+    const double c00 = b00 * ip, c11 = b11 * ip, c22 = b22 * ip;
+    const double c01 = d01 * ip, c02 = d02 * ip, c12 = d12 * ip;
+    double r = 0.5 * (c00 * (c11 * c22 - c12 * c12) - c01 * (c01 * c22 - c12 * c02) +
+                      c02 * (c01 * c12 - c11 * c02));
+    r = fmin(1.0, fmax(-1.0, r));
+    const double phi = acos(r) / 3.0;
+    const double e_hi = q + 2.0 * p * cos(phi);
+    const double e_lo = q + 2.0 * p * cos(phi + 2.0943951023931954923);
+    return fmax(fabs(e_hi), fabs(e_lo));
 }
 
 // Left stretch of M (tensors.polar_decompose(M)[1], tensors.py:14-19) = sqrt(M M^T)

@@ -61,6 +61,7 @@ struct IntegrateArgs {
     double gbm_mobility, gbs_threshold;
     TolArgs tol;
     double *h_io;
+    const int32_t *order;  // optional queue permutation (longest systems first)
     int32_t *status, *n_rhs, *n_accept, *n_reject;
     double *scratch;       // n_slots * slot_doubles
     int64_t slot_doubles;  // per-CTA scratch size in doubles
@@ -198,16 +199,15 @@ __device__ inline void fill_stage_flow(StageFlow &sf, const double *L) {
 __device__ __forceinline__ bool exceeds_one(double x) {  // |x| >= 1 (conservative, one compare)
     return ((uint32_t)__double2hiint(x) & 0x7fffffffu) >= 0x3ff00000u;
 }
-__device__ __forceinline__ bool not_finite(double x) {
-    return ((uint32_t)__double2hiint(x) & 0x7ff00000u) == 0x7ff00000u;
-}
 
 // clip the nine entries to [-1, 1] (utils.py:187) only when some entry needs it
 __device__ __forceinline__ void clip9(double (&a)[9]) {
     bool any = false;
 #pragma unroll
     for (int c = 0; c < 9; ++c) any |= exceeds_one(a[c]);
-    if (any) {
+    // warp-uniform branch: without the vote the compiler predicates the (almost never
+    // needed) clip sequence and issues it for every grain
+    if (__any_sync(0xffffffffu, any)) {
 #pragma unroll
         for (int c = 0; c < 9; ++c) a[c] = clip1(a[c]);
     }
@@ -241,9 +241,14 @@ __device__ __forceinline__ void stage_rhs(const double (&a)[9], const StageFlow 
     }
 }
 
-// weighted error ratio in float32: only its magnitude relative to 1 steers the step size
+// Weighted error ratio |err| / (atol + relw |y_new|).  Only its size relative to 1 steers
+// the step, so the reciprocal is the 2^-23-accurate hardware approximation and the running
+// maximum is kept in float32; a float sum of all ratios carries NaN/inf to the accept test.
 __device__ __forceinline__ float err_ratio(double err, double ynew, double atol_abs, double relw) {
-    return __fdividef((float)fabs(err), (float)(atol_abs + relw * fabs(ynew)));
+    const double sc = fma(relw, fabs(ynew), atol_abs);
+    double rc;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(sc));
+    return (float)(fabs(err) * rc);
 }
 
 // Chunks of 32 grains a warp can keep in registers during the fraction stages and the
@@ -254,7 +259,8 @@ __global__ void __launch_bounds__(INT_BLOCK, 1)
 integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
     extern __shared__ __align__(128) double dyn_smem[];
     __shared__ StepShared sh;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
     const int64_t N = A.N;
     const int64_t n_chunks = (N + 31) / 32;
     const bool fast = n_chunks <= (int64_t)MAXQ * INT_WARPS;
@@ -278,7 +284,10 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) sh.sys = atomicAdd(A.queue, 1);
+        if (tid == 0) {
+            const int ticket = atomicAdd(A.queue, 1);
+            sh.sys = (ticket < A.S && A.order != nullptr) ? A.order[ticket] : ticket;
+        }
         __syncthreads();
         const int64_t s = sh.sys;
         if (s >= A.S) break;
@@ -396,13 +405,15 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                 break;
             }
             auto issue_chunk = [&](int64_t q) {
-                // lanes 0..17 each fetch one 256 B row of the SoA arrays into rows 0-17
-                if (lane == 0) mbar_expect_tx(mbar, 18u * 256u);
-                __syncwarp();
-                if (lane < 18) {
-                    const double *src = (lane < 9) ? o_cur + (int64_t)lane * N + q * 32
-                                                   : k_cur + (int64_t)(lane - 9) * N + q * 32;
-                    bulk_g2s(stage + lane * 32, src, 256u, mbar);
+                // one elected lane fetches the 18 rows (256 B each) of chunk q into rows 0-17;
+                // every operand is warp-uniform, so the copies issue from uniform registers
+                if (lane == 0) {
+                    mbar_expect_tx(mbar, 18u * 256u);
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) {
+                        bulk_g2s(stage + c * 32, o_cur + (int64_t)c * N + q * 32, 256u, mbar);
+                        bulk_g2s(stage + (9 + c) * 32, k_cur + (int64_t)c * N + q * 32, 256u, mbar);
+                    }
                 }
             };
             // prefetch this warp's first chunk while the stage flows are being set up
@@ -441,10 +452,11 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                     left_stretch(sh.kFnew, sh.st[2].V);
                 }
             }
-            __syncthreads();
+            // only the diffusion regime reads tid 0's results (V) during phase 1; errF and
+            // Fnew are consumed after the block reductions below
+            if (regime == 1) __syncthreads();
             const double h = sh.h;
-            float emax_f = 0.0f;
-            bool bad = false;
+            float emax_f = 0.0f, racc = 0.0f;  // max and sum of the error ratios
 
             // ---- phase 1: every grain through all three stages, no synchronisation --------
             for (int64_t q = warp; q < n_chunks; q += INT_WARPS) {
@@ -503,15 +515,16 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                     for (int c = 0; c < 9; ++c) {
                         const double yn = sy[c * 32];
                         const double err = h * (se[c * 32] + BS_E4 * k[c]);
-                        emax_f = fmaxf(emax_f, err_ratio(err, yn, atol_abs, relw));
-                        bad |= not_finite(yn) | not_finite(k[c]);
+                        const float r = err_ratio(err, yn, atol_abs, relw);
+                        emax_f = fmaxf(emax_f, r);
+                        racc += r;  // any non-finite k or y_new makes err, hence r, non-finite
                         o_nxt[c * N + g] = yn;
                         k_nxt[c * N + g] = k[c];
                     }
                 }
             }
             n_rhs += 3;
-            double emax = bad ? INFINITY : (double)emax_f;
+            double emax = (racc < INFINITY) ? (double)emax_f : INFINITY;
             double sum_clip_new = sum_clip;
 
             // ---- phase 2: coupled volume fractions (core.py:431-436) --------------------
@@ -570,8 +583,7 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                 sum_clip_new = sc_;
                 mean = se_ / sc_;
                 pref = sh.st[2].s * gbm_scale;
-                float ef = 0.0f;
-                bool badf = false;
+                float ef = 0.0f, rf = 0.0f;
 #pragma unroll
                 for (int j = 0; j < MAXQ; ++j) {  // k4 (FSAL), error
                     const int64_t g = ((int64_t)warp + j * INT_WARPS) * 32 + lane;
@@ -580,11 +592,12 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                         kf_nxt[g] = k4;
                         f_nxt[g] = k2[j];
                         const double err = h * (k1[j] + BS_E4 * k4);
-                        ef = fmaxf(ef, err_ratio(err, k2[j], atol_abs, relw));
-                        badf |= not_finite(k4) | not_finite(k2[j]);
+                        const float r = err_ratio(err, k2[j], atol_abs, relw);
+                        ef = fmaxf(ef, r);
+                        rf += r;
                     }
                 }
-                emax = badf ? INFINITY : fmax(emax, (double)ef);
+                emax = (rf < INFINITY) ? fmax(emax, (double)ef) : INFINITY;
             } else if (f_active) {
                 // generic path for ensembles too large for the register path: the same four
                 // sweeps through memory (E2 -> k2 -> error combination, E3 -> new fraction)
@@ -640,19 +653,19 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                 sum_clip_new = sc_;
                 mean = se_ / sc_;
                 pref = sh.st[2].s * gbm_scale;
-                float ef = 0.0f;
-                bool badf = false;
+                float ef = 0.0f, rf = 0.0f;
                 for (int64_t q = warp; q < n_chunks; q += INT_WARPS) {  // k4 (FSAL), error
                     const int64_t g = q * 32 + lane;
                     if (g < N) {
                         const double k4 = pref * (fs[g] / sumc) * (mean - E4[g]);
                         kf_nxt[g] = k4;
                         const double err = h * (acce[g] + BS_E4 * k4);
-                        ef = fmaxf(ef, err_ratio(err, fnew_s[g], atol_abs, relw));
-                        badf |= not_finite(k4) | not_finite(fnew_s[g]);
+                        const float r = err_ratio(err, fnew_s[g], atol_abs, relw);
+                        ef = fmaxf(ef, r);
+                        rf += r;
                     }
                 }
-                emax = badf ? INFINITY : fmax(emax, (double)ef);
+                emax = (rf < INFINITY) ? fmax(emax, (double)ef) : INFINITY;
             }
             emax = block_max<INT_BLOCK>(emax, sh.red);
             emax = fmax(emax, sh.errF);

@@ -186,7 +186,7 @@ def _integrate_minerals(minerals, params, deformation_gradients, get_velocity_gr
         S, 1, N, P(meta[0]), P(meta[1]), P(meta[2]), P(meta[3]), P(vf),
         P(meta_host[1]), P(meta_host[2]), P(meta_host[3]),
         P(F), P(o_soa), P(f), P(o_soa), P(f), P(t0), P(t1), int(kind), int(nodes.shape[0]), P(Ln),
-        ctypes.byref(p), ctypes.byref(tol), P(h_io),
+        ctypes.byref(p), ctypes.byref(tol), P(h_io), None,
         P(stats[0]), P(stats[1]), P(stats[2]), P(stats[3]), P(ws), ws_bytes, st))
     _lib.check(lib.drex_unpack_soa_f64(P(o_soa), P(o_aos), S, N, st))
     stats_h = stats.cpu().numpy()
