@@ -57,7 +57,14 @@ struct GrainProbe {  // optional intermediates for drex_grain_probe_f64
 
 // a: orientation (already clipped by the caller where the reference clips),
 // D: symmetric strain rate (D/smax), L: velocity gradient (L/smax).
-template <bool PROBE>
+// MODE selects what is decided at compile time (the integrator's hot loop is instantiated
+// once per variant so that only that variant's code sits in the instruction cache):
+//   0 runtime dispatch on fc, 1 olivine with the default exponents, 2 olivine with generic
+//   exponents, 3 enstatite.
+constexpr int GRAIN_RUNTIME = 0, GRAIN_OLIVINE_DEFAULT = 1, GRAIN_OLIVINE_GENERIC = 2,
+              GRAIN_ENSTATITE = 3;
+
+template <bool PROBE, int MODE = GRAIN_RUNTIME>
 __device__ __forceinline__ void grain_rhs(const double (&a)[9], const double (&D)[9],
                                           const double (&L)[9], const FabricConsts &fc,
                                           GrainOut &out, GrainProbe *probe) {
@@ -82,8 +89,11 @@ __device__ __forceinline__ void grain_rhs(const double (&a)[9], const double (&D
     double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;  // relative slip rates by system
     double w0 = 0.0, w1 = 0.0, w2 = 0.0;            // |gamma_i|^(p/n) for i = 0..2
     const bool all_zero = (I0 == 0.0) & (I1 == 0.0) & (I2 == 0.0) & (I3 == 0.0);
+    const bool olivine = (MODE == GRAIN_RUNTIME) ? (fc.phase == 0) : (MODE != GRAIN_ENSTATITE);
+    const bool default_exponents =
+        (MODE == GRAIN_RUNTIME) ? (fc.default_exponents != 0) : (MODE == GRAIN_OLIVINE_DEFAULT);
 
-    if (fc.phase == 0) {
+    if (olivine) {
         // the three finite-CRSS systems (x, y, z); z is natural index 2 or 3 (CTA-uniform)
         const bool inf3 = fc.inf_index == 3;
         const double vz = inf3 ? I2 : I3;
@@ -102,7 +112,7 @@ __device__ __forceinline__ void grain_rhs(const double (&a)[9], const double (&D
         const double qx = pre * ux, qy = pre * uy, qz = pre * uz;
         const double ax = fabs(qx), ay = fabs(qy), az = fabs(qz);
         double rx, ry, rz_, px, py, pz;  // q|q|^(n-1) and |q|^p
-        if (fc.default_exponents) {
+        if (default_exponents) {
             const double sx = sqrt(ax), sy = sqrt(ay), sz = sqrt(az);
             rx = qx * (ax * ax * sx); ry = qy * (ay * ay * sy); rz_ = qz * (az * az * sz);
             px = ax * sx; py = ay * sy; pz = az * sz;
@@ -170,7 +180,7 @@ __device__ __forceinline__ void grain_rhs(const double (&a)[9], const double (&D
 
     // strain energy over slip systems 0..2 in natural order (core.py:674-684)
     double energy = 0.0;
-    if (fc.phase == 0) {
+    if (olivine) {
         const double gp = pow_nonneg(fabs(gamma0), fc.p_over_n);
         const double rho0 = fc.rho_pref[0] * (w0 * gp);
         const double rho1 = fc.rho_pref[1] * (w1 * gp);

@@ -31,6 +31,8 @@
 #include "drex_derivatives.cuh"
 #include "drex_grain.cuh"
 
+#include <type_traits>
+
 namespace drex {
 
 constexpr int INT_BLOCK = 512;
@@ -214,10 +216,14 @@ __device__ __forceinline__ void clip9(double (&a)[9]) {
 }
 
 // Rotation rate (already multiplied by strain_rate_max, minerals.py:450) and strain
-// energy of one grain at one stage, for any supported regime.
+// energy of one grain at one stage.  MODE is a GRAIN_* constant for the dislocation
+// regimes, or STAGE_OTHER for the regimes without slip (0, 1, 7).
+constexpr int STAGE_OTHER = 4;
+
+template <int MODE>
 __device__ __forceinline__ void stage_rhs(const double (&a)[9], const StageFlow &sf, int regime,
                                           const FabricConsts &fc, double (&k)[9], double &energy) {
-    if (regime == 4 || regime == 6) {
+    if (MODE != STAGE_OTHER && (MODE != GRAIN_RUNTIME || regime == 4 || regime == 6)) {
         double D[9], L[9];
 #pragma unroll
         for (int c = 0; c < 9; ++c) {
@@ -225,7 +231,7 @@ __device__ __forceinline__ void stage_rhs(const double (&a)[9], const StageFlow 
             L[c] = sf.Ls[c];
         }
         GrainOut out;
-        grain_rhs<false>(a, D, L, fc, out, nullptr);
+        grain_rhs<false, MODE>(a, D, L, fc, out, nullptr);
         const double sc = (regime == 6) ? 0.3 * sf.s : sf.s;  // core.py:459
 #pragma unroll
         for (int c = 0; c < 9; ++c) k[c] = sc * out.da[c];
@@ -355,7 +361,7 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                     fn = ok ? f_in[gn] : 0.0;
                 }
                 clip9(a);
-                stage_rhs(a, sh.st[2], regime, fc, k, e);
+                stage_rhs<GRAIN_RUNTIME>(a, sh.st[2], regime, fc, k, e);
                 if (g < N) {
 #pragma unroll
                     for (int c = 0; c < 9; ++c) k_cur[c * N + g] = k[c];
@@ -459,6 +465,8 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
             float emax_f = 0.0f, racc = 0.0f;  // max and sum of the error ratios
 
             // ---- phase 1: every grain through all three stages, no synchronisation --------
+            auto phase1 = [&](auto mode_tag) {
+            constexpr int MODE = decltype(mode_tag)::value;
             for (int64_t q = warp; q < n_chunks; q += INT_WARPS) {
                 const int64_t g = q * 32 + lane;
                 const bool full = use_bulk && (q * 32 + 32 <= N);
@@ -492,7 +500,7 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
 #pragma unroll 1
                 for (int stg = 0; stg < 3; ++stg) {
                     clip9(st);
-                    stage_rhs(st, sh.st[stg], regime, fc, k, e);
+                    stage_rhs<MODE>(st, sh.st[stg], regime, fc, k, e);
                     if (f_active && live) p2[stg][g] = e;  // E2, E3, E4
                     if (stg == 2) break;
                     const double cb = (stg == 0) ? (h * BS_B2) : (h * BS_B3);
@@ -524,6 +532,12 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                     }
                 }
             }
+            };
+            // one instantiation per variant: only that variant's code is in the hot loop
+            if (regime != 4 && regime != 6) phase1(std::integral_constant<int, STAGE_OTHER>{});
+            else if (fc.phase != 0) phase1(std::integral_constant<int, GRAIN_ENSTATITE>{});
+            else if (fc.default_exponents) phase1(std::integral_constant<int, GRAIN_OLIVINE_DEFAULT>{});
+            else phase1(std::integral_constant<int, GRAIN_OLIVINE_GENERIC>{});
             n_rhs += 3;
             double emax = (racc < INFINITY) ? (double)emax_f : INFINITY;
             double sum_clip_new = sum_clip;
