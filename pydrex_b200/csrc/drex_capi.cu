@@ -244,7 +244,7 @@ size_t drex_integrate_workspace_bytes(int64_t S, int64_t N, int device) {
     int slots = integrate_slots(device);
     if (slots < 1) slots = 1;
     if ((int64_t)slots > S) slots = (int)S;
-    const size_t slot_bytes = align_up((size_t)drex::SLOT_ARRAYS * (size_t)N * sizeof(double), 256);
+    const size_t slot_bytes = align_up((size_t)drex::SLOT_ARRAYS * (size_t)((N + 31) / 32 * 32) * sizeof(double), 256);
     return 256 + (size_t)slots * slot_bytes;
 }
 
@@ -280,7 +280,7 @@ int drex_integrate_f64(int64_t S, int64_t P, int64_t N, const int32_t *sys_parti
     int slots = integrate_slots(device);
     if (slots < 1) return fail(DREX_E_CUDA, "could not query occupancy of the integrator kernel");
     if ((int64_t)slots > S) slots = (int)S;
-    const size_t slot_bytes = align_up((size_t)drex::SLOT_ARRAYS * (size_t)N * sizeof(double), 256);
+    const size_t slot_bytes = align_up((size_t)drex::SLOT_ARRAYS * (size_t)((N + 31) / 32 * 32) * sizeof(double), 256);
     const size_t need = 256 + (size_t)slots * slot_bytes;
     if (!workspace || workspace_bytes < need)
         return fail(DREX_E_WORKSPACE, "drex_integrate_f64: workspace too small (%zu < %zu)",
@@ -305,8 +305,6 @@ int drex_integrate_f64(int64_t S, int64_t P, int64_t N, const int32_t *sys_parti
     int smem_arrays = 0;
     const size_t dyn_smem = integrate_smem_bytes(device, N, &smem_arrays);
     A.smem_arrays = smem_arrays;
-    // TMA bulk copies need 16 B aligned rows: even N and 16 B aligned base pointers
-    A.bulk_ok = (N % 2 == 0) && ((uintptr_t)o_in % 16 == 0) && ((uintptr_t)workspace % 16 == 0);
     DREX_CUDA_CHECK(cudaFuncSetAttribute(drex::integrate_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
     DREX_CUDA_CHECK(cudaMemsetAsync(workspace, 0, 256, st));

@@ -69,14 +69,17 @@ struct IntegrateArgs {
     int64_t slot_doubles;  // per-CTA scratch size in doubles
     int *queue;            // atomic work counter, zeroed before launch
     int smem_arrays;       // how many of the 4 fraction-stage arrays live in shared memory
-    int bulk_ok;           // 1: SoA rows are 16 B aligned -> TMA bulk staging allowed
 };
 
-// per-CTA global scratch layout, in units of N doubles
-constexpr int SLOT_OA = 0, SLOT_OB = 9, SLOT_KA = 18, SLOT_KB = 27;  // orientation ping-pong, FSAL k
+// per-CTA global scratch layout, in units of Npad = 32 * ceil(N / 32) doubles.
+// YK buffers hold the running state in CHUNKED SoA: [chunk][row 0..17][32 grains], rows 0-8
+// the orientation and 9-17 its FSAL slope, so that one chunk is one contiguous 4608 B block
+// = one TMA bulk copy.
+constexpr int SLOT_YKA = 0, SLOT_YKB = 18;
 constexpr int SLOT_FA = 36, SLOT_FB = 37, SLOT_KFA = 38, SLOT_KFB = 39;
 constexpr int SLOT_P2 = 40;  // 4 fraction-stage arrays when they do not fit in shared memory
 constexpr int SLOT_ARRAYS = 44;
+constexpr int CHUNK_DOUBLES = 18 * 32;
 
 // ---- TMA bulk copy + mbarrier (sm_90+/sm_100a PTX) ------------------------------------
 __device__ __forceinline__ uint32_t smem_addr(const void *p) {
@@ -197,22 +200,19 @@ __device__ inline void fill_stage_flow(StageFlow &sf, const double *L) {
         }
 }
 
-// |x| > 1 on the integer pipe (the FP64 pipe is the bottleneck; clipping almost never fires)
-__device__ __forceinline__ bool exceeds_one(double x) {  // |x| >= 1 (conservative, one compare)
-    return ((uint32_t)__double2hiint(x) & 0x7fffffffu) >= 0x3ff00000u;
+// Clip to [-1, 1] (utils.py:187) on the integer pipe: the FP64 pipe is the bottleneck and
+// the clip almost never fires.  |x| >= 1 (including inf/NaN) becomes +-1 exactly; a NaN
+// state is still caught by the error test through the unclipped new state.
+__device__ __forceinline__ double clip_int(double x) {
+    const uint32_t hi = (uint32_t)__double2hiint(x);
+    const bool big = (hi & 0x7fffffffu) >= 0x3ff00000u;
+    const int nhi = big ? (int)((hi & 0x80000000u) | 0x3ff00000u) : (int)hi;
+    const int nlo = big ? 0 : __double2loint(x);
+    return __hiloint2double(nhi, nlo);
 }
-
-// clip the nine entries to [-1, 1] (utils.py:187) only when some entry needs it
 __device__ __forceinline__ void clip9(double (&a)[9]) {
-    bool any = false;
 #pragma unroll
-    for (int c = 0; c < 9; ++c) any |= exceeds_one(a[c]);
-    // warp-uniform branch: without the vote the compiler predicates the (almost never
-    // needed) clip sequence and issues it for every grain
-    if (__any_sync(0xffffffffu, any)) {
-#pragma unroll
-        for (int c = 0; c < 9; ++c) a[c] = clip1(a[c]);
-    }
+    for (int c = 0; c < 9; ++c) a[c] = clip_int(a[c]);
 }
 
 // Rotation rate (already multiplied by strain_rate_max, minerals.py:450) and strain
@@ -276,11 +276,10 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
     const int64_t Npad = (N + 31) / 32 * 32;
     // stage energies (and the generic path's clipped fractions): shared memory while they
     // fit, global scratch otherwise
-    double *p2[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-        p2[i] = (i < A.smem_arrays) ? p2_smem + i * Npad : slot + (SLOT_P2 + i) * N;
-    double *E2 = p2[0], *E3 = p2[1], *E4 = p2[2], *fs = p2[3];
+    double *E2 = (0 < A.smem_arrays) ? p2_smem : slot + (SLOT_P2 + 0) * Npad;
+    double *E3 = (1 < A.smem_arrays) ? p2_smem + 1 * Npad : slot + (SLOT_P2 + 1) * Npad;
+    double *E4 = (2 < A.smem_arrays) ? p2_smem + 2 * Npad : slot + (SLOT_P2 + 2) * Npad;
+    double *fs = (3 < A.smem_arrays) ? p2_smem + 3 * Npad : slot + (SLOT_P2 + 3) * Npad;
 
     uint64_t *mbar = &sh.mbar[warp];
     uint32_t mbar_parity = 0;
@@ -311,12 +310,10 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
         const bool f_active = (regime == 4 || regime == 6) && fc.phase == 0 && gbm_scale != 0.0;
         const double relw = A.tol.atol_rel + A.tol.rtol, atol_abs = A.tol.atol_abs;
 
-        const double *o_cur = o_in;
+        double *yk_cur = slot + SLOT_YKA * Npad, *yk_nxt = slot + SLOT_YKB * Npad;
         const double *f_cur = f_in;
-        double *o_nxt = slot + SLOT_OA * N;
-        double *k_cur = slot + SLOT_KA * N, *k_nxt = slot + SLOT_KB * N;
-        double *f_nxt = slot + SLOT_FA * N;
-        double *kf_cur = slot + SLOT_KFA * N, *kf_nxt = slot + SLOT_KFB * N;
+        double *f_nxt = slot + SLOT_FA * Npad;
+        double *kf_cur = slot + SLOT_KFA * Npad, *kf_nxt = slot + SLOT_KFB * Npad;
 
         // ---- initial slope at t0 (one right-hand side) --------------------------------
         if (tid == 0) {
@@ -360,11 +357,14 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                     for (int c = 0; c < 9; ++c) an[c] = ok ? o_in[c * N + gn] : 0.0;
                     fn = ok ? f_in[gn] : 0.0;
                 }
+                double *blk = yk_cur + q * CHUNK_DOUBLES + lane;
+#pragma unroll
+                for (int c = 0; c < 9; ++c) blk[c * 32] = a[c];  // idle lanes of the tail: zeros
                 clip9(a);
                 stage_rhs<GRAIN_RUNTIME>(a, sh.st[2], regime, fc, k, e);
-                if (g < N) {
 #pragma unroll
-                    for (int c = 0; c < 9; ++c) k_cur[c * N + g] = k[c];
+                for (int c = 0; c < 9; ++c) blk[(9 + c) * 32] = k[c];
+                if (g < N) {
                     if (f_active) E4[g] = e;
                     sumc += xc;
                     sume += xc * e;
@@ -401,29 +401,23 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
         bool done = (span == 0.0);
         bool last_rejected = false;
         double h_carry = 0.0;
-        const bool use_bulk = A.bulk_ok != 0;
 
         // ---- adaptive steps -------------------------------------------------------------
         while (!done) {
-            __syncthreads();  // k_cur / kf_cur / o_cur of the previous step are complete
+            __syncthreads();  // the state buffers of the previous step are complete
             if (n_acc + n_rej >= A.tol.max_steps) {
                 status = 1;  // DREX_STATUS_MAX_STEPS
                 break;
             }
             auto issue_chunk = [&](int64_t q) {
-                // one elected lane fetches the 18 rows (256 B each) of chunk q into rows 0-17;
-                // every operand is warp-uniform, so the copies issue from uniform registers
+                // one elected lane fetches chunk q (18 rows x 256 B, contiguous) into rows 0-17
                 if (lane == 0) {
-                    mbar_expect_tx(mbar, 18u * 256u);
-#pragma unroll
-                    for (int c = 0; c < 9; ++c) {
-                        bulk_g2s(stage + c * 32, o_cur + (int64_t)c * N + q * 32, 256u, mbar);
-                        bulk_g2s(stage + (9 + c) * 32, k_cur + (int64_t)c * N + q * 32, 256u, mbar);
-                    }
+                    mbar_expect_tx(mbar, (uint32_t)(CHUNK_DOUBLES * sizeof(double)));
+                    bulk_g2s(stage, yk_cur + q * CHUNK_DOUBLES, (uint32_t)(CHUNK_DOUBLES * sizeof(double)), mbar);
                 }
             };
             // prefetch this warp's first chunk while the stage flows are being set up
-            if (use_bulk && warp < n_chunks && (int64_t)warp * 32 + 32 <= N) issue_chunk(warp);
+            if (warp < n_chunks) issue_chunk(warp);
 
             // stage flows at t + h/2, t + 3h/4, t + h (three lanes), then F by lane 0
             if (tid < 3) {
@@ -469,23 +463,13 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
             constexpr int MODE = decltype(mode_tag)::value;
             for (int64_t q = warp; q < n_chunks; q += INT_WARPS) {
                 const int64_t g = q * 32 + lane;
-                const bool full = use_bulk && (q * 32 + 32 <= N);
                 const int64_t qn = q + INT_WARPS;
-                const bool next_full = use_bulk && qn < n_chunks && (qn * 32 + 32 <= N);
                 const bool live = g < N;
                 double *sa = stage + lane, *sk = stage + 9 * 32 + lane;
                 double *sy = stage + 18 * 32 + lane, *se = stage + 27 * 32 + lane;
                 double k[9], st[9], e = 0.0;
-                if (full) {
-                    mbar_wait(mbar, mbar_parity);
-                    mbar_parity ^= 1u;
-                } else {  // ragged tail (or unaligned rows): plain loads; idle lanes get zeros
-#pragma unroll
-                    for (int c = 0; c < 9; ++c) {
-                        sa[c * 32] = live ? o_cur[c * N + g] : 0.0;
-                        sk[c * 32] = live ? k_cur[c * N + g] : 0.0;
-                    }
-                }
+                mbar_wait(mbar, mbar_parity);
+                mbar_parity ^= 1u;
 #pragma unroll
                 for (int c = 0; c < 9; ++c) {
                     const double ac = sa[c * 32], kc = sk[c * 32];
@@ -501,7 +485,10 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                 for (int stg = 0; stg < 3; ++stg) {
                     clip9(st);
                     stage_rhs<MODE>(st, sh.st[stg], regime, fc, k, e);
-                    if (f_active && live) p2[stg][g] = e;  // E2, E3, E4
+                    if (f_active && live) {
+                        double *Ep = (stg == 0) ? E2 : ((stg == 1) ? E3 : E4);
+                        Ep[g] = e;
+                    }
                     if (stg == 2) break;
                     const double cb = (stg == 0) ? (h * BS_B2) : (h * BS_B3);
                     const double ce = (stg == 0) ? BS_E2 : BS_E3;
@@ -516,10 +503,11 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                     if (stg == 0) {
                         // rows 0-17 are free now: fetch the next chunk behind stages 3 and 4
                         __syncwarp();
-                        if (next_full) issue_chunk(qn);
+                        if (qn < n_chunks) issue_chunk(qn);
                     }
                 }
-                if (live) {
+                {
+                    double *blk = yk_nxt + q * CHUNK_DOUBLES + lane;  // idle tail lanes carry zeros
 #pragma unroll
                     for (int c = 0; c < 9; ++c) {
                         const double yn = sy[c * 32];
@@ -527,8 +515,8 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                         const float r = err_ratio(err, yn, atol_abs, relw);
                         emax_f = fmaxf(emax_f, r);
                         racc += r;  // any non-finite k or y_new makes err, hence r, non-finite
-                        o_nxt[c * N + g] = yn;
-                        k_nxt[c * N + g] = k[c];
+                        blk[c * 32] = yn;
+                        blk[(9 + c) * 32] = k[c];
                     }
                 }
             }
@@ -702,16 +690,13 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                 h_carry = h_next;
                 sum_clip = sum_clip_new;
                 // swap ping-pong buffers
-                const double *o_old = o_cur;
-                o_cur = o_nxt;
-                o_nxt = (o_old == o_in) ? slot + SLOT_OB * N : const_cast<double *>(o_old);
-                double *kt = k_cur;
-                k_cur = k_nxt;
-                k_nxt = kt;
+                double *ykt = yk_cur;
+                yk_cur = yk_nxt;
+                yk_nxt = ykt;
                 if (f_active) {
                     const double *f_old = f_cur;
                     f_cur = f_nxt;
-                    f_nxt = (f_old == f_in) ? slot + SLOT_FB * N : const_cast<double *>(f_old);
+                    f_nxt = (f_old == f_in) ? slot + SLOT_FB * Npad : const_cast<double *>(f_old);
                     double *kft = kf_cur;
                     kf_cur = kf_nxt;
                     kf_nxt = kft;
@@ -791,9 +776,10 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
             {
                 const int64_t g0 = (int64_t)warp * 32 + lane;
                 const bool ok = warp < n_chunks && g0 < N;
-                const double *src = (slide_mask & 1u) ? o_in : o_cur;
+                const bool sl = (slide_mask & 1u) != 0;
+                const double *blk = yk_cur + (int64_t)warp * CHUNK_DOUBLES + lane;
 #pragma unroll
-                for (int c = 0; c < 9; ++c) an[c] = ok ? src[c * N + g0] : 0.0;
+                for (int c = 0; c < 9; ++c) an[c] = ok ? (sl ? o_in[c * N + g0] : blk[c * 32]) : 0.0;
             }
             int j = 0;
             for (int64_t q = warp; q < n_chunks; q += INT_WARPS, ++j) {
@@ -804,9 +790,10 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                 {
                     const int64_t gn = (q + INT_WARPS) * 32 + lane;
                     const bool ok = (q + INT_WARPS) < n_chunks && gn < N;
-                    const double *src = ((slide_mask >> (j + 1)) & 1u) ? o_in : o_cur;
+                    const bool sl = ((slide_mask >> (j + 1)) & 1u) != 0;
+                    const double *blk = yk_cur + (q + INT_WARPS) * CHUNK_DOUBLES + lane;
 #pragma unroll
-                    for (int c = 0; c < 9; ++c) an[c] = ok ? src[c * N + gn] : 0.0;
+                    for (int c = 0; c < 9; ++c) an[c] = ok ? (sl ? o_in[c * N + gn] : blk[c * 32]) : 0.0;
                 }
                 clip9(a);
                 if (g < N) {
@@ -821,7 +808,8 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                 const bool slide = fa < floor_v;
                 double a[9];
 #pragma unroll
-                for (int c = 0; c < 9; ++c) a[c] = slide ? o_in[c * N + g] : o_cur[c * N + g];
+                for (int c = 0; c < 9; ++c)
+                    a[c] = slide ? o_in[c * N + g] : yk_cur[(g >> 5) * CHUNK_DOUBLES + c * 32 + (g & 31)];
 #pragma unroll
                 for (int c = 0; c < 9; ++c) o_out[c * N + g] = clip1(a[c]);
                 fa = slide ? floor_v : fa;
