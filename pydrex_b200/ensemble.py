@@ -211,6 +211,100 @@ class ParticleEnsemble:
             self.total_steps += int(stats[2].sum())
         return self.stats[0]
 
+    def update_host(self, h_o, h_f, h_F, t0, t1, L_nodes, kind=_lib.L_CONSTANT, tol=None,
+                    h_stats=None, n_chunks=4):
+        """Advance particles whose state lives in (pinned) HOST memory in the reference's
+        layout and write the new state back: the call a geodynamics code makes once per
+        model time step (cf. the Fluidity coupling, examples/fluidity/corner2d).
+
+        `h_o` [S, N, 3, 3] (AoS like `Mineral.orientations[-1]`), `h_f` [S, N], `h_F` [S, 3, 3]
+        are CPU tensors updated IN PLACE; `t0`, `t1` [P] and `L_nodes` [P, K, 3, 3] are CPU or
+        device tensors; `h_stats` optional int32 [4, S] CPU tensor receiving status / n_rhs /
+        n_accept / n_reject.  The particles are cut into `n_chunks` groups and pipelined over
+        three streams so the host->device copy of group i+1, the integration of group i and
+        the device->host copy of group i-1 overlap (PCIe is full duplex).  Synchronises
+        before returning.
+        """
+        lib, torch = _lib.load(), self._torch
+        dev, f64 = self.device, torch.float64
+        S, N, K_ph = self.S, self.N, self.n_phases
+        if tol is None:
+            tol = self.tolerances()
+        if getattr(self, "_pipe", None) is None:
+            per = -(-self.P // n_chunks) * K_ph
+            self._pipe = {
+                "streams": [torch.cuda.Stream(device=dev) for _ in range(3)],
+                "aos": [torch.empty((per, N, 9), dtype=f64, device=dev) for _ in range(2)],
+            }
+        s_in, s_run, s_out = self._pipe["streams"]
+        main = torch.cuda.current_stream(dev)
+        t0 = torch.as_tensor(t0, dtype=f64).to(dev, non_blocking=True)
+        t1 = torch.as_tensor(t1, dtype=f64).to(dev, non_blocking=True)
+        L_nodes = torch.as_tensor(L_nodes, dtype=f64).to(dev, non_blocking=True)
+        if L_nodes.dim() == 3:
+            L_nodes = L_nodes[:, None]
+        K = int(L_nodes.shape[1])
+        L_nodes = L_nodes.reshape(self.P, K, 9).contiguous()
+        ready = torch.cuda.Event()
+        ready.record(main)
+        for st in (s_in, s_run, s_out):
+            st.wait_event(ready)
+        p = self.params
+        prm = _lib.DrexParams(float(p["stress_exponent"]), float(p["deformation_exponent"]),
+                              float(p["nucleation_efficiency"]), float(p["gbm_mobility"]),
+                              float(p["gbs_threshold"]))
+        if self._ws is None:
+            nbytes = lib.drex_integrate_workspace_bytes(S, N, dev.index or 0)
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        h_o3 = h_o.reshape(S, N, 9)
+        h_F2 = h_F.reshape(S, 9)
+        Pp = _lib.ptr
+        m, mh = self.meta, self.meta_host
+        per_p = -(-self.P // n_chunks)
+        out_done = [None, None]
+        for c in range(n_chunks):
+            p0, p1 = c * per_p, min(self.P, (c + 1) * per_p)
+            if p0 >= p1:
+                break
+            s0, s1 = p0 * K_ph, p1 * K_ph
+            n = s1 - s0
+            aos = self._pipe["aos"][c % 2][:n]
+            with torch.cuda.stream(s_in):
+                if out_done[c % 2] is not None:
+                    s_in.wait_event(out_done[c % 2])  # staging buffer free again
+                aos.copy_(h_o3[s0:s1], non_blocking=True)
+                self.f[s0:s1].copy_(h_f[s0:s1], non_blocking=True)
+                self.F[s0:s1].copy_(h_F2[s0:s1], non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(s_in)
+            with torch.cuda.stream(s_run):
+                s_run.wait_event(ev_in)
+                sp = _lib.stream_ptr(torch)
+                _lib.check(lib.drex_pack_soa_f64(Pp(aos), Pp(self.o[s0:s1]), n, N, sp))
+                _lib.check(lib.drex_integrate_f64(
+                    n, self.P, N, Pp(m[0][s0:s1]), Pp(m[1][s0:s1]), Pp(m[2][s0:s1]),
+                    Pp(m[3][s0:s1]), Pp(self.vol_frac[s0:s1]), Pp(mh[1][s0:s1]), Pp(mh[2][s0:s1]),
+                    Pp(mh[3][s0:s1]), Pp(self.F[s0:s1]), Pp(self.o[s0:s1]), Pp(self.f[s0:s1]),
+                    Pp(self.o[s0:s1]), Pp(self.f[s0:s1]), Pp(t0), Pp(t1), int(kind), K,
+                    Pp(L_nodes), ctypes.byref(prm), ctypes.byref(tol), Pp(self.h[s0:s1]), None,
+                    Pp(self.stats[0][s0:s1]), Pp(self.stats[1][s0:s1]), Pp(self.stats[2][s0:s1]),
+                    Pp(self.stats[3][s0:s1]), Pp(self._ws), self._ws.numel(), sp))
+                _lib.check(lib.drex_unpack_soa_f64(Pp(self.o[s0:s1]), Pp(aos), n, N, sp))
+                ev_run = torch.cuda.Event()
+                ev_run.record(s_run)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_run)
+                h_o3[s0:s1].copy_(aos, non_blocking=True)
+                h_f[s0:s1].copy_(self.f[s0:s1], non_blocking=True)
+                h_F2[s0:s1].copy_(self.F[s0:s1], non_blocking=True)
+                out_done[c % 2] = torch.cuda.Event()
+                out_done[c % 2].record(s_out)
+        if h_stats is not None:
+            with torch.cuda.stream(s_out):
+                h_stats.copy_(self.stats, non_blocking=True)
+        s_out.synchronize()
+        main.wait_stream(s_run)
+
     # -- diagnostics -----------------------------------------------------------------------
     def voigt_averages(self, elastic_tensors=None):
         """Voigt-averaged stiffness per particle, [P, 6, 6] (minerals.voigt_averages for the

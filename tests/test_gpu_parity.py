@@ -505,3 +505,32 @@ def test_full_size_invariants(drex):
     nt.assert_allclose(F, np.broadcast_to(expect, F.shape), atol=1e-9)
     # all particles share seedless L but different textures: step counts recorded
     assert ens.total_rhs > 0 and ens.total_steps >= 5 * ens.S
+
+
+def test_update_host_matches_resident_update(drex):
+    """The pipelined host-buffer call gives bit-identical state to the resident path."""
+    import torch
+
+    P, N = 10, 512
+    a = drex.ParticleEnsemble(P, N, TWO_PHASE, seed=3)
+    b = drex.ParticleEnsemble(P, N, TWO_PHASE, seed=3)
+    rng = np.random.default_rng(1)
+    Ls = rng.normal(size=(P, 3, 3))
+    Ls -= np.eye(3)[None] * np.trace(Ls, axis1=1, axis2=2)[:, None, None] / 3
+    Ls = torch.as_tensor(Ls)
+    h_o = b.orientations().reshape(b.S, N, 3, 3).cpu().pin_memory()
+    h_f = b.f.cpu().pin_memory()
+    h_F = b.F.reshape(b.S, 3, 3).cpu().pin_memory()
+    h_stats = torch.zeros((4, b.S), dtype=torch.int32).pin_memory()
+    for k in range(3):
+        t0 = torch.full((P,), 0.05 * k, dtype=torch.float64)
+        t1 = torch.full((P,), 0.05 * (k + 1), dtype=torch.float64)
+        a.h.zero_()  # same first trial step on both sides
+        b.h.zero_()
+        a.update(t0.cuda(), t1.cuda(), Ls)
+        b.update_host(h_o, h_f, h_F, t0, t1, Ls, h_stats=h_stats, n_chunks=3)
+        assert int(h_stats[0].abs().sum()) == 0
+        nt.assert_array_equal(h_o.numpy(), a.orientations().reshape(a.S, N, 3, 3).cpu().numpy())
+        nt.assert_array_equal(h_f.numpy(), a.f.cpu().numpy())
+        nt.assert_array_equal(h_F.numpy().reshape(a.S, 9), a.F.cpu().numpy())
+        nt.assert_array_equal(h_stats[1].numpy(), a.stats[1].cpu().numpy())
