@@ -144,20 +144,24 @@ def make_workload(name, P, n_steps, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.
 
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    The sampler runs from before the warm-up (nvidia-smi takes ~0.1 s to start) at 20 ms
+    intervals; only samples time-stamped inside [mark_start, mark_end] are reported."""
+
+    QUERY = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.t_start = self.t_end = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-i", str(self.index), "-lms", "100"],
+                 "-i", str(self.index), "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -168,27 +172,47 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark_start(self):
+        self.t_start = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
+
     def stop(self):
+        import datetime
+
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         self.thread.join(timeout=2)
-        sm, smax, reasons = [], None, set()
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.lines:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[1]))
-                smax = float(parts[2])
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(parts[1]), float(parts[2]), float(parts[3]), parts[4:8]))
             except ValueError:
                 continue
-            for name, val in zip(names, parts[4:8]):
+        inside = [r for r in rows if self.t_start - 0.01 <= r[0] <= self.t_end + 0.01]
+        window = "timed region"
+        if not inside and rows:  # region shorter than the sampling interval: nearest samples
+            mid = 0.5 * (self.t_start + self.t_end)
+            inside = sorted(rows, key=lambda r: abs(r[0] - mid))[:3]
+            window = "nearest samples (timed region shorter than the sampling interval)"
+        reasons = set()
+        for r in inside:
+            for name, val in zip(names, r[4]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median([r[1] for r in inside])) if inside else None,
+                "sm_max_mhz": inside[0][2] if inside else None,
+                "power_w_max": max(r[3] for r in inside) if inside else None,
+                "reasons": sorted(reasons), "samples": len(inside), "window": window,
+                "region_ms": 1e3 * (self.t_end - self.t_start)}
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -237,14 +261,15 @@ def run_gpu(args):
     S = ens.S
     # state + scratch exceed L2 (126 MB) by far, so consecutive steps cannot hit in L2
     state_bytes = S * N * 10 * 8
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for k in range(W):
         ens.update(t_lo[k], t_hi[k], L_dev[k], kind, tol, check=False)
     counters = torch.zeros((3,), dtype=torch.int64, device=dev)
     step_ms = []
-    sampler = ClockSampler(local_rank)
     barrier()
-    if rank == 0:
-        sampler.start()
+    sampler.mark_start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
     ev[0].record()
     for k in range(W, n_total):
@@ -252,6 +277,7 @@ def run_gpu(args):
         counters += ens.stats[1:4].sum(dim=1)  # n_rhs, n_accept, n_reject (torch, tiny)
         ev[k - W + 1].record()
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     total_ms = max_over_ranks(ev[0].elapsed_time(ev[K]))
     step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(K)]
@@ -437,7 +463,9 @@ def _cpu_worker(job):
 
 
 def cpu_run(args, n_particles, n_steps, cores):
-    """Time the CPU port on `cores` processes; returns (grain-steps/s, evals/s, info)."""
+    """Time the CPU port on `cores` worker processes (one particle per task, like the
+    reference's Pool.imap over particles); returns (grain-steps/s, evals/s, steps/s, wall).
+    The pool is started and warmed (imports, library load) before the clock starts."""
     import multiprocessing as mp
 
     from oracle import oracle
@@ -447,10 +475,14 @@ def cpu_run(args, n_particles, n_steps, cores):
     kind, tables, t_edges = make_workload(args.workload, n_particles, n_steps, seed=1000)
     jobs = [(8816 + 2 * p, N, n_steps, kind, [t[p] for t in tables],
              (t_edges[0][:, p], t_edges[1][:, p])) for p in range(n_particles)]
-    t0 = time.perf_counter()
+    warm = [(1, 64, 1, kind, [t[p % n_particles] for t in tables],
+             (t_edges[0][:, p % n_particles], t_edges[1][:, p % n_particles]))
+            for p in range(cores)]
     with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_cpu_worker, warm, chunksize=1)
+        t0 = time.perf_counter()
         out = pool.map(_cpu_worker, jobs, chunksize=1)
-    wall = time.perf_counter() - t0
+        wall = time.perf_counter() - t0
     nfev = sum(o[1] for o in out)
     nsteps = sum(o[2] for o in out)
     grain_steps = n_particles * 2 * N * n_steps
@@ -459,8 +491,8 @@ def cpu_run(args, n_particles, n_steps, cores):
 
 def cpu_baseline(args):
     cores = len(os.sched_getaffinity(0))
-    n_particles = max(cores, 8)
-    n_steps = 2
+    n_particles = 8 * cores  # ~10-20 s of wall time on all cores
+    n_steps = 4
     v, evals, internal, wall = cpu_run(args, n_particles, n_steps, cores)
     return {"value": v, "unit": "grain-steps/s", "cores": cores, "kind": "port",
             "grain_evals_per_s": evals, "grain_internal_steps_per_s": internal,
@@ -475,11 +507,10 @@ def run_reference(args):
         return
     cores = len(os.sched_getaffinity(0))
     K, W = args.steps, args.warmup
-    n_particles = max(cores, 8)
-    # bounded sample: each "step" advances n_particles particles through one outer interval
-    if W > 0:
-        cpu_run(args, n_particles, min(W, 1), cores)
-    n_steps = min(K, 3)
+    n_particles = 8 * cores
+    # bounded sample: each "step" advances n_particles particles through one outer interval;
+    # the warm-up is the pool warm-up inside cpu_run
+    n_steps = min(K, 4)
     v, evals, internal, wall = cpu_run(args, n_particles, n_steps, cores)
     sample = (f"{n_particles} particles x 2 phases x {args.grains} grains x {n_steps} outer steps "
               f"per timed run (bounded sample of the GPU arm's workload), oracle port "
