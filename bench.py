@@ -323,6 +323,16 @@ def run_gpu(args):
     bytes_per_attempt = 288.0 + 0.5 * (24.0 + 10 * 8.0 * 2)
     attempts = (n_acc + n_rej) * N / K
     hbm_gbs = bytes_per_attempt * attempts / (kernel_ms * 1e-3) / 1e9
+    # DRAM traffic of the integrator from the committed ncu capture (profiles/), scaled by
+    # right-hand sides per launch: the capture's launch and this run's launches differ only
+    # in how many evaluations the step-size control needed
+    traffic = None
+    try:
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r01_integrate_traffic.json")))
+        if (cap["workload"], cap["particles_per_gpu"], cap["grains"]) == (args.workload, P, N):
+            traffic = cap["dram_bytes_per_launch"] / cap["evals_per_launch"] * evals_per_launch
+    except (OSError, KeyError, ValueError):
+        pass
     cpu = None if args.no_cpu_baseline else cpu_baseline(args)
     line = {
         "metric": "grain-steps/s", "value": value, "unit": "grain-steps/s",
@@ -356,8 +366,11 @@ def run_gpu(args):
                     "frac": hbm_gbs / hbm_peak, "bytes_per_grain_attempt": bytes_per_attempt,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)"
                     if peaks else "fallback 6650 GB/s"},
-            "traffic": None,
+            "traffic": traffic,
+            "traffic_source": "profiles/r01_integrate_traffic.json (ncu --set full, dram__bytes_read+write "
+                              "per launch) scaled by evaluations per launch" if traffic else None,
         },
+        "step_ms": step_ms,
         "cpu_baseline": cpu,
         "clocks": clocks,
     }
