@@ -14,7 +14,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libdrex_b200.so")
+LIB_PATH = os.environ.get("PYDREX_B200_LIB", os.path.join(LIB_DIR, "libdrex_b200.so"))
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
 NVCC_FLAGS = [

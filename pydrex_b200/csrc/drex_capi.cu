@@ -109,7 +109,7 @@ size_t integrate_smem_bytes(int device, int64_t N, int *smem_arrays) {
     int optin = 0;
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     const size_t stage_bytes = (size_t)drex::INT_WARPS * drex::STAGE_DOUBLES * sizeof(double);
-    const size_t static_bytes = sizeof(drex::StepShared) + 256;
+    const size_t static_bytes = sizeof(drex::StepShared) + drex::MATH_TABLE_DOUBLES * sizeof(double) + 256;
     const size_t array_bytes = (size_t)((N + 31) / 32 * 32) * sizeof(double);
     size_t avail = (size_t)optin > stage_bytes + static_bytes ? (size_t)optin - stage_bytes - static_bytes : 0;
     int n = (int)(avail / array_bytes);

@@ -58,6 +58,9 @@ struct DerivArgs {
 
 __global__ void __launch_bounds__(DERIV_BLOCK)
 derivatives_grain_kernel(const DerivArgs A, const __grid_constant__ FabricTable T) {
+    __shared__ __align__(16) double mt[MATH_TABLE_DOUBLES];
+    load_math_tables(mt);
+    __syncthreads();
     const int64_t s = blockIdx.y;
     const int64_t g = (int64_t)blockIdx.x * DERIV_BLOCK + threadIdx.x;
     if (g >= A.N) return;
@@ -85,7 +88,7 @@ derivatives_grain_kernel(const DerivArgs A, const __grid_constant__ FabricTable 
     }
     const FabricConsts &fc = T.fab[A.fabric[s]];
     GrainOut out;
-    grain_rhs<false>(a, D, L, fc, out, nullptr);
+    grain_rhs<false>(a, D, L, fc, mt, out, nullptr);
     const double scale = (regime == 6) ? 0.3 : 1.0;  // core.py:459
 #pragma unroll
     for (int c = 0; c < 9; ++c) dst[c * A.N] = (regime == 6) ? scale * out.da[c] : out.da[c];
@@ -125,6 +128,9 @@ struct ProbeArgs {
 
 __global__ void __launch_bounds__(128)
 grain_probe_kernel(const ProbeArgs A, const __grid_constant__ FabricConsts fc) {
+    __shared__ __align__(16) double mt[MATH_TABLE_DOUBLES];
+    load_math_tables(mt);
+    __syncthreads();
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= A.n) return;
     double a[9], D[9], L[9];
@@ -136,7 +142,7 @@ grain_probe_kernel(const ProbeArgs A, const __grid_constant__ FabricConsts fc) {
     }
     GrainOut out;
     GrainProbe pr;
-    grain_rhs<true>(a, D, L, fc, out, &pr);
+    grain_rhs<true>(a, D, L, fc, mt, out, &pr);
     if (A.inv)
         for (int i = 0; i < 4; ++i) A.inv[g * 4 + i] = pr.inv[i];
     if (A.rates)

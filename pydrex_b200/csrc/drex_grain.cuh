@@ -21,6 +21,8 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+#include "drex_math.cuh"
+
 namespace drex {
 
 // Per-(phase, fabric) constants, built on the host (drex_capi.cu: make_fabric_consts).
@@ -38,14 +40,6 @@ struct FabricConsts {
     int pad_;
 };
 
-// x^y for x >= 0 with C pow() conventions at 0; exp(y log x) is accurate to
-// ~|y log x| * 2^-53 relative, far inside the 1e-10 parity bound.
-// log(0) = -inf makes x = 0 come out right for y != 0 without a per-thread branch; y is
-// a model exponent (uniform across the launch).
-__device__ __forceinline__ double pow_nonneg(double x, double y) {
-    return (y == 0.0) ? 1.0 : exp(y * log(x));
-}
-
 struct GrainOut {
     double da[9];  // orientation_change (core.py:601-642), dimensionless time
     double energy; // strain_energy (core.py:645-684)
@@ -56,7 +50,8 @@ struct GrainProbe {  // optional intermediates for drex_grain_probe_f64
 };
 
 // a: orientation (already clipped by the caller where the reference clips),
-// D: symmetric strain rate (D/smax), L: velocity gradient (L/smax).
+// D: symmetric strain rate (D/smax), L: velocity gradient (L/smax),
+// mt: the exp/log tables in shared memory (drex_math.cuh: load_math_tables).
 // MODE selects what is decided at compile time (the integrator's hot loop is instantiated
 // once per variant so that only that variant's code sits in the instruction cache):
 //   0 runtime dispatch on fc, 1 olivine with the default exponents, 2 olivine with generic
@@ -67,7 +62,8 @@ constexpr int GRAIN_RUNTIME = 0, GRAIN_OLIVINE_DEFAULT = 1, GRAIN_OLIVINE_GENERI
 template <bool PROBE, int MODE = GRAIN_RUNTIME>
 __device__ __forceinline__ void grain_rhs(const double (&a)[9], const double (&D)[9],
                                           const double (&L)[9], const FabricConsts &fc,
-                                          GrainOut &out, GrainProbe *probe) {
+                                          const double *__restrict__ mt, GrainOut &out,
+                                          GrainProbe *probe) {
     // D.a_r for the three crystal axes (rows of a)
     double Da0[3], Da1[3], Da2[3];
 #pragma unroll
@@ -117,10 +113,10 @@ __device__ __forceinline__ void grain_rhs(const double (&a)[9], const double (&D
             rx = qx * (ax * ax * sx); ry = qy * (ay * ay * sy); rz_ = qz * (az * az * sz);
             px = ax * sx; py = ay * sy; pz = az * sz;
         } else {
-            rx = qx * pow_nonneg(ax, fc.n_minus_1);
-            ry = qy * pow_nonneg(ay, fc.n_minus_1);
-            rz_ = qz * pow_nonneg(az, fc.n_minus_1);
-            px = pow_nonneg(ax, fc.p); py = pow_nonneg(ay, fc.p); pz = pow_nonneg(az, fc.p);
+            rx = qx * pow_nonneg(ax, fc.n_minus_1, mt);
+            ry = qy * pow_nonneg(ay, fc.n_minus_1, mt);
+            rz_ = qz * pow_nonneg(az, fc.n_minus_1, mt);
+            px = pow_nonneg(ax, fc.p, mt); py = pow_nonneg(ay, fc.p, mt); pz = pow_nonneg(az, fc.p, mt);
         }
         // the softest system slips at rate exactly 1 (core.py:567)
         g0 = x_max ? 1.0 : rx;
@@ -181,13 +177,13 @@ __device__ __forceinline__ void grain_rhs(const double (&a)[9], const double (&D
     // strain energy over slip systems 0..2 in natural order (core.py:674-684)
     double energy = 0.0;
     if (olivine) {
-        const double gp = pow_nonneg(fabs(gamma0), fc.p_over_n);
+        const double gp = pow_nonneg(fabs(gamma0), fc.p_over_n, mt);
         const double rho0 = fc.rho_pref[0] * (w0 * gp);
         const double rho1 = fc.rho_pref[1] * (w1 * gp);
-        energy = rho0 * exp(-fc.lambda * rho0 * rho0) + rho1 * exp(-fc.lambda * rho1 * rho1);
+        energy = rho0 * exp_tab(-fc.lambda * rho0 * rho0, mt) + rho1 * exp_tab(-fc.lambda * rho1 * rho1, mt);
         if (fc.inf_index == 3) {  // otherwise rho_2 = (1/inf)^(n-p) * ... = 0 contributes 0
             const double rho2 = fc.rho_pref[2] * (w2 * gp);
-            energy += rho2 * exp(-fc.lambda * rho2 * rho2);
+            energy += rho2 * exp_tab(-fc.lambda * rho2 * rho2, mt);
         }
     }
     if (all_zero) {  // core.py:721-722

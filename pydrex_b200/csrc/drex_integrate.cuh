@@ -35,7 +35,10 @@
 
 namespace drex {
 
-constexpr int INT_BLOCK = 512;
+#ifndef DREX_INT_BLOCK
+#define DREX_INT_BLOCK 512
+#endif
+constexpr int INT_BLOCK = DREX_INT_BLOCK;
 constexpr int INT_WARPS = INT_BLOCK / 32;
 // per-warp shared-memory stage, rows of 32 grains: 0-8 orientation and 9-17 FSAL slope (TMA
 // targets), 18-26 running new state, 27-35 running error combination.  Keeping the two
@@ -222,7 +225,8 @@ constexpr int STAGE_OTHER = 4;
 
 template <int MODE>
 __device__ __forceinline__ void stage_rhs(const double (&a)[9], const StageFlow &sf, int regime,
-                                          const FabricConsts &fc, double (&k)[9], double &energy) {
+                                          const FabricConsts &fc, const double *__restrict__ mt,
+                                          double (&k)[9], double &energy) {
     if (MODE != STAGE_OTHER && (MODE != GRAIN_RUNTIME || regime == 4 || regime == 6)) {
         double D[9], L[9];
 #pragma unroll
@@ -231,7 +235,7 @@ __device__ __forceinline__ void stage_rhs(const double (&a)[9], const StageFlow 
             L[c] = sf.Ls[c];
         }
         GrainOut out;
-        grain_rhs<false, MODE>(a, D, L, fc, out, nullptr);
+        grain_rhs<false, MODE>(a, D, L, fc, mt, out, nullptr);
         const double sc = (regime == 6) ? 0.3 * sf.s : sf.s;  // core.py:459
 #pragma unroll
         for (int c = 0; c < 9; ++c) k[c] = sc * out.da[c];
@@ -259,12 +263,17 @@ __device__ __forceinline__ float err_ratio(double err, double ynew, double atol_
 
 // Chunks of 32 grains a warp can keep in registers during the fraction stages and the
 // end-of-interval pass (fast path: N <= 32 * INT_WARPS * MAXQ = 5120 grains).
-constexpr int MAXQ = 10;
+#ifndef DREX_MAXQ
+#define DREX_MAXQ 10
+#endif
+constexpr int MAXQ = DREX_MAXQ;
 
 __global__ void __launch_bounds__(INT_BLOCK, 1)
 integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
     extern __shared__ __align__(128) double dyn_smem[];
     __shared__ StepShared sh;
+    __shared__ __align__(16) double math_tab[MATH_TABLE_DOUBLES];
+    load_math_tables(math_tab);
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
     const int64_t N = A.N;
@@ -361,7 +370,7 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
 #pragma unroll
                 for (int c = 0; c < 9; ++c) blk[c * 32] = a[c];  // idle lanes of the tail: zeros
                 clip9(a);
-                stage_rhs<GRAIN_RUNTIME>(a, sh.st[2], regime, fc, k, e);
+                stage_rhs<GRAIN_RUNTIME>(a, sh.st[2], regime, fc, math_tab, k, e);
 #pragma unroll
                 for (int c = 0; c < 9; ++c) blk[(9 + c) * 32] = k[c];
                 if (g < N) {
@@ -484,7 +493,7 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
 #pragma unroll 1
                 for (int stg = 0; stg < 3; ++stg) {
                     clip9(st);
-                    stage_rhs<MODE>(st, sh.st[stg], regime, fc, k, e);
+                    stage_rhs<MODE>(st, sh.st[stg], regime, fc, math_tab, k, e);
                     if (f_active && live) {
                         double *Ep = (stg == 0) ? E2 : ((stg == 1) ? E3 : E4);
                         Ep[g] = e;
