@@ -139,7 +139,7 @@ int drex_grain_helper_f64(int op, const double *in0, const double *in1, const do
 /* ---- Mineral.update_orientations (minerals.py:312-541) ---------------------------- */
 
 typedef struct drex_tolerances {
-    /* error weight of component i: atol_abs + (atol_rel + rtol) * max(|y_i|, |y_new_i|);
+    /* error weight of component i: atol_abs + (atol_rel + rtol) * |y_new_i|;
      * reference default (minerals.py:523-524): rtol 1e-6, atol 1e-4 + 1e-6 |y0_i|;
      * weighted MAX norm as in ODEPACK lsoda */
     double rtol;
@@ -149,7 +149,8 @@ typedef struct drex_tolerances {
                                0 selects the whole interval */
     double max_step_frac;   /* cap on the step as a fraction of |t1 - t0| (<= 0: none) */
     int32_t max_steps;      /* attempted steps per system before DREX_STATUS_MAX_STEPS */
-    int32_t method;         /* 0: Bogacki-Shampine 3(2) with FSAL */
+    int32_t method;         /* low byte 0: Bogacki-Shampine 3(2) with FSAL; bit 0x100 forces the
+                               through-memory fraction stages used for N > 5120 (testing aid) */
 } drex_tolerances_t;
 
 size_t drex_integrate_workspace_bytes(int64_t S, int64_t N, int device);

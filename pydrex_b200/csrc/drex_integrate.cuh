@@ -278,7 +278,7 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
     const int64_t N = A.N;
     const int64_t n_chunks = (N + 31) / 32;
-    const bool fast = n_chunks <= (int64_t)MAXQ * INT_WARPS;
+    const bool fast = n_chunks <= (int64_t)MAXQ * INT_WARPS && !(A.tol.method & 0x100);
     double *slot = A.scratch + (int64_t)blockIdx.x * A.slot_doubles;
     double *stage = dyn_smem + warp * STAGE_DOUBLES;  // [STAGE_ROWS][32] doubles of this warp
     double *p2_smem = dyn_smem + INT_WARPS * STAGE_DOUBLES;
@@ -536,6 +536,9 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
             else if (fc.default_exponents) phase1(std::integral_constant<int, GRAIN_OLIVINE_DEFAULT>{});
             else phase1(std::integral_constant<int, GRAIN_OLIVINE_GENERIC>{});
             n_rhs += 3;
+            // the new state was written through the generic proxy and is read by TMA (async
+            // proxy) in the next step
+            asm volatile("fence.proxy.async;" ::: "memory");
             double emax = (racc < INFINITY) ? (double)emax_f : INFINITY;
             double sum_clip_new = sum_clip;
 

@@ -534,3 +534,50 @@ def test_update_host_matches_resident_update(drex):
         nt.assert_array_equal(h_f.numpy(), a.f.cpu().numpy())
         nt.assert_array_equal(h_F.numpy().reshape(a.S, 9), a.F.cpu().numpy())
         nt.assert_array_equal(h_stats[1].numpy(), a.stats[1].cpu().numpy())
+
+
+def test_generic_memory_path_is_bit_identical(drex):
+    """Ensembles above 5120 grains use through-memory fraction stages instead of the
+    register-resident ones; forcing that path on a small ensemble must not change a bit.
+    Also covers N not a multiple of 32, odd N, and N > 5120 end to end."""
+    import torch
+
+    for N in (333, 1000):
+        a = drex.ParticleEnsemble(3, N, TWO_PHASE, seed=5)
+        b = drex.ParticleEnsemble(3, N, TWO_PHASE, seed=5)
+        L = torch.zeros((3, 3, 3), dtype=torch.float64)
+        L[:, 1, 0] = torch.tensor([2.0, 1.0, 3.0])
+        tol_a, tol_b = a.tolerances(), b.tolerances()
+        tol_b.method = 0x100
+        for k in range(3):
+            a.update(0.05 * k, 0.05 * (k + 1), L, tol=tol_a)
+            b.update(0.05 * k, 0.05 * (k + 1), L, tol=tol_b)
+        nt.assert_array_equal(a.o.cpu().numpy(), b.o.cpu().numpy())
+        nt.assert_array_equal(a.f.cpu().numpy(), b.f.cpu().numpy())
+        nt.assert_array_equal(a.stats.cpu().numpy(), b.stats.cpu().numpy())
+    # N = 6001 > 5120: the generic path for real; invariants + agreement with the oracle RHS
+    N = 6001
+    c = drex.ParticleEnsemble(2, N, TWO_PHASE, seed=9)
+    L = torch.zeros((2, 3, 3), dtype=torch.float64)
+    L[:, 0, 2] = 2.0
+    c.update(0.0, 0.05, L)
+    f = c.fractions().cpu().numpy()
+    nt.assert_allclose(f.sum(axis=-1), 1.0, atol=1e-12)
+    o = c.orientations().cpu().numpy()
+    assert np.abs(np.einsum("pkgij,pkglj->pkgil", o, o) - np.eye(3)).max() < 5e-3
+
+
+def test_backward_interval_and_status_codes(drex):
+    """t1 < t0 integrates backwards (LSODA allows it); max_steps exhaustion raises."""
+    m = drex.Mineral(n_grains=128, seed=4)
+    L = np.array([[0.0, 0, 0], [2, 0, 0], [0, 0, 0]])
+    o0, f0 = m.orientations[0].copy(), m.fractions[0].copy()
+    params = dict(OL_PARAMS, gbs_threshold=0.0)
+    F = m.update_orientations(params, np.eye(3), _const(L), (0.0, 0.1, lambda t: np.zeros(3)), **TIGHT)
+    F = m.update_orientations(params, F, _const(L), (0.1, 0.0, lambda t: np.zeros(3)), **TIGHT)
+    nt.assert_allclose(F, np.eye(3), atol=1e-9)
+    nt.assert_allclose(m.orientations[-1], o0, atol=1e-7)
+    nt.assert_allclose(m.fractions[-1], f0, rtol=1e-6)
+    with pytest.raises(drex.IterationError, match="maximum number"):
+        m.update_orientations(params, F, _const(L), (0.0, 1.0, lambda t: np.zeros(3)),
+                              rtol=1e-12, atol=1e-14, max_steps=5)
