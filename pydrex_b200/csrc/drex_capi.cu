@@ -453,22 +453,52 @@ int drex_misorientations_random_host(double low, double high, int system_a, int 
     return DREX_OK;
 }
 
-static size_t mindex_ws_layout(int64_t S, int64_t N, int n_ops, int tmax, size_t *off_counts,
-                               size_t *off_theory) {
-    size_t quats = align_up((size_t)S * (size_t)N * (size_t)n_ops * sizeof(float4), 256);
+// Bin thresholds for mindex_bin (drex_diagnostics.cuh): thr[b], b = 1..tmax, is the largest
+// float32 d with floor(2 * (double)(float)(acosf(d) * rad2deg_f)) >= b; thr[tmax + 1] the largest
+// d whose angle exceeds tmax.  Uses the host libm acosf, the function numpy/numba call for the
+// reference's float32 arrays (geometry.py:104-116).
+static void mindex_thresholds(int tmax, float *thr) {
+    const float rad2deg_f = (float)(180.0 / 3.14159265358979323846);
+    auto angle = [&](float d) { return 2.0 * (double)(float)(acosf(d) * rad2deg_f); };
+    thr[0] = 2.0f;  // unused
+    for (int b = 1; b <= tmax + 1; ++b) {
+        // condition C(d): b <= tmax ? angle(d) >= b : angle(d) > tmax ; monotone: true for small d
+        auto cond = [&](float d) { return b <= tmax ? angle(d) >= (double)b : angle(d) > (double)tmax; };
+        const double target = (b <= tmax ? b : tmax) * 0.5 * 3.14159265358979323846 / 180.0;
+        float d = (float)std::cos(target);
+        if (d < 0.0f) d = 0.0f;
+        if (d > 1.0f) d = 1.0f;
+        if (!cond(0.0f)) {  // unreachable even at d = 0 (angle(0) = 180)
+            thr[b] = -1.0f;
+            continue;
+        }
+        while (d > 0.0f && !cond(d)) d = std::nextafterf(d, -1.0f);
+        while (d < 1.0f && cond(std::nextafterf(d, 2.0f))) d = std::nextafterf(d, 2.0f);
+        thr[b] = d;
+    }
+}
+
+static size_t mindex_ws_layout(int64_t S, int64_t N, int n_store, int tmax, size_t *off_counts,
+                               size_t *off_theory, size_t *off_thr) {
+    size_t quats = align_up((size_t)S * (size_t)N * (size_t)n_store * sizeof(float4), 256);
     *off_counts = quats;
     size_t counts = align_up((size_t)S * (size_t)tmax * sizeof(unsigned long long), 256);
     *off_theory = quats + counts;
-    return quats + counts + align_up((size_t)tmax * sizeof(double), 256);
+    size_t theory = align_up((size_t)tmax * sizeof(double), 256);
+    *off_thr = quats + counts + theory;
+    return quats + counts + theory + align_up((size_t)(tmax + 2) * sizeof(float), 256);
 }
+
+// monoclinic / orthorhombic: identity + 3 rotations stored, 3 sign-flip reflections implied
+static inline bool reflect7(int a, int b) { return a == 2 && (b == 2 || b == 4); }
 
 size_t drex_mindex_workspace_bytes(int64_t S, int64_t N, int system_a, int system_b) {
     drex::SymOps ops;
     const int n_ops = build_symops(system_a, system_b, &ops);
     const int tmax = max_misorientation(system_a, system_b);
     if (n_ops < 0 || tmax < 0 || S <= 0 || N <= 0) return 256;
-    size_t a, b;
-    return mindex_ws_layout(S, N, n_ops, tmax, &a, &b);
+    size_t a, b, c;
+    return mindex_ws_layout(S, N, reflect7(system_a, system_b) ? 4 : n_ops, tmax, &a, &b, &c);
 }
 
 int drex_mindex_f32(const double *o_soa, int64_t S, int64_t N, int system_a, int system_b,
@@ -485,8 +515,10 @@ int drex_mindex_f32(const double *o_soa, int64_t S, int64_t N, int system_a, int
     if (S < 0 || N < 0) return fail(DREX_E_INVALID, "negative size");
     if (S == 0) return DREX_OK;
     if (!o_soa || !M) return fail(DREX_E_INVALID, "drex_mindex_f32: null pointer");
-    size_t off_counts, off_theory;
-    const size_t need = mindex_ws_layout(S, N, n_ops, tmax, &off_counts, &off_theory);
+    size_t off_counts, off_theory, off_thr;
+    const bool refl = reflect7(system_a, system_b);
+    const int n_store = refl ? 4 : n_ops;
+    const size_t need = mindex_ws_layout(S, N, n_store, tmax, &off_counts, &off_theory, &off_thr);
     if (!workspace || workspace_bytes < need)
         return fail(DREX_E_WORKSPACE, "drex_mindex_f32: workspace too small (%zu < %zu)",
                     workspace_bytes, need);
@@ -494,19 +526,26 @@ int drex_mindex_f32(const double *o_soa, int64_t S, int64_t N, int system_a, int
     float4 *quats = (float4 *)workspace;
     unsigned long long *cnt = (unsigned long long *)((char *)workspace + off_counts);
     double *theory = (double *)((char *)workspace + off_theory);
+    float *thr = (float *)((char *)workspace + off_thr);
+    float thr_host[drex::MAX_THETA + 2];
+    mindex_thresholds(tmax, thr_host);
     DREX_CUDA_CHECK(cudaMemsetAsync(cnt, 0, (size_t)S * tmax * sizeof(unsigned long long), st));
     DREX_CUDA_CHECK(cudaMemcpyAsync(theory, theory_host, tmax * sizeof(double), cudaMemcpyHostToDevice, st));
+    DREX_CUDA_CHECK(cudaMemcpyAsync(thr, thr_host, (tmax + 2) * sizeof(float), cudaMemcpyHostToDevice, st));
     if (N > 0) {
         dim3 gq((unsigned)((N + 127) / 128), (unsigned)S);
-        drex::mindex_quats_kernel<<<gq, 128, 0, st>>>(o_soa, N, quats, ops);
+        drex::mindex_quats_kernel<<<gq, 128, 0, st>>>(o_soa, N, quats, n_store, ops);
         DREX_CUDA_CHECK(cudaGetLastError());
         const int n_tiles = (int)((N + drex::MINDEX_TILE - 1) / drex::MINDEX_TILE);
         dim3 gp((unsigned)((int64_t)n_tiles * (n_tiles + 1) / 2), (unsigned)S);
+        if (refl) {
+            drex::mindex_pairs_reflect_kernel<<<gp, drex::MINDEX_TILE, 0, st>>>(quats, N, n_tiles, tmax, thr, cnt);
+        } else
         switch (n_ops) {
-        case 1: drex::mindex_pairs_kernel<1><<<gp, drex::MINDEX_TILE, 0, st>>>(quats, N, n_tiles, tmax, cnt); break;
-        case 7: drex::mindex_pairs_kernel<7><<<gp, drex::MINDEX_TILE, 0, st>>>(quats, N, n_tiles, tmax, cnt); break;
-        case 10: drex::mindex_pairs_kernel<10><<<gp, drex::MINDEX_TILE, 0, st>>>(quats, N, n_tiles, tmax, cnt); break;
-        case 16: drex::mindex_pairs_kernel<16><<<gp, drex::MINDEX_TILE, 0, st>>>(quats, N, n_tiles, tmax, cnt); break;
+        case 1: drex::mindex_pairs_kernel<1><<<gp, drex::MINDEX_TILE, 0, st>>>(quats, N, n_tiles, tmax, thr, cnt); break;
+        case 7: drex::mindex_pairs_kernel<7><<<gp, drex::MINDEX_TILE, 0, st>>>(quats, N, n_tiles, tmax, thr, cnt); break;
+        case 10: drex::mindex_pairs_kernel<10><<<gp, drex::MINDEX_TILE, 0, st>>>(quats, N, n_tiles, tmax, thr, cnt); break;
+        case 16: drex::mindex_pairs_kernel<16><<<gp, drex::MINDEX_TILE, 0, st>>>(quats, N, n_tiles, tmax, thr, cnt); break;
         default: return fail(DREX_E_INVALID, "unexpected symmetry operator count %d", n_ops);
         }
         DREX_CUDA_CHECK(cudaGetLastError());

@@ -4,8 +4,9 @@
 //      per grain the rotated stiffness is P S P^T with P the 6x6 matrix of products of
 //      direction cosines (equivalent to tensors.rotate + elastic_tensor_to_voigt,
 //      tensors.py:187-273, for tensors with the minor symmetries voigt_to_elastic_tensor
-//      builds), ~400 FMA instead of the reference's 3^8-term loop; one CTA per system,
-//      21 accumulators per thread, fixed-order block reduction.
+//      builds), ~500 FP64 FMA instead of the reference's 3^8-term loop; one CTA per system,
+//      21 accumulators per thread, fixed-order block reduction.  At 80 B and ~1000 flop per
+//      grain the kernel is FP64-bound, not HBM-bound (measured 59 % of the DFMA peak).
 //  mindex_*               diagnostics.misorientation_index (diagnostics.py:332-367) with
 //      stats.misorientation_hist (stats.py:83-127) and geometry.misorientation_angles
 //      (geometry.py:74-118): all pairs x all symmetry-operator pairs, tiled on chip; the
@@ -61,26 +62,25 @@ voigt_average_kernel(const double *__restrict__ o_soa, const double *__restrict_
                 Pm[I][A] = (A < 3) ? rpk * rql : rpk * rql + a[3 * l + p] * a[3 * k + q];
             }
         }
-        double Q[6][6];
+        int idx = 0;
 #pragma unroll
-        for (int I = 0; I < 6; ++I)
+        for (int I = 0; I < 6; ++I) {
+            double Q[6];  // row I of P S: only one row is live at a time (register pressure)
 #pragma unroll
             for (int B = 0; B < 6; ++B) {
                 double t = 0.0;
 #pragma unroll
                 for (int A = 0; A < 6; ++A) t += Pm[I][A] * Ssym[6 * A + B];
-                Q[I][B] = t;
+                Q[B] = t;
             }
-        int idx = 0;
-#pragma unroll
-        for (int I = 0; I < 6; ++I)
 #pragma unroll
             for (int J = I; J < 6; ++J) {
                 double t = 0.0;
 #pragma unroll
-                for (int B = 0; B < 6; ++B) t += Q[I][B] * Pm[J][B];
+                for (int B = 0; B < 6; ++B) t += Q[B] * Pm[J][B];
                 acc[idx++] += w * t;
             }
+        }
     }
     const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
@@ -165,18 +165,18 @@ __device__ inline void matrix_to_quat(const double *M_in, double *q) {
     for (int i = 0; i < 4; ++i) q[i] /= nrm;
 }
 
-// K1: transformed float32 quaternions, layout [S][N][n_ops] float4
+// K1: transformed float32 quaternions, layout [S][N][n_store] float4
 __global__ void __launch_bounds__(128)
 mindex_quats_kernel(const double *__restrict__ o_soa, int64_t N, float4 *__restrict__ quats,
-                    const __grid_constant__ SymOps ops) {
+                    int n_store, const __grid_constant__ SymOps ops) {
     const int64_t s = blockIdx.y;
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= N) return;
     double a[9], q[4];
     for (int c = 0; c < 9; ++c) a[c] = o_soa[s * 9 * N + c * N + g];
     matrix_to_quat(a, q);
-    float4 *dst = quats + (s * N + g) * ops.n;
-    for (int k = 0; k < ops.n; ++k) {
+    float4 *dst = quats + (s * N + g) * n_store;  // the sign-flip ops are not materialised
+    for (int k = 0; k < n_store; ++k) {
         double r[4];
         for (int i = 0; i < 4; ++i) {
             double t = 0.0;
@@ -187,23 +187,71 @@ mindex_quats_kernel(const double *__restrict__ o_soa, int64_t N, float4 *__restr
     }
 }
 
-// K2: pair tiles.  grid.x enumerates tile pairs (ti <= tj), grid.y = system.
-template <int NOPS>
-__global__ void __launch_bounds__(MINDEX_TILE)
-mindex_pairs_kernel(const float4 *__restrict__ quats, int64_t N, int n_tiles, int theta_max,
-                    unsigned long long *__restrict__ counts) {
-    __shared__ float4 qj[MINDEX_TILE * NOPS];
-    __shared__ unsigned int hist[MAX_THETA];
-    const int64_t s = blockIdx.y;
-    // decode (ti, tj), ti <= tj, from the linear upper-triangular index
-    int ti = 0, rem = blockIdx.x;
+// Bin index of a pair from its largest |dot| WITHOUT evaluating acos per pair.
+// The reference's chain is float32: a = acosf(d); h = a * rad2deg (float32); angle = 2 h
+// (float64); bin = floor(angle) (np.histogram with 1-degree bins).  Every step is monotone
+// in d, so for each integer b there is a float32 threshold thr[b] with angle >= b  <=>
+// d <= thr[b].  The host computes the thresholds with ITS libm acosf (the function numpy
+// and numba call), which makes the binning identical to the reference's, not merely
+// close; the device does a 8-step binary search over at most 181 thresholds.
+// thr[1..theta_max] as above; thr[theta_max + 1]: angle > theta_max (dropped, stats.py:127).
+__device__ __forceinline__ int mindex_bin(float d, const float *thr, int theta_max) {
+    // k = number of b in [1, theta_max + 1] with d <= thr[b]; thr is non-increasing in b
+    int lo = 0, hi = theta_max + 1;  // invariant: d <= thr[b] for b <= lo, d > thr[b] for b > hi
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (d <= thr[mid]) lo = mid; else hi = mid - 1;
+    }
+    if (lo > theta_max) return -1;             // outside the histogram range
+    return lo == theta_max ? theta_max - 1 : lo;  // right edge belongs to the last bin
+}
+
+// decode (ti, tj), ti <= tj, from the linear upper-triangular tile index
+__device__ __forceinline__ void mindex_tile(int linear, int n_tiles, int &ti, int &tj) {
+    ti = 0;
+    int rem = linear;
     while (rem >= n_tiles - ti) {
         rem -= n_tiles - ti;
         ++ti;
     }
-    const int tj = ti + rem;
+    tj = ti + rem;
+}
+
+// float32 product-then-sum exactly as numpy/numba evaluate np.sum(q1 * q2, axis=1) on
+// float32 arrays (geometry.py:104-112): rounded products, left-to-right rounded sums.
+__device__ __forceinline__ float dot4_ref(const float4 a, const float4 b) {
+    return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z)),
+                     __fmul_rn(a.w, b.w));
+}
+
+// The four dots (R a).b for R in {I, diag(1,-1,-1,1), diag(1,-1,1,-1), diag(1,1,-1,-1)}: sign
+// flips are exact in float32, so the four sums share their products and first partial sums
+// and are bit-identical to the reference's separately transformed quaternions.
+__device__ __forceinline__ float absmax_sign4(const float4 a, const float4 b, float best) {
+    const float p0 = __fmul_rn(a.x, b.x), p1 = __fmul_rn(a.y, b.y);
+    const float p2 = __fmul_rn(a.z, b.z), p3 = __fmul_rn(a.w, b.w);
+    const float sp = __fadd_rn(p0, p1), sm = __fsub_rn(p0, p1);
+    const float dI = __fadd_rn(__fadd_rn(sp, p2), p3);
+    const float d1 = __fadd_rn(__fsub_rn(sm, p2), p3);
+    const float d2 = __fsub_rn(__fadd_rn(sm, p2), p3);
+    const float d3 = __fsub_rn(__fsub_rn(sp, p2), p3);
+    return fmaxf(fmaxf(fmaxf(best, fabsf(dI)), fmaxf(fabsf(d1), fabsf(d2))), fabsf(d3));
+}
+
+// K2 (generic): all NOPS x NOPS operator pairs.  grid.x = tile pairs (ti <= tj), grid.y = system.
+template <int NOPS>
+__global__ void __launch_bounds__(MINDEX_TILE)
+mindex_pairs_kernel(const float4 *__restrict__ quats, int64_t N, int n_tiles, int theta_max,
+                    const float *__restrict__ thresholds, unsigned long long *__restrict__ counts) {
+    __shared__ float4 qj[MINDEX_TILE * NOPS];
+    __shared__ unsigned int hist[MAX_THETA];
+    __shared__ float thr[MAX_THETA + 2];
+    const int64_t s = blockIdx.y;
+    int ti, tj;
+    mindex_tile(blockIdx.x, n_tiles, ti, tj);
     const int tid = threadIdx.x;
     for (int b = tid; b < theta_max; b += MINDEX_TILE) hist[b] = 0u;
+    for (int b = tid; b < theta_max + 2; b += MINDEX_TILE) thr[b] = thresholds[b];
     const float4 *base = quats + s * N * NOPS;
     const int64_t j0 = (int64_t)tj * MINDEX_TILE;
     const int nj = (int)min((int64_t)MINDEX_TILE, N - j0);
@@ -216,31 +264,69 @@ mindex_pairs_kernel(const float4 *__restrict__ quats, int64_t N, int n_tiles, in
     }
     __syncthreads();
     if (i < N) {
-        const float rad2deg_f = 57.29577951308232f;
-        int jstart = (ti == tj) ? tid + 1 : 0;  // pairs (i, j) with i < j only (stats.py:113-115)
+        const int jstart = (ti == tj) ? tid + 1 : 0;  // pairs (i, j) with i < j only (stats.py:113-115)
         for (int jj = jstart; jj < nj; ++jj) {
             float best = 0.0f;  // max |dot| over operator pairs == min angle (geometry.py:102-118)
 #pragma unroll
-            for (int a = 0; a < NOPS; ++a) {
+            for (int a = 0; a < NOPS; ++a)
 #pragma unroll
-                for (int b = 0; b < NOPS; ++b) {
-                    const float4 v = qj[jj * NOPS + b];
-                    // float32 products and left-to-right float32 sum, no contraction
-                    float d = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(qi[a].x, v.x), __fmul_rn(qi[a].y, v.y)),
-                                                  __fmul_rn(qi[a].z, v.z)),
-                                        __fmul_rn(qi[a].w, v.w));
-                    d = fminf(1.0f, fmaxf(-1.0f, d));
-                    best = fmaxf(best, fabsf(d));
-                }
-            }
-            // correctly rounded float32 acos, float32 rad2deg, then 2 * (float64)
-            const float half_deg = __fmul_rn((float)acos((double)best), rad2deg_f);
-            const double ang = 2.0 * (double)half_deg;
-            if (ang >= 0.0 && ang <= (double)theta_max) {
-                int bin = (int)ang;
-                if (bin >= theta_max) bin = theta_max - 1;
-                atomicAdd(&hist[bin], 1u);
-            }
+                for (int b = 0; b < NOPS; ++b) best = fmaxf(best, fabsf(dot4_ref(qi[a], qj[jj * NOPS + b])));
+            const int bin = mindex_bin(fminf(best, 1.0f), thr, theta_max);  // clip (geometry.py:108)
+            if (bin >= 0) atomicAdd(&hist[bin], 1u);
+        }
+    }
+    __syncthreads();
+    for (int b = tid; b < theta_max; b += MINDEX_TILE)
+        if (hist[b]) atomicAdd(&counts[s * theta_max + b], (unsigned long long)hist[b]);
+}
+
+// K2 (monoclinic / orthorhombic): the 7 operations are identity, three "rotations" (stored
+// per grain as slots 1..3) and three diagonal sign matrices (geometry.py:133-150).  The
+// sign matrices with the identity form a group of exact float32 sign flips, so the 49
+// operator pairs collapse to 4 + 12 + 12 shared-product dots and 9 plain ones: 161 float
+// operations per pair instead of 343, with bit-identical maxima.  Slots per grain: 4.
+__global__ void __launch_bounds__(MINDEX_TILE)
+mindex_pairs_reflect_kernel(const float4 *__restrict__ quats, int64_t N, int n_tiles, int theta_max,
+                            const float *__restrict__ thresholds,
+                            unsigned long long *__restrict__ counts) {
+    __shared__ float4 qj[MINDEX_TILE * 4];
+    __shared__ unsigned int hist[MAX_THETA];
+    __shared__ float thr[MAX_THETA + 2];
+    const int64_t s = blockIdx.y;
+    int ti, tj;
+    mindex_tile(blockIdx.x, n_tiles, ti, tj);
+    const int tid = threadIdx.x;
+    for (int b = tid; b < theta_max; b += MINDEX_TILE) hist[b] = 0u;
+    for (int b = tid; b < theta_max + 2; b += MINDEX_TILE) thr[b] = thresholds[b];
+    const float4 *base = quats + s * N * 4;
+    const int64_t j0 = (int64_t)tj * MINDEX_TILE;
+    const int nj = (int)min((int64_t)MINDEX_TILE, N - j0);
+    for (int e = tid; e < nj * 4; e += MINDEX_TILE) qj[e] = base[j0 * 4 + e];
+    const int64_t i = (int64_t)ti * MINDEX_TILE + tid;
+    float4 q1 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = q1, v2 = q1, v3 = q1;
+    if (i < N) {
+        q1 = base[i * 4 + 0];
+        v1 = base[i * 4 + 1];
+        v2 = base[i * 4 + 2];
+        v3 = base[i * 4 + 3];
+    }
+    __syncthreads();
+    if (i < N) {
+        const int jstart = (ti == tj) ? tid + 1 : 0;
+        for (int jj = jstart; jj < nj; ++jj) {
+            const float4 q2 = qj[jj * 4 + 0], u1 = qj[jj * 4 + 1], u2 = qj[jj * 4 + 2], u3 = qj[jj * 4 + 3];
+            float best = absmax_sign4(q1, q2, 0.0f);  // {I, R} x {I, R}
+            best = absmax_sign4(q1, u1, best);         // {I, R} q1 . rotations of q2
+            best = absmax_sign4(q1, u2, best);
+            best = absmax_sign4(q1, u3, best);
+            best = absmax_sign4(v1, q2, best);         // rotations of q1 . {I, R} q2
+            best = absmax_sign4(v2, q2, best);
+            best = absmax_sign4(v3, q2, best);
+            best = fmaxf(best, fmaxf(fmaxf(fabsf(dot4_ref(v1, u1)), fabsf(dot4_ref(v1, u2))), fabsf(dot4_ref(v1, u3))));
+            best = fmaxf(best, fmaxf(fmaxf(fabsf(dot4_ref(v2, u1)), fabsf(dot4_ref(v2, u2))), fabsf(dot4_ref(v2, u3))));
+            best = fmaxf(best, fmaxf(fmaxf(fabsf(dot4_ref(v3, u1)), fabsf(dot4_ref(v3, u2))), fabsf(dot4_ref(v3, u3))));
+            const int bin = mindex_bin(fminf(best, 1.0f), thr, theta_max);
+            if (bin >= 0) atomicAdd(&hist[bin], 1u);
         }
     }
     __syncthreads();
