@@ -122,9 +122,11 @@ __device__ inline double strain_rate_max(const double *L) {
     double r = 0.5 * (c00 * (c11 * c22 - c12 * c12) - c01 * (c01 * c22 - c12 * c02) +
                       c02 * (c01 * c12 - c11 * c02));
     r = fmin(1.0, fmax(-1.0, r));
-    const double phi = acos(r) / 3.0;
-    const double e_hi = q + 2.0 * p * cos(phi);
-    const double e_lo = q + 2.0 * p * cos(phi + 2.0943951023931954923);
+    const double cphi = cos(acos(r) / 3.0);  // phi in [0, pi/3]
+    const double sphi = sqrt(fmax(0.0, 1.0 - cphi * cphi));
+    const double e_hi = q + 2.0 * p * cphi;
+    // cos(phi + 2 pi/3) = -cos(phi)/2 - sqrt(3)/2 sin(phi)
+    const double e_lo = q - p * (cphi + 1.7320508075688772935 * sphi);
     return fmax(fabs(e_hi), fabs(e_lo));
 }
 

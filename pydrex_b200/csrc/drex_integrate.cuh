@@ -161,6 +161,37 @@ __device__ inline void eval_L(const IntegrateArgs &A, int64_t ip, double t, doub
     for (int c = 0; c < 9; ++c) L[c] = numer[c] / denom;
 }
 
+// One component c of L(t): lets 27 lanes (3 stage times x 9 components) evaluate the three
+// stage matrices in parallel instead of one lane looping over all of it -- this sits on the
+// serial path of every step while the other 15 warps wait at a barrier.
+__device__ inline double eval_L_component(const IntegrateArgs &A, int64_t ip, double t, double ta,
+                                          double tb, int c, const double *xnode) {
+    const double *nodes = A.L_nodes + ip * A.K * 9 + c;
+    if (A.L_kind == 0 || A.K == 1) return nodes[0];
+    const double span = tb - ta;
+    const double x = (span != 0.0) ? (t - ta) / span : 0.0;
+    if (A.L_kind == 1) return nodes[0] + x * (nodes[9] - nodes[0]);
+    if (A.L_kind == 3) {
+        const double pos = fmin(fmax(x, 0.0), 1.0) * (A.K - 1);
+        int j = (int)pos;
+        if (j > A.K - 2) j = A.K - 2;
+        return nodes[j * 9] + (pos - j) * (nodes[(j + 1) * 9] - nodes[j * 9]);
+    }
+    double numer = 0.0, denom = 0.0;
+    const int K = A.K;
+    for (int j = 0; j < K; ++j) {
+        const double xj = (j < 33) ? xnode[j] : 0.5 * (1.0 - cospi((double)j / (double)(K - 1)));
+        const double d = x - xj;
+        if (fabs(d) < 1e-15) return nodes[j * 9];
+        double w = (j & 1) ? -1.0 : 1.0;
+        if (j == 0 || j == K - 1) w *= 0.5;
+        w /= d;
+        denom += w;
+        numer += w * nodes[j * 9];
+    }
+    return numer / denom;
+}
+
 // Per-stage flow quantities shared by the CTA.
 struct StageFlow {
     double D[9];     // sym(L)/s
@@ -178,7 +209,9 @@ struct StepShared {
     double t, h, tend;
     double red[64];
     uint64_t mbar[INT_WARPS];
+    double xnode[33];      // Chebyshev-Lobatto abscissae of the L(t) table (K <= 33)
     int sys, flag;
+    int const_flow;        // L(t) constant over the interval: stage flows computed once
 };
 
 // Bogacki-Shampine 3(2)
@@ -329,6 +362,14 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
             double L[9];
             eval_L(A, ip, t_begin, t_begin, t_end, L);
             fill_stage_flow(sh.st[2], L);
+            sh.const_flow = (A.L_kind == 0 || A.K == 1) ? 1 : 0;
+            if (sh.const_flow) {
+                sh.st[0] = sh.st[2];
+                sh.st[1] = sh.st[2];
+            } else if (A.L_kind == 2) {
+                for (int j = 0; j < A.K && j < 33; ++j)
+                    sh.xnode[j] = 0.5 * (1.0 - cospi((double)j / (double)(A.K - 1)));
+            }
             for (int c = 0; c < 9; ++c) sh.F[c] = A.F[s * 9 + c];
             matmul3(L, sh.F, sh.kF);
             if (regime == 1) left_stretch(sh.kF, sh.st[2].V);
@@ -429,11 +470,19 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
             if (warp < n_chunks) issue_chunk(warp);
 
             // stage flows at t + h/2, t + 3h/4, t + h (three lanes), then F by lane 0
-            if (tid < 3) {
-                const double cfrac = (tid == 0) ? BS_A21 : ((tid == 1) ? BS_A32 : 1.0);
-                double L[9];
-                eval_L(A, ip, sh.t + cfrac * sh.h, t_begin, t_end, L);
-                fill_stage_flow(sh.st[tid], L);
+            if (!sh.const_flow && tid < 32) {
+                if (lane < 27) {
+                    const int si = lane / 9, c = lane - 9 * si;
+                    const double cfrac = (si == 0) ? BS_A21 : ((si == 1) ? BS_A32 : 1.0);
+                    sh.st[si].Lraw[c] = eval_L_component(A, ip, sh.t + cfrac * sh.h, t_begin, t_end,
+                                                          c, sh.xnode);
+                }
+                __syncwarp();
+                if (lane < 3) {
+                    double L[9];
+                    for (int c = 0; c < 9; ++c) L[c] = sh.st[lane].Lraw[c];
+                    fill_stage_flow(sh.st[lane], L);
+                }
             }
             __syncthreads();
             if (tid == 0) {
