@@ -78,6 +78,18 @@ int drex_device_info(int device, int *sm_count, int *cc_major, int *cc_minor);
 int drex_pack_soa_f64(const double *aos, double *soa, int64_t S, int64_t N, void *stream);
 int drex_unpack_soa_f64(const double *soa, double *aos, int64_t S, int64_t N, void *stream);
 
+/* Fluidity particle-attribute wire format (examples/fluidity/corner2d/corner2d.flml:98-175):
+ * one row of 10 N + 22 doubles per particle,
+ *   [ orientations N x 3 x 3 | fractions N | strain | position 3 | L_prev 9 | F 9 ].
+ * unpack: rows cpo[P][10N+22] -> SoA state, F, previous velocity gradient, strain.
+ * pack:   the inverse; writes position and L_new into the row and advances the strain by
+ *         |dt| * max|eig sym(L_new)| (utils.strain_increment, utils.py:143-156). */
+int drex_fluidity_unpack_f64(const double *cpo, int64_t P, int64_t N, double *o_soa, double *f,
+                             double *F, double *L_prev, double *strain, void *stream);
+int drex_fluidity_pack_f64(const double *o_soa, const double *f, const double *F,
+                           const double *strain, const double *position, const double *L_new,
+                           double dt, int64_t P, int64_t N, double *cpo, void *stream);
+
 /* ---- core.derivatives (core.py:347-474) ------------------------------------------- */
 
 /* Scalar parameters of the D-Rex model shared by all systems of a call

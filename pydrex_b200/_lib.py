@@ -27,6 +27,7 @@ NVCC_FLAGS = [
 EXPORTS = (
     "drex_version", "drex_last_error", "drex_device_info",
     "drex_pack_soa_f64", "drex_unpack_soa_f64",
+    "drex_fluidity_unpack_f64", "drex_fluidity_pack_f64",
     "drex_derivatives_workspace_bytes", "drex_derivatives_f64", "drex_grain_probe_f64",
     "drex_grain_helper_f64",
     "drex_integrate_workspace_bytes", "drex_integrate_f64",
@@ -113,6 +114,8 @@ def _declare(lib):
     lib.drex_device_info.argtypes = [i32] + [c.POINTER(c.c_int)] * 3
     lib.drex_pack_soa_f64.argtypes = [vp, vp, i64, i64, vp]
     lib.drex_unpack_soa_f64.argtypes = [vp, vp, i64, i64, vp]
+    lib.drex_fluidity_unpack_f64.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, vp]
+    lib.drex_fluidity_pack_f64.argtypes = [vp, vp, vp, vp, vp, vp, dbl, i64, i64, vp, vp]
     lib.drex_derivatives_workspace_bytes.restype = szt
     lib.drex_derivatives_workspace_bytes.argtypes = [i64, i64]
     lib.drex_derivatives_f64.argtypes = (

@@ -100,7 +100,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 int integrate_slots(int device) {
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
-    return sms;
+    return sms * drex::INT_CTAS_PER_SM;
 }
 
 // Dynamic shared memory of the integrator: the per-warp TMA stages plus as many of the four
@@ -108,6 +108,7 @@ int integrate_slots(int device) {
 size_t integrate_smem_bytes(int device, int64_t N, int *smem_arrays) {
     int optin = 0;
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (drex::INT_CTAS_PER_SM > 1) optin = (optin + 1024) / drex::INT_CTAS_PER_SM - 1024;  // 1 KB reserved per CTA
     const size_t stage_bytes = (size_t)drex::INT_WARPS * drex::STAGE_DOUBLES * sizeof(double);
     const size_t static_bytes = sizeof(drex::StepShared) + drex::MATH_TABLE_DOUBLES * sizeof(double) + 256;
     const size_t array_bytes = (size_t)((N + 31) / 32 * 32) * sizeof(double);
@@ -162,6 +163,32 @@ int drex_unpack_soa_f64(const double *soa, double *aos, int64_t S, int64_t N, vo
     if (!aos || !soa) return fail(DREX_E_INVALID, "drex_unpack_soa_f64: null pointer");
     dim3 grid((unsigned)((N + 255) / 256), (unsigned)S);
     drex::unpack_soa_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(soa, aos, S, N);
+    DREX_CUDA_CHECK(cudaGetLastError());
+    return DREX_OK;
+}
+
+int drex_fluidity_unpack_f64(const double *cpo, int64_t P, int64_t N, double *o_soa, double *f,
+                             double *F, double *L_prev, double *strain, void *stream) {
+    if (P < 0 || N < 0) return fail(DREX_E_INVALID, "negative size");
+    if (P == 0) return DREX_OK;
+    if (!cpo || !o_soa || !f || !F || !L_prev || !strain)
+        return fail(DREX_E_INVALID, "drex_fluidity_unpack_f64: null pointer");
+    dim3 grid((unsigned)((N + 255) / 256 > 0 ? (N + 255) / 256 : 1), (unsigned)P);
+    drex::fluidity_unpack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(cpo, N, o_soa, f, F, L_prev, strain);
+    DREX_CUDA_CHECK(cudaGetLastError());
+    return DREX_OK;
+}
+
+int drex_fluidity_pack_f64(const double *o_soa, const double *f, const double *F,
+                           const double *strain, const double *position, const double *L_new,
+                           double dt, int64_t P, int64_t N, double *cpo, void *stream) {
+    if (P < 0 || N < 0) return fail(DREX_E_INVALID, "negative size");
+    if (P == 0) return DREX_OK;
+    if (!cpo || !o_soa || !f || !F || !strain || !position || !L_new)
+        return fail(DREX_E_INVALID, "drex_fluidity_pack_f64: null pointer");
+    dim3 grid((unsigned)((N + 255) / 256 > 0 ? (N + 255) / 256 : 1), (unsigned)P);
+    drex::fluidity_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(o_soa, f, F, strain, position,
+                                                                       L_new, dt, N, cpo);
     DREX_CUDA_CHECK(cudaGetLastError());
     return DREX_OK;
 }

@@ -239,4 +239,49 @@ __global__ void grain_helper_kernel(const HelperArgs A) {
     }
 }
 
+// ---- Fluidity particle attribute layout -------------------------------------------------
+// One row per particle, 10 N + 22 doubles (examples/fluidity/corner2d/corner2d.flml:98-175):
+//   [ orientations N x 3 x 3 (AoS) | fractions N | strain | position 3 | L_prev 9 | F 9 ]
+// unpack: row -> SoA state + the auxiliary fields; pack: the inverse, with the strain
+// advanced by |dt| * max|eig sym(L_new)| (utils.strain_increment, utils.py:143-156).
+__global__ void __launch_bounds__(256)
+fluidity_unpack_kernel(const double *__restrict__ cpo, int64_t N, double *__restrict__ o_soa,
+                       double *__restrict__ f, double *__restrict__ F, double *__restrict__ L_prev,
+                       double *__restrict__ strain) {
+    const int64_t p = blockIdx.y, row = 10 * N + 22;
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const double *src = cpo + p * row;
+    if (g < N) {
+#pragma unroll
+        for (int c = 0; c < 9; ++c) o_soa[p * 9 * N + c * N + g] = src[9 * g + c];
+        f[p * N + g] = src[9 * N + g];
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 9) {
+        L_prev[p * 9 + threadIdx.x] = src[10 * N + 4 + threadIdx.x];
+        F[p * 9 + threadIdx.x] = src[10 * N + 13 + threadIdx.x];
+        if (threadIdx.x == 0) strain[p] = src[10 * N];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+fluidity_pack_kernel(const double *__restrict__ o_soa, const double *__restrict__ f,
+                     const double *__restrict__ F, const double *__restrict__ strain,
+                     const double *__restrict__ position, const double *__restrict__ L_new, double dt,
+                     int64_t N, double *__restrict__ cpo) {
+    const int64_t p = blockIdx.y, row = 10 * N + 22;
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double *dst = cpo + p * row;
+    if (g < N) {
+#pragma unroll
+        for (int c = 0; c < 9; ++c) dst[9 * g + c] = o_soa[p * 9 * N + c * N + g];
+        dst[9 * N + g] = f[p * N + g];
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 9) {
+        dst[10 * N + 4 + threadIdx.x] = L_new[p * 9 + threadIdx.x];
+        dst[10 * N + 13 + threadIdx.x] = F[p * 9 + threadIdx.x];
+        if (threadIdx.x < 3) dst[10 * N + 1 + threadIdx.x] = position[p * 3 + threadIdx.x];
+        if (threadIdx.x == 0) dst[10 * N] = strain[p] + fabs(dt) * strain_rate_max(L_new + p * 9);
+    }
+}
+
 }  // namespace drex

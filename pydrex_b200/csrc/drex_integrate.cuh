@@ -301,7 +301,12 @@ __device__ __forceinline__ float err_ratio(double err, double ynew, double atol_
 #endif
 constexpr int MAXQ = DREX_MAXQ;
 
-__global__ void __launch_bounds__(INT_BLOCK, 1)
+#ifndef DREX_CTAS_PER_SM
+#define DREX_CTAS_PER_SM 1
+#endif
+constexpr int INT_CTAS_PER_SM = DREX_CTAS_PER_SM;
+
+__global__ void __launch_bounds__(INT_BLOCK, INT_CTAS_PER_SM)
 integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
     extern __shared__ __align__(128) double dyn_smem[];
     __shared__ StepShared sh;

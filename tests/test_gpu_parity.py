@@ -581,3 +581,45 @@ def test_backward_interval_and_status_codes(drex):
     with pytest.raises(drex.IterationError, match="maximum number"):
         m.update_orientations(params, F, _const(L), (0.0, 1.0, lambda t: np.zeros(3)),
                               rtol=1e-12, atol=1e-14, max_steps=5)
+
+
+def test_fluidity_cpo_rows_match_per_particle_path(drex, oracle):
+    """Fluidity wire format (10 N + 22 doubles per particle, corner2d.flml:98-175): advancing
+    the whole cloud in one call equals the per-particle hook (fresh Mineral + linear-in-time
+    L, corner2d.py:22-41) and the oracle's LSODA run."""
+    from pydrex_b200.fluidity import advance_cpo
+
+    P, N = 5, 200
+    rng = np.random.default_rng(4)
+    params = dict(OL_PARAMS)
+    rows = np.empty((P, 10 * N + 22))
+    L_prev = rng.normal(size=(P, 3, 3)) * 1e-14
+    L_new = L_prev + rng.normal(size=(P, 3, 3)) * 3e-15
+    for L in (L_prev, L_new):
+        L -= np.eye(3)[None] * np.trace(L, axis1=1, axis2=2)[:, None, None] / 3
+    F_prev = np.eye(3)[None] + 0.05 * rng.normal(size=(P, 3, 3))
+    minerals = [drex.Mineral(n_grains=N, seed=100 + p) for p in range(P)]
+    for p, m in enumerate(minerals):
+        rows[p] = np.hstack((m.orientations[0].ravel(), m.fractions[0], 0.25, np.zeros(3),
+                             L_prev[p].ravel(), F_prev[p].ravel()))
+    t, dt = 3e13, 1e13
+    pos = rng.normal(size=(P, 3))
+    new = advance_cpo(rows, pos, L_new, t, dt, params, rtol=1e-11, atol_abs=1e-13, atol_rel=0.0)
+    assert new.shape == rows.shape
+    for p, m in enumerate(minerals):
+        get_L = lambda tt, x, p=p: L_prev[p] + (tt - t + dt) / dt * (L_new[p] - L_prev[p])  # noqa: E731
+        F = m.update_orientations(params, F_prev[p], get_L, (t - dt, t, lambda tt: np.zeros(3)), **TIGHT)
+        nt.assert_allclose(new[p, :9 * N].reshape(N, 3, 3), m.orientations[-1], rtol=0, atol=1e-9)
+        nt.assert_allclose(new[p, 9 * N:10 * N], m.fractions[-1], rtol=1e-8, atol=1e-14)
+        nt.assert_allclose(new[p, 10 * N + 13:].reshape(3, 3), F, rtol=1e-9, atol=1e-12)
+        nt.assert_allclose(new[p, 10 * N + 1:10 * N + 4], pos[p])
+        nt.assert_allclose(new[p, 10 * N + 4:10 * N + 13].reshape(3, 3), L_new[p])
+        D = (L_new[p] + L_new[p].T) / 2
+        nt.assert_allclose(new[p, 10 * N], 0.25 + dt * np.abs(np.linalg.eigvalsh(D)).max(), rtol=1e-12)
+    # oracle for one particle
+    get_L = lambda tt, x: L_prev[0] + (tt - t + dt) / dt * (L_new[0] - L_prev[0])  # noqa: E731
+    Fo, oo, fo = oracle.update_orientations(
+        rows[0, :9 * N].reshape(N, 3, 3), rows[0, 9 * N:10 * N], 4, 0, 0, params, F_prev[0], get_L,
+        (t - dt, t, lambda tt: np.zeros(3)), rtol=1e-10, atol=1e-12)
+    nt.assert_allclose(new[0, :9 * N].reshape(N, 3, 3), oo, rtol=0, atol=2e-8)
+    nt.assert_allclose(new[0, 9 * N:10 * N], fo, rtol=1e-7, atol=1e-12)
