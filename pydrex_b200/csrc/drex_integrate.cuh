@@ -385,6 +385,8 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
             h = copysign(fabs(h), span);
             if (A.tol.max_step_frac > 0.0 && fabs(h) > A.tol.max_step_frac * fabs(span))
                 h = A.tol.max_step_frac * span;
+            // a step carried over from a longer interval must not leave this one
+            if (!(fabs(h) < fabs(span))) h = span;
             sh.h = h;
         }
         __syncthreads();

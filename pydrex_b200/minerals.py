@@ -318,6 +318,17 @@ class Mineral:
         else:
             np.savez(filename, **data)
 
+    def load(self, filename, postfix=None):
+        """Load CPO data from an NPZ file written by `save` (minerals.py:595-621)."""
+        if not filename.endswith(".npz"):
+            raise ValueError(f"Must only load from numpy NPZ format. Cannot load from {filename}.")
+        data = np.load(filename)
+        sfx = "" if postfix is None else f"_{postfix}"
+        self.phase, self.fabric, self.regime = (int(x) for x in data["meta" + sfx])
+        self.fractions = list(data["fractions" + sfx])
+        self.orientations = list(data["orientations" + sfx])
+        self.n_grains = len(self.fractions[0])
+
     @classmethod
     def from_file(cls, filename, postfix=None):
         """Construct a `Mineral` from an NPZ file written by `save` (minerals.py:623-656)."""

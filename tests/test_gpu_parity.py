@@ -623,3 +623,74 @@ def test_fluidity_cpo_rows_match_per_particle_path(drex, oracle):
         (t - dt, t, lambda tt: np.zeros(3)), rtol=1e-10, atol=1e-12)
     nt.assert_allclose(new[0, :9 * N].reshape(N, 3, 3), oo, rtol=0, atol=2e-8)
     nt.assert_allclose(new[0, 9 * N:10 * N], fo, rtol=1e-7, atol=1e-12)
+
+
+def test_corner_flow_default_tolerances_drop_in_band(drex, golden_integrate):
+    """Mode B on the corner-flow pathline (config 3 at small size), olivine + enstatite: at
+    the reference's default tolerances the device texture and the diagnostics derived from it
+    sit inside the reference's own default-vs-converged band:
+    |dC| <= 0.1 GPa, |dM-index| <= 5e-3, orientation p99 <= 1e-3, fractions p99 <= 2 %."""
+    g = golden_integrate
+    N = g["i3_tight_ol_o"].shape[1]
+    get_L = _cheb_callable(g["i3_default_tnodes"], g["i3_default_Lnodes"])
+    olA = drex.Mineral(0, 0, 4, n_grains=N, orientations_init=g["i3_default_ol_o"][0].copy(),
+                       fractions_init=g["i3_default_ol_f"][0].copy())
+    ens = drex.Mineral(1, 5, 4, n_grains=N, orientations_init=g["i3_default_en_o"][0].copy(),
+                       fractions_init=g["i3_default_en_f"][0].copy())
+    F = np.eye(3)
+    ts = g["i3_default_ts"]
+    for t0, t1 in zip(ts[:-1], ts[1:]):
+        F = drex.update_all([olA, ens], TWO_PHASE, F, get_L, (t0, t1, lambda t: np.zeros(3)))
+    ref_o, ref_f = g["i3_tight_ol_o"][-1], g["i3_tight_ol_f"][-1]
+    agree = np.isclose(olA.fractions[-1], ref_f, rtol=0.2)  # same GBS decision
+    assert agree.mean() > 0.98
+    err = np.abs(olA.orientations[-1] - ref_o)[agree]
+    assert np.median(err) <= 1e-4 and np.quantile(err, 0.99) <= 1e-3
+    rel_f = (np.abs(olA.fractions[-1] - ref_f) / ref_f)[agree]
+    assert np.quantile(rel_f, 0.99) <= 2e-2
+    nt.assert_allclose(F, g["i3_tight_F"], rtol=1e-4, atol=1e-5)
+
+    class M:
+        pass
+
+    def voigt(o_ol, f_ol, o_en, f_en):
+        a, b = M(), M()
+        a.phase, b.phase, a.n_grains, b.n_grains = 0, 1, N, N
+        a.orientations, a.fractions, b.orientations, b.fractions = [o_ol], [f_ol], [o_en], [f_en]
+        return drex.voigt_averages([a, b], [0, 1], [0.7, 0.3])[0]
+
+    C = voigt(olA.orientations[-1], olA.fractions[-1], ens.orientations[-1], ens.fractions[-1])
+    C_ref = voigt(ref_o, ref_f, g["i3_tight_en_o"][-1], g["i3_tight_en_f"][-1])
+    assert np.abs(C - C_ref).max() <= 0.1  # GPa
+    M_dev = drex.misorientation_index(olA.orientations[-1], drex.LatticeSystem.orthorhombic)
+    M_ref = drex.misorientation_index(ref_o, drex.LatticeSystem.orthorhombic)
+    assert abs(M_dev - M_ref) <= 5e-3
+
+
+def test_carried_step_longer_than_next_interval(drex, oracle):
+    """Regression: the step size suggested at the end of one interval is the first trial
+    step of the next; when the next interval is shorter, the step must be cut to it (an
+    uncut step once overshot t1 and integrated back with extrapolated L(t))."""
+    import torch
+
+    P, N = 2, 256
+    ens = drex.ParticleEnsemble(P, N, TWO_PHASE, seed=11)
+    o0 = ens.orientations().cpu().numpy()
+    L = np.zeros((P, 3, 3))
+    L[:, 1, 0] = 2.0
+    Lt = torch.as_tensor(L)
+    ens.update(0.0, 0.2, Lt)
+    h_after_long = ens.h.cpu().numpy().copy()
+    ens.update(0.2, 0.21, Lt)  # much shorter than the carried steps
+    assert np.all(np.abs(h_after_long) > 0.01)
+    assert int(ens.stats[3].sum()) == 0  # nothing to reject on a 0.01 interval
+    assert int(ens.stats[2].max()) == 1  # one accepted step each
+    assert np.all(ens.h.cpu().numpy() > 0)
+    o_dev = ens.orientations().cpu().numpy()
+    Fo, oo, fo = np.eye(3), o0[0, 0], np.full(N, 1 / N)
+    for ta, tb in ((0.0, 0.2), (0.2, 0.21)):
+        Fo, oo, fo = oracle.update_orientations(oo, fo, 4, 0, 0, TWO_PHASE, Fo, _const(L[0]),
+                                                (ta, tb, lambda t: np.zeros(3)), rtol=1e-10, atol=1e-12)
+    agree = np.isclose(ens.fractions().cpu().numpy()[0, 0], fo, rtol=0.2)
+    assert np.quantile(np.abs(o_dev[0, 0] - oo)[agree], 0.99) <= 1e-3
+    nt.assert_allclose(ens.deformation_gradients().cpu().numpy()[0], Fo, atol=1e-9)
