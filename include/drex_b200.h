@@ -206,6 +206,12 @@ int drex_voigt_average_f64(const double *o_soa, const double *f, const double *s
                            const double *phase_fraction, int64_t S, int64_t N, double *Cbar,
                            int accumulate, void *stream);
 
+/* diagnostics.elasticity_components (diagnostics.py:38-182; Browaeys & Chevrot 2004) for P
+ * Voigt matrices voigt[P][36] (upper triangle is used).  out[P][11] = bulk modulus, shear
+ * modulus, % anisotropy, % hexagonal, % tetragonal, % orthorhombic, % monoclinic,
+ * % triclinic, hexagonal axis (3; defined up to sign like the reference's LAPACK vectors). */
+int drex_elasticity_components_f64(const double *voigt, int64_t P, double *out, void *stream);
+
 /* ---- diagnostics.misorientation_index (diagnostics.py:332-367) -------------------- */
 
 size_t drex_mindex_workspace_bytes(int64_t S, int64_t N, int system_a, int system_b);

@@ -354,6 +354,15 @@ int drex_voigt_average_f64(const double *o_soa, const double *f, const double *s
     return DREX_OK;
 }
 
+int drex_elasticity_components_f64(const double *voigt, int64_t P, double *out, void *stream) {
+    if (P < 0) return fail(DREX_E_INVALID, "negative size");
+    if (P == 0) return DREX_OK;
+    if (!voigt || !out) return fail(DREX_E_INVALID, "drex_elasticity_components_f64: null pointer");
+    drex::elasticity_components_kernel<<<(unsigned)((P + 63) / 64), 64, 0, (cudaStream_t)stream>>>(voigt, P, out);
+    DREX_CUDA_CHECK(cudaGetLastError());
+    return DREX_OK;
+}
+
 // ---- M-index ---------------------------------------------------------------------------
 
 static int max_misorientation(int a, int b) {  // stats.py:203-215

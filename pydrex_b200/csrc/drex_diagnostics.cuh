@@ -111,6 +111,183 @@ voigt_average_kernel(const double *__restrict__ o_soa, const double *__restrict_
     }
 }
 
+// ------------------------------------------------------------------ elasticity decomposition
+
+// Symmetric 3x3 eigen-decomposition, eigenvalues ascending, eigenvectors in the COLUMNS of V
+// (what scipy.linalg.eigh returns, up to the sign of each column).
+__device__ inline void eigh3_ascending(const double *A, double *w, double *V) {
+    jacobi_eig3(A, w, V);
+    for (int i = 0; i < 2; ++i)  // selection sort of 3 values, swapping columns
+        for (int j = i + 1; j < 3; ++j)
+            if (w[j] < w[i]) {
+                const double t = w[i]; w[i] = w[j]; w[j] = t;
+                for (int r = 0; r < 3; ++r) {
+                    const double u = V[3 * r + i]; V[3 * r + i] = V[3 * r + j]; V[3 * r + j] = u;
+                }
+            }
+}
+
+// voigt(rotate(C, a^T)) for a symmetric Voigt matrix S, all 36 entries (tensors.py:187-273)
+__device__ inline void rotate_voigt_full(const double *a, const double *S, double *out) {
+    double Pm[6][6], Q[6][6];
+    for (int I = 0; I < 6; ++I) {
+        const int p = voigt_p(I), q = voigt_q(I);
+        for (int A = 0; A < 6; ++A) {
+            const int k = voigt_p(A), l = voigt_q(A);
+            const double rpk = a[3 * k + p], rql = a[3 * l + q];
+            Pm[I][A] = (A < 3) ? rpk * rql : rpk * rql + a[3 * l + p] * a[3 * k + q];
+        }
+    }
+    for (int I = 0; I < 6; ++I)
+        for (int B = 0; B < 6; ++B) {
+            double t = 0.0;
+            for (int A = 0; A < 6; ++A) t += Pm[I][A] * S[6 * A + B];
+            Q[I][B] = t;
+        }
+    for (int I = 0; I < 6; ++I)
+        for (int J = 0; J < 6; ++J) {
+            double t = 0.0;
+            for (int B = 0; B < 6; ++B) t += Q[I][B] * Pm[J][B];
+            out[6 * I + J] = t;
+        }
+}
+
+// tensors.voigt_matrix_to_vector (tensors.py:206-219)
+__device__ inline void voigt_to_vector21(const double *m, double *v) {
+    const double r2 = 1.4142135623730951;
+    for (int i = 0; i < 3; ++i) {
+        const int j = (i + 1) % 3, k = (i + 2) % 3;
+        v[i] = m[6 * i + i];
+        v[i + 3] = r2 * m[6 * j + k];
+        v[i + 6] = 2.0 * m[6 * (i + 3) + i + 3];
+        v[i + 9] = 2.0 * m[6 * i + i + 3];
+        v[i + 12] = 2.0 * m[6 * k + i + 3];
+        v[i + 15] = 2.0 * m[6 * j + i + 3];
+        v[i + 18] = 2.0 * r2 * m[6 * (j + 3) + k + 3];
+    }
+}
+
+__device__ inline double norm_n(const double *v, int n) {
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s += v[i] * v[i];
+    return sqrt(s);
+}
+
+// diagnostics.elasticity_components (diagnostics.py:38-182; Browaeys & Chevrot 2004), one
+// thread per Voigt matrix.  out[m][0..10] = bulk modulus, shear modulus, % anisotropy,
+// % hexagonal, % tetragonal, % orthorhombic, % monoclinic, % triclinic, hexagonal axis (3).
+// Follows the reference including its quirks: the "nearest eigenvector" search only accepts
+// angles below 10 degrees (the initial value of `angle` is 10 while smallest_angle returns
+// degrees, diagnostics.py:112) and the signed index multiplies the eigenvector
+// (diagnostics.py:123-131).
+__global__ void __launch_bounds__(64)
+elasticity_components_kernel(const double *__restrict__ voigt, int64_t P, double *__restrict__ out) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= P) return;
+    double C[36];
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j)  // tensors.upper_tri_to_symmetric (tensors.py:143-164)
+            C[6 * i + j] = (j >= i) ? voigt[m * 36 + 6 * i + j] : voigt[m * 36 + 6 * j + i];
+    // tensors.voigt_decompose (tensors.py:39-73)
+    double d[9], v[9];
+    for (int i = 0; i < 3; ++i) d[3 * i + i] = C[i] + C[6 + i] + C[12 + i];
+    d[1] = d[3] = C[5] + C[11] + C[17];
+    d[2] = d[6] = C[4] + C[10] + C[16];
+    d[5] = d[7] = C[3] + C[9] + C[15];
+    v[0] = C[0] + C[28] + C[35];
+    v[4] = C[7] + C[21] + C[35];
+    v[8] = C[14] + C[21] + C[28];
+    v[1] = v[3] = C[5] + C[11] + C[22];
+    v[2] = v[6] = C[4] + C[16] + C[23];
+    v[5] = v[7] = C[9] + C[15] + C[29];
+    const double K = (d[0] + d[4] + d[8]) / 9.0;
+    const double G = ((v[0] + v[4] + v[8]) - 3.0 * K) / 10.0;
+    double *o = out + m * 11;
+    o[0] = K;
+    o[1] = G;
+    double iso[21], X[21], tmp[21];
+    for (int i = 0; i < 21; ++i) iso[i] = 0.0;
+    for (int i = 0; i < 3; ++i) {
+        iso[i] = K + 4.0 * G / 3.0;
+        iso[i + 3] = 1.4142135623730951 * (K - 2.0 * G / 3.0);
+        iso[i + 6] = 2.0 * G;
+    }
+    voigt_to_vector21(C, X);
+    const double normX = norm_n(X, 21);
+    for (int i = 0; i < 21; ++i) tmp[i] = X[i] - iso[i];
+    o[2] = norm_n(tmp, 21) / normX * 100.0;
+    for (int i = 3; i < 11; ++i) o[i] = NAN;  // the reference leaves these unset if no permutation improves
+
+    double wd[3], Vd[9], wv[3], Vv[9], sccs[9];
+    eigh3_ascending(d, wd, Vd);
+    eigh3_ascending(v, wv, Vv);
+    for (int i = 0; i < 3; ++i) {
+        double index_vij = 0.0, angle = 10.0;
+        for (int j = 0; j < 3; ++j) {
+            double dot = 0.0, nd = 0.0, nv = 0.0;
+            for (int r = 0; r < 3; ++r) {
+                dot += Vd[3 * r + i] * Vv[3 * r + j];
+                nd += Vd[3 * r + i] * Vd[3 * r + i];
+                nv += Vv[3 * r + j] * Vv[3 * r + j];
+            }
+            double ang = acos(fmin(1.0, fmax(-1.0, dot / (sqrt(nd) * sqrt(nv))))) * 57.29577951308232;
+            if (ang > 90.0) ang = 180.0 - ang;  // diagnostics.smallest_angle (diagnostics.py:386-430)
+            if (ang < angle) {
+                angle = ang;
+                index_vij = (dot != 0.0) ? ((dot > 0.0) ? (double)j : -(double)j) : (double)j;
+            }
+        }
+        const int jj = (int)fabs(index_vij);
+        double vec[3], nrm = 0.0;
+        for (int r = 0; r < 3; ++r) {
+            vec[r] = (Vd[3 * r + i] + index_vij * Vv[3 * r + jj]) / 2.0;
+            nrm += vec[r] * vec[r];
+        }
+        nrm = sqrt(nrm);
+        for (int r = 0; r < 3; ++r) sccs[3 * r + i] = vec[r] / nrm;
+    }
+    double distance = normX;
+    for (int i = 0; i < 3; ++i) {
+        double perm[9], rot[36], Y[21], mono[21], ortho[21], tetr[21], hexv[21];
+        for (int r = 0; r < 3; ++r)
+            for (int j = 0; j < 3; ++j) perm[3 * r + j] = sccs[3 * r + (i + j) % 3];
+        rotate_voigt_full(perm, C, rot);
+        voigt_to_vector21(rot, Y);
+        for (int k = 0; k < 21; ++k) mono[k] = Y[k];  // tensors.mono_project (tensors.py:76-89)
+        mono[9] = mono[10] = mono[12] = mono[13] = mono[15] = mono[16] = mono[18] = mono[19] = 0.0;
+        for (int k = 0; k < 21; ++k) ortho[k] = (k < 9) ? mono[k] : 0.0;  // ortho_project
+        for (int k = 0; k < 21; ++k) tetr[k] = ortho[k];                  // tetr_project
+        tetr[0] = tetr[1] = 0.5 * (ortho[0] + ortho[1]);
+        tetr[3] = tetr[4] = 0.5 * (ortho[3] + ortho[4]);
+        tetr[6] = tetr[7] = 0.5 * (ortho[6] + ortho[7]);
+        for (int k = 0; k < 21; ++k) hexv[k] = 0.0;                       // hex_project
+        const double r2 = 1.4142135623730951;
+        hexv[0] = hexv[1] = 3.0 / 8.0 * (tetr[0] + tetr[1]) + tetr[5] / 4.0 / r2 + tetr[8] / 4.0;
+        hexv[2] = tetr[2];
+        hexv[3] = hexv[4] = (tetr[3] + tetr[4]) / 2.0;
+        hexv[5] = (tetr[0] + tetr[1]) / 4.0 / r2 + 3.0 / 4.0 * tetr[5] - tetr[8] / 2.0 / r2;
+        hexv[6] = hexv[7] = (tetr[6] + tetr[7]) / 2.0;
+        hexv[8] = (tetr[0] + tetr[1]) / 4.0 - tetr[5] / 2.0 / r2 + tetr[8] / 2.0;
+        for (int k = 0; k < 21; ++k) tmp[k] = Y[k] - hexv[k];
+        const double delta = norm_n(tmp, 21);
+        if (delta < distance) {
+            distance = delta;
+            const double pct = 100.0 / normX;
+            for (int k = 0; k < 21; ++k) tmp[k] = Y[k] - mono[k];
+            o[7] = norm_n(tmp, 21) * pct;  // triclinic
+            for (int k = 0; k < 21; ++k) tmp[k] = mono[k] - ortho[k];
+            o[6] = norm_n(tmp, 21) * pct;  // monoclinic
+            for (int k = 0; k < 21; ++k) tmp[k] = ortho[k] - tetr[k];
+            o[5] = norm_n(tmp, 21) * pct;  // orthorhombic
+            for (int k = 0; k < 21; ++k) tmp[k] = tetr[k] - hexv[k];
+            o[4] = norm_n(tmp, 21) * pct;  // tetragonal
+            for (int k = 0; k < 21; ++k) tmp[k] = hexv[k] - iso[k];
+            o[3] = norm_n(tmp, 21) * pct;  // hexagonal
+            for (int r = 0; r < 3; ++r) o[8 + r] = perm[3 * r + 2];  // last SCCS axis
+        }
+    }
+}
+
 // ------------------------------------------------------------------ M-index
 
 constexpr int MAX_SYMOPS = 16;

@@ -50,3 +50,31 @@ def misorientation_indices(orientation_stack, system, bins=None, ncpus=None, poo
     """
     M, _ = _mindex_device(orientation_stack, system)
     return M
+
+
+def elasticity_components(voigt_matrices):
+    """Elasticity decomposition of a series of Voigt matrices (diagnostics.py:38-182,
+    Browaeys & Chevrot 2004): bulk and shear modulus, % anisotropy, the percentages of the
+    norm carried by each symmetry class and the hexagonal (transverse-isotropy) axis.
+
+    Same dictionary keys as the reference.  The hexagonal axis is defined up to sign (in
+    the reference it inherits the arbitrary sign of LAPACK's eigenvectors).
+    """
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    is_torch = type(voigt_matrices).__module__.startswith("torch")
+    C = voigt_matrices if is_torch else torch.as_tensor(
+        np.ascontiguousarray(voigt_matrices, dtype=np.float64))
+    C = C.to(device=dev, dtype=torch.float64).reshape(-1, 36).contiguous()
+    P = int(C.shape[0])
+    out = torch.empty((P, 11), dtype=torch.float64, device=dev)
+    _lib.check(lib.drex_elasticity_components_f64(_lib.ptr(C), P, _lib.ptr(out),
+                                                  _lib.stream_ptr(torch)))
+    o = out.cpu().numpy()
+    keys = ("bulk_modulus", "shear_modulus", "percent_anisotropy", "percent_hexagonal",
+            "percent_tetragonal", "percent_orthorhombic", "percent_monoclinic",
+            "percent_triclinic")
+    res = {k: o[:, i].copy() for i, k in enumerate(keys)}
+    res["hexagonal_axis"] = o[:, 8:11].copy()
+    return res

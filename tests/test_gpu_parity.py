@@ -694,3 +694,20 @@ def test_carried_step_longer_than_next_interval(drex, oracle):
     agree = np.isclose(ens.fractions().cpu().numpy()[0, 0], fo, rtol=0.2)
     assert np.quantile(np.abs(o_dev[0, 0] - oo)[agree], 0.99) <= 1e-3
     nt.assert_allclose(ens.deformation_gradients().cpu().numpy()[0], Fo, atol=1e-9)
+
+
+def test_elasticity_components_match_golden(drex):
+    """diagnostics.elasticity_components (next-row f3) vs the reference's output on Voigt
+    averages of evolved textures and on rotated single-crystal olivine."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "elasticity.npz"))
+    out = drex.elasticity_components(g["voigt"])
+    for key in ("bulk_modulus", "shear_modulus", "percent_anisotropy"):
+        nt.assert_allclose(out[key], g[key], rtol=1e-11, err_msg=key)
+    for key in ("percent_hexagonal", "percent_tetragonal", "percent_orthorhombic",
+                "percent_monoclinic", "percent_triclinic"):
+        nt.assert_allclose(out[key], g[key], rtol=1e-7, atol=1e-9, err_msg=key)
+    # the axis inherits the arbitrary sign of the eigenvectors: compare up to sign
+    dots = np.abs(np.einsum("ij,ij->i", out["hexagonal_axis"], g["hexagonal_axis"]))
+    nt.assert_allclose(dots, 1.0, atol=1e-9)
