@@ -212,6 +212,13 @@ int drex_voigt_average_f64(const double *o_soa, const double *f, const double *s
  * % triclinic, hexagonal axis (3; defined up to sign like the reference's LAPACK vectors). */
 int drex_elasticity_components_f64(const double *voigt, int64_t P, double *out, void *stream);
 
+/* Scatter-matrix statistics of one crystallographic axis (row 0/1/2 = a/b/c) of S textures:
+ * stats._scatter_matrix (stats.py:67-80) -> diagnostics.symmetry_pgr (diagnostics.py:233-270)
+ * and diagnostics.bingham_average (diagnostics.py:185-213).  out[S][9] = P, G, R, mean axis
+ * (unit eigenvector of the largest eigenvalue, sign arbitrary), eigenvalues descending. */
+int drex_axis_scatter_f64(const double *o_soa, int64_t S, int64_t N, int row, double *out,
+                          void *stream);
+
 /* ---- diagnostics.misorientation_index (diagnostics.py:332-367) -------------------- */
 
 size_t drex_mindex_workspace_bytes(int64_t S, int64_t N, int system_a, int system_b);

@@ -14,7 +14,13 @@ from .core import (
     derivatives,
     get_crss,
 )
-from .diagnostics import elasticity_components, misorientation_index, misorientation_indices
+from .diagnostics import (
+    bingham_average,
+    elasticity_components,
+    misorientation_index,
+    misorientation_indices,
+    symmetry_pgr,
+)
 from .ensemble import ParticleEnsemble, gather_to_rank0, shard_range
 from .exceptions import Error, IterationError
 from .geometry import LatticeSystem, symmetry_operations
@@ -30,7 +36,7 @@ from .stats import misorientation_hist, misorientations_random
 
 __all__ = [
     "DefaultParams", "DeformationRegime", "MineralFabric", "MineralPhase", "derivatives",
-    "get_crss", "elasticity_components", "misorientation_index", "misorientation_indices", "ParticleEnsemble",
+    "get_crss", "bingham_average", "elasticity_components", "symmetry_pgr", "misorientation_index", "misorientation_indices", "ParticleEnsemble",
     "gather_to_rank0", "shard_range", "Error", "IterationError", "LatticeSystem",
     "symmetry_operations", "Mineral", "StiffnessTensors", "update_all", "voigt_averages",
     "misorientation_hist", "misorientations_random", "OLIVINE_PRIMARY_AXIS",

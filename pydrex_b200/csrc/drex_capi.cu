@@ -363,6 +363,17 @@ int drex_elasticity_components_f64(const double *voigt, int64_t P, double *out, 
     return DREX_OK;
 }
 
+int drex_axis_scatter_f64(const double *o_soa, int64_t S, int64_t N, int row, double *out,
+                          void *stream) {
+    if (S < 0 || N < 0) return fail(DREX_E_INVALID, "negative size");
+    if (row < 0 || row > 2) return fail(DREX_E_INVALID, "axis must be 'a', 'b', or 'c'");
+    if (S == 0) return DREX_OK;
+    if (!o_soa || !out) return fail(DREX_E_INVALID, "drex_axis_scatter_f64: null pointer");
+    drex::axis_scatter_kernel<<<(unsigned)S, 256, 0, (cudaStream_t)stream>>>(o_soa, N, row, out);
+    DREX_CUDA_CHECK(cudaGetLastError());
+    return DREX_OK;
+}
+
 // ---- M-index ---------------------------------------------------------------------------
 
 static int max_misorientation(int a, int b) {  // stats.py:203-215

@@ -288,6 +288,52 @@ elasticity_components_kernel(const double *__restrict__ voigt, int64_t P, double
     }
 }
 
+// ------------------------------------------------------------------ axis statistics
+
+// Scatter (inertia) matrix of one crystallographic axis over a texture
+// (stats._scatter_matrix, stats.py:67-80), its eigen-decomposition, and from it
+// diagnostics.symmetry_pgr (diagnostics.py:233-270) and diagnostics.bingham_average
+// (diagnostics.py:185-213).  One CTA per texture.  out[s][0..8] = P, G, R, mean axis (3, the
+// eigenvector of the largest eigenvalue, unit length, sign arbitrary), eigenvalues descending.
+__global__ void __launch_bounds__(256)
+axis_scatter_kernel(const double *__restrict__ o_soa, int64_t N, int row, double *__restrict__ out) {
+    __shared__ double red[6][8];
+    const int64_t s = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double *o = o_soa + s * 9 * N + (int64_t)(3 * row) * N;
+    double acc[6] = {0, 0, 0, 0, 0, 0};  // xx, yy, zz, xy, xz, yz
+    for (int64_t g = tid; g < N; g += 256) {
+        const double x = o[g], y = o[N + g], z = o[2 * N + g];
+        acc[0] += x * x; acc[1] += y * y; acc[2] += z * z;
+        acc[3] += x * y; acc[4] += x * z; acc[5] += y * z;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const double v = warp_sum(acc[i]);
+        if (lane == 0) red[i][warp] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double t[6];
+        for (int i = 0; i < 6; ++i) {
+            double v = 0.0;
+            for (int w = 0; w < 8; ++w) v += red[i][w];
+            t[i] = v;
+        }
+        const double A[9] = {t[0], t[3], t[4], t[3], t[1], t[5], t[4], t[5], t[2]};
+        double w[3], V[9];
+        eigh3_ascending(A, w, V);
+        const double sum = w[0] + w[1] + w[2];
+        double *o9 = out + s * 9;
+        o9[0] = (w[2] - w[1]) / sum;
+        o9[1] = 2.0 * (w[1] - w[0]) / sum;
+        o9[2] = 3.0 * w[0] / sum;
+        const double nrm = sqrt(V[2] * V[2] + V[5] * V[5] + V[8] * V[8]);
+        o9[3] = V[2] / nrm; o9[4] = V[5] / nrm; o9[5] = V[8] / nrm;
+        o9[6] = w[2]; o9[7] = w[1]; o9[8] = w[0];
+    }
+}
+
 // ------------------------------------------------------------------ M-index
 
 constexpr int MAX_SYMOPS = 16;

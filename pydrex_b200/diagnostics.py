@@ -78,3 +78,39 @@ def elasticity_components(voigt_matrices):
     res = {k: o[:, i].copy() for i, k in enumerate(keys)}
     res["hexagonal_axis"] = o[:, 8:11].copy()
     return res
+
+
+_AXIS_ROW = {"a": 0, "b": 1, "c": 2}
+
+
+def _axis_scatter(orientation_stack, axis):
+    """[T, 9] rows of (P, G, R, mean axis, eigenvalues descending) for textures [T, N, 3, 3]."""
+    if axis not in _AXIS_ROW:
+        raise ValueError(f"axis must be 'a', 'b', or 'c', not {axis}")
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    is_torch = type(orientation_stack).__module__.startswith("torch")
+    o = orientation_stack if is_torch else torch.as_tensor(
+        np.ascontiguousarray(orientation_stack, dtype=np.float64))
+    o = o.to(device=dev, dtype=torch.float64).contiguous()
+    T, N = int(o.shape[0]), int(o.shape[1])
+    o_soa = torch.empty((T, 9, N), dtype=torch.float64, device=dev)
+    out = torch.empty((T, 9), dtype=torch.float64, device=dev)
+    st = _lib.stream_ptr(torch)
+    _lib.check(lib.drex_pack_soa_f64(_lib.ptr(o.reshape(T, N, 9)), _lib.ptr(o_soa), T, N, st))
+    _lib.check(lib.drex_axis_scatter_f64(_lib.ptr(o_soa), T, N, _AXIS_ROW[axis], _lib.ptr(out), st))
+    return out.cpu().numpy()
+
+
+def symmetry_pgr(orientations, axis="a"):
+    """Point, Girdle and Random eigenvalue diagnostics of one crystallographic axis
+    (diagnostics.py:233-270; Vollmer 1990).  Returns the tuple (P, G, R)."""
+    r = _axis_scatter(np.asarray(orientations)[None], axis)[0]
+    return float(r[0]), float(r[1]), float(r[2])
+
+
+def bingham_average(orientations, axis="a"):
+    """Antipodally symmetric mean direction of one crystallographic axis
+    (diagnostics.py:185-213); unit vector, defined up to sign."""
+    return _axis_scatter(np.asarray(orientations)[None], axis)[0][3:6].copy()

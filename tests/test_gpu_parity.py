@@ -711,3 +711,18 @@ def test_elasticity_components_match_golden(drex):
     # the axis inherits the arbitrary sign of the eigenvectors: compare up to sign
     dots = np.abs(np.einsum("ij,ij->i", out["hexagonal_axis"], g["hexagonal_axis"]))
     nt.assert_allclose(dots, 1.0, atol=1e-9)
+
+
+def test_symmetry_pgr_and_bingham_average_match_golden(drex):
+    """diagnostics.symmetry_pgr / bingham_average (next-row f4) vs the reference."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "texture_axes.npz"))
+    for name in ("evolved", "start", "corner"):
+        o = g[name + "_o"]
+        for ax in "abc":
+            nt.assert_allclose(drex.symmetry_pgr(o, axis=ax), g[f"{name}_pgr_{ax}"], rtol=1e-10, atol=1e-12)
+            v = drex.bingham_average(o, axis=ax)
+            assert abs(abs(np.dot(v, g[f"{name}_bingham_{ax}"])) - 1.0) < 1e-9
+    with pytest.raises(ValueError):
+        drex.symmetry_pgr(g["start_o"], axis="d")
