@@ -183,14 +183,28 @@ __device__ inline double eval_L_component(const IntegrateArgs &A, int64_t ip, do
         const double xj = (j < 33) ? xnode[j] : 0.5 * (1.0 - cospi((double)j / (double)(K - 1)));
         const double d = x - xj;
         if (fabs(d) < 1e-15) return nodes[j * 9];
-        double w = (j & 1) ? -1.0 : 1.0;
+        // 1/d by the hardware approximation + two Newton steps (full double accuracy; the
+        // barycentric form uses the same weights above and below the fraction bar)
+        double r;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+        r = fma(r, fma(-d, r, 1.0), r);
+        r = fma(r, fma(-d, r, 1.0), r);
+        double w = (j & 1) ? -r : r;
         if (j == 0 || j == K - 1) w *= 0.5;
-        w /= d;
         denom += w;
-        numer += w * nodes[j * 9];
+        numer = fma(w, nodes[j * 9], numer);
     }
     return numer / denom;
 }
+
+// The flow quantities of `n` stage times (n = 1 or 3) evaluated cooperatively by warp 0:
+// 9 n lanes fetch the components of L(t_i), n lanes solve for the strain-rate scale, 9 n lanes
+// normalise.  This is serial work every other warp of the CTA waits for at a barrier, so
+// it is spread over the lanes instead of being looped by one thread.
+struct StageFlow;
+__device__ inline void warp_stage_flows(const IntegrateArgs &A, int64_t ip, StageFlow *st, int first,
+                                        int n, double t0s, double t1s, double t2s, double ta,
+                                        double tb, const double *xnode, int lane);
 
 // Per-stage flow quantities shared by the CTA.
 struct StageFlow {
@@ -224,6 +238,28 @@ struct StepShared {
 #define BS_E2 (1.0 / 12.0)
 #define BS_E3 (1.0 / 9.0)
 #define BS_E4 (-1.0 / 8.0)
+
+__device__ inline void warp_stage_flows(const IntegrateArgs &A, int64_t ip, StageFlow *st, int first,
+                                        int n, double t0s, double t1s, double t2s, double ta,
+                                        double tb, const double *xnode, int lane) {
+    const int si = lane / 9, c = lane - 9 * si;
+    const bool active = lane < 9 * n;
+    if (active) {
+        const double t = (si == 0) ? t0s : ((si == 1) ? t1s : t2s);
+        st[first + si].Lraw[c] = eval_L_component(A, ip, t, ta, tb, c, xnode);
+    }
+    __syncwarp();
+    if (lane < n) st[first + lane].s = strain_rate_max(st[first + lane].Lraw);
+    __syncwarp();
+    if (active) {
+        StageFlow &sf = st[first + si];
+        const int ct = 3 * (c % 3) + c / 3;  // transposed component
+        const double l = sf.Lraw[c], lt = sf.Lraw[ct], sc = sf.s;
+        sf.Ls[c] = l / sc;               // minerals.py:439
+        sf.D[c] = (0.5 * (l + lt)) / sc;  // minerals.py:421,438
+    }
+    __syncwarp();
+}
 
 __device__ inline void fill_stage_flow(StageFlow &sf, const double *L) {
     const double s = strain_rate_max(L);
@@ -363,17 +399,19 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
         double *kf_cur = slot + SLOT_KFA * Npad, *kf_nxt = slot + SLOT_KFB * Npad;
 
         // ---- initial slope at t0 (one right-hand side) --------------------------------
+        if (tid < 32) {
+            if (A.L_kind == 2)
+                for (int j = lane; j < A.K && j < 33; j += 32)
+                    sh.xnode[j] = 0.5 * (1.0 - cospi((double)j / (double)(A.K - 1)));
+            __syncwarp();
+            warp_stage_flows(A, ip, sh.st, 2, 1, t_begin, t_begin, t_begin, t_begin, t_end, sh.xnode, lane);
+        }
         if (tid == 0) {
-            double L[9];
-            eval_L(A, ip, t_begin, t_begin, t_end, L);
-            fill_stage_flow(sh.st[2], L);
+            const double *L = sh.st[2].Lraw;
             sh.const_flow = (A.L_kind == 0 || A.K == 1) ? 1 : 0;
             if (sh.const_flow) {
                 sh.st[0] = sh.st[2];
                 sh.st[1] = sh.st[2];
-            } else if (A.L_kind == 2) {
-                for (int j = 0; j < A.K && j < 33; ++j)
-                    sh.xnode[j] = 0.5 * (1.0 - cospi((double)j / (double)(A.K - 1)));
             }
             for (int c = 0; c < 9; ++c) sh.F[c] = A.F[s * 9 + c];
             matmul3(L, sh.F, sh.kF);
@@ -477,20 +515,9 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
             if (warp < n_chunks) issue_chunk(warp);
 
             // stage flows at t + h/2, t + 3h/4, t + h (three lanes), then F by lane 0
-            if (!sh.const_flow && tid < 32) {
-                if (lane < 27) {
-                    const int si = lane / 9, c = lane - 9 * si;
-                    const double cfrac = (si == 0) ? BS_A21 : ((si == 1) ? BS_A32 : 1.0);
-                    sh.st[si].Lraw[c] = eval_L_component(A, ip, sh.t + cfrac * sh.h, t_begin, t_end,
-                                                          c, sh.xnode);
-                }
-                __syncwarp();
-                if (lane < 3) {
-                    double L[9];
-                    for (int c = 0; c < 9; ++c) L[c] = sh.st[lane].Lraw[c];
-                    fill_stage_flow(sh.st[lane], L);
-                }
-            }
+            if (!sh.const_flow && tid < 32)
+                warp_stage_flows(A, ip, sh.st, 0, 3, sh.t + BS_A21 * sh.h, sh.t + BS_A32 * sh.h,
+                                 sh.t + sh.h, t_begin, t_end, sh.xnode, lane);
             __syncthreads();
             if (tid == 0) {
                 // dF/dt = L(t) F (minerals.py:426), same BS3(2) stages
