@@ -109,7 +109,7 @@ __device__ __forceinline__ void grain_rhs(const double (&a)[9], const double (&D
         const double ax = fabs(qx), ay = fabs(qy), az = fabs(qz);
         double rx, ry, rz_, px, py, pz;  // q|q|^(n-1) and |q|^p
         if (default_exponents) {
-            const double sx = sqrt(ax), sy = sqrt(ay), sz = sqrt(az);
+            const double sx = sqrt_fast(ax), sy = sqrt_fast(ay), sz = sqrt_fast(az);
             rx = qx * (ax * ax * sx); ry = qy * (ay * ay * sy); rz_ = qz * (az * az * sz);
             px = ax * sx; py = ay * sy; pz = az * sz;
         } else {

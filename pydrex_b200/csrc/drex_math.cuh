@@ -1,4 +1,4 @@
-// drex_math.cuh -- table-driven FP64 exp / log for the per-grain physics (sm_100a).
+// drex_math.cuh -- table-driven FP64 exp / log / sqrt for the per-grain physics (sm_100a).
 //
 // The integrator is bound by issue slots, and every FP64 instruction costs two of them
 // (16 FP64 lanes per scheduler).  CUDA's exp() and log() spend ~30 and ~45 FP64
@@ -6,11 +6,14 @@
 // memory the polynomials shrink to degree 6 / 8 and the functions to ~12 FP64 instructions
 // each, at the same ~1 ulp accuracy (the parity tests hold 1e-10 relative on derivatives
 // that cancel, so full double accuracy is required -- lower-precision shortcuts are not an
-// option here).
+// option here).  Polynomial coefficients are read from constant memory as instruction
+// operands (no immediate-materialising moves); range handling is folded into integer
+// clamps and one select per pow() instead of three selects per exp().
 //
 //   exp:  x = (64 m + j) ln2/64 + r, |r| <= ln2/128;  e^x = 2^m * 2^(j/64) * e^r
 //   log:  x = 2^e * mant, mant in [1,2), j = top 6 mantissa bits, c_j = 1 + (j + 1/2)/64,
 //         r = mant/c_j - 1, |r| <= 2^-7;  ln x = e ln2 + ln c_j + log1p(r)
+//   sqrt: hardware rsqrt approximation + two Goldschmidt steps + one residual correction
 //
 // Tables (scripts/gen_math_tables.py, correctly rounded from 60-digit decimals) live in
 // constant memory and are copied to shared memory by each CTA: the per-thread index
@@ -25,34 +28,46 @@ namespace drex {
 
 constexpr int MATH_TABLE_DOUBLES = 64 + 128;
 
+// polynomial coefficients: exp (r^6 ... r^2 of e^r), log1p (r^8 ... r^2), split constants
+__device__ __constant__ double DREX_EXP_C[5] = {1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5};
+__device__ __constant__ double DREX_LOG_C[7] = {-1.0 / 8.0, 1.0 / 7.0,  -1.0 / 6.0, 0.2,
+                                                -0.25,      1.0 / 3.0, -0.5};
+__device__ __constant__ double DREX_LN2[5] = {92.33248261689366,       // 64 / ln2
+                                              -0.010830424696223417,   // -(ln2/64) high 36 bits
+                                              -2.572804622327669e-14,  // -(ln2/64) low part
+                                              0.6931471805598903,      // ln2 high 42 bits
+                                              5.497923018708371e-14};  // ln2 low part
+
 // copy the tables into `dst` (shared memory, MATH_TABLE_DOUBLES doubles); caller syncs
 __device__ __forceinline__ void load_math_tables(double *dst) {
     for (int i = threadIdx.x; i < MATH_TABLE_DOUBLES; i += blockDim.x)
         dst[i] = (i < 64) ? DREX_EXP2_TAB[i] : DREX_LOG_TAB[i - 64];
 }
 
+// e^x for finite x < ~709 (and NaN, which propagates).  Arguments below -708 give a value
+// of order 1e-308 instead of a denormal or 0 -- indistinguishable for every use here; the
+// caller handles -inf (see pow_nonneg).
 __device__ __forceinline__ double exp_tab(double x, const double *__restrict__ mt) {
     const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: rint() in the low mantissa word
-    const double t = fma(x, 92.33248261689366, MAGIC);  // x * 64/ln2
+    const double t = fma(x, DREX_LN2[0], MAGIC);
     const int n = __double2loint(t);
     const double nd = t - MAGIC;
-    double r = fma(nd, -0.010830424696223417, x);  // ln2/64, high 36 bits: nd * hi is exact
-    r = fma(nd, -2.572804622327669e-14, r);
-    double p = fma(r, 1.0 / 720.0, 1.0 / 120.0);
-    p = fma(p, r, 1.0 / 24.0);
-    p = fma(p, r, 1.0 / 6.0);
-    p = fma(p, r, 0.5);
+    double r = fma(nd, DREX_LN2[1], x);  // nd * hi is exact
+    r = fma(nd, DREX_LN2[2], r);
+    double p = fma(r, DREX_EXP_C[0], DREX_EXP_C[1]);
+    p = fma(p, r, DREX_EXP_C[2]);
+    p = fma(p, r, DREX_EXP_C[3]);
+    p = fma(p, r, DREX_EXP_C[4]);
     p = fma(p, r, 1.0);
     p = p * r;  // e^r - 1
     const double tj = mt[n & 63];
-    double v = fma(tj, p, tj);
-    v = __hiloint2double(__double2hiint(v) + ((n >> 6) << 20), __double2loint(v));  // * 2^m
-    v = (x < -708.0) ? 0.0 : v;       // (sub)normal underflow: not needed to 1e-308
-    v = (x > 709.0) ? INFINITY : v;
-    return (x != x) ? x : v;
+    const double v = fma(tj, p, tj);
+    const int m = max(n >> 6, -1022);  // keep the result a normal number
+    return __hiloint2double(__double2hiint(v) + (m << 20), __double2loint(v));  // * 2^m
 }
 
-// natural log of x >= 0 (x = 0 and subnormals give -inf, inf/NaN pass through)
+// natural log of a finite normal x > 0.  x = 0, subnormals, inf and NaN give finite garbage:
+// callers that can see those values patch the result (pow_nonneg).
 __device__ __forceinline__ double log_tab(double x, const double *__restrict__ mt) {
     const int hi = __double2hiint(x), lo = __double2loint(x);
     const int e = (hi >> 20) - 1023;
@@ -60,27 +75,44 @@ __device__ __forceinline__ double log_tab(double x, const double *__restrict__ m
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
     const double2 tab = *reinterpret_cast<const double2 *>(mt + 64 + 2 * j);  // {1/c_j, ln c_j}
     const double r = fma(m, tab.x, -1.0);
-    double q = fma(r, -1.0 / 8.0, 1.0 / 7.0);
-    q = fma(q, r, -1.0 / 6.0);
-    q = fma(q, r, 0.2);
-    q = fma(q, r, -0.25);
-    q = fma(q, r, 1.0 / 3.0);
-    q = fma(q, r, -0.5);
+    double q = fma(r, DREX_LOG_C[0], DREX_LOG_C[1]);
+    q = fma(q, r, DREX_LOG_C[2]);
+    q = fma(q, r, DREX_LOG_C[3]);
+    q = fma(q, r, DREX_LOG_C[4]);
+    q = fma(q, r, DREX_LOG_C[5]);
+    q = fma(q, r, DREX_LOG_C[6]);
     const double r2 = r * r;
     const double ed = (double)e;
-    // e*ln2_hi is exact (ln2_hi has 42 significant bits, |e| < 2^11)
-    double res = fma(ed, 0.6931471805598903, tab.y);
+    double res = fma(ed, DREX_LN2[3], tab.y);  // e * ln2_hi is exact (42 bits x 11 bits)
     res += fma(r2, q, r);
-    res = fma(ed, 5.497923018708371e-14, res);
-    res = (hi < 0x00100000) ? -INFINITY : res;
-    return (hi >= 0x7ff00000) ? x : res;
+    return fma(ed, DREX_LN2[4], res);
 }
 
-// x^y for x >= 0 with C pow() conventions at 0: log(0) = -inf makes x = 0 come out right
-// for y != 0 without a per-thread branch; y is a model exponent (uniform over the launch).
-// exp(y log x) is accurate to ~|y log x| * 2^-52 relative, far inside the 1e-10 bound.
+// x^y for x >= 0 and a model exponent y (uniform over the launch), C pow() conventions at
+// 0; NaN and inf propagate.  exp(y log x) is accurate to ~|y log x| * 2^-52 relative, far
+// inside the 1e-10 bound.
 __device__ __forceinline__ double pow_nonneg(double x, double y, const double *__restrict__ mt) {
-    return (y == 0.0) ? 1.0 : exp_tab(y * log_tab(x, mt), mt);
+    if (y == 0.0) return 1.0;
+    double v = exp_tab(y * log_tab(x, mt), mt);
+    v += x - x;  // NaN (and inf) in, NaN out: log_tab/exp_tab drop them
+    const bool tiny = (unsigned)__double2hiint(x) < 0x00100000u;  // +0 and subnormals
+    return tiny ? ((y > 0.0) ? 0.0 : INFINITY) : v;
+}
+
+// sqrt of x >= 0 to ~1 ulp without the special-case branches of the library routine.
+__device__ __forceinline__ double sqrt_fast(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double g = x * y, h = 0.5 * y;
+    double r = fma(-h, g, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-h, g, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    g = fma(fma(-g, g, x), h, g);  // residual correction
+    // x = 0 (rsqrt = inf -> NaN) and subnormals: sqrt is 0 to every purpose here
+    return ((unsigned)__double2hiint(x) < 0x00100000u) ? 0.0 : g;
 }
 
 }  // namespace drex
