@@ -145,18 +145,25 @@ __device__ __forceinline__ void grain_rhs(const double (&a)[9], const double (&D
             for (int j = 0; j < 3; ++j) G[3 * i + j] = 2.0 * (a[i] * u[j] + a[6 + i] * v[j]);
     }
     // slip rate on the softest system (core.py:513-538)
-    double num = 0.0, den = 0.0;
+    // three independent partial sums per row instead of one 12-term chain: the FP64 pipe has
+    // a long dependent-issue latency and only four warps per scheduler to hide it
+    double num, den;
+    {
+        double nr[3], dr[3];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        const int k = (j + 1) % 3;
-        const double ga = G[3 * j + k] - G[3 * k + j];
-        num -= (L[3 * j + k] - L[3 * k + j]) * ga;
-        den -= ga * ga;
-#pragma unroll
-        for (int l = 0; l < 3; ++l) {
-            num += 2.0 * G[3 * j + l] * L[3 * j + l];
-            den += 2.0 * G[3 * j + l] * G[3 * j + l];
+        for (int j = 0; j < 3; ++j) {
+            const int k = (j + 1) % 3;
+            const double ga = G[3 * j + k] - G[3 * k + j];
+            double n2 = G[3 * j] * L[3 * j], d2 = G[3 * j] * G[3 * j];
+            n2 = fma(G[3 * j + 1], L[3 * j + 1], n2);
+            d2 = fma(G[3 * j + 1], G[3 * j + 1], d2);
+            n2 = fma(G[3 * j + 2], L[3 * j + 2], n2);
+            d2 = fma(G[3 * j + 2], G[3 * j + 2], d2);
+            nr[j] = fma(2.0, n2, -(L[3 * j + k] - L[3 * k + j]) * ga);
+            dr[j] = fma(2.0, d2, -ga * ga);
         }
+        num = (nr[0] + nr[1]) + nr[2];
+        den = (dr[0] + dr[1]) + dr[2];
     }
     const double gamma0 = (den > -1e-15 && den < 1e-15) ? 0.0 : num / den;
 

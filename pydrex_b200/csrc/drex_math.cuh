@@ -54,12 +54,14 @@ __device__ __forceinline__ double exp_tab(double x, const double *__restrict__ m
     const double nd = t - MAGIC;
     double r = fma(nd, DREX_LN2[1], x);  // nd * hi is exact
     r = fma(nd, DREX_LN2[2], r);
-    double p = fma(r, DREX_EXP_C[0], DREX_EXP_C[1]);
-    p = fma(p, r, DREX_EXP_C[2]);
-    p = fma(p, r, DREX_EXP_C[3]);
-    p = fma(p, r, DREX_EXP_C[4]);
-    p = fma(p, r, 1.0);
-    p = p * r;  // e^r - 1
+    // Estrin: e^r - 1 = r + r^2 (1/2 + r/6) + r^4 (1/24 + r/120 + r^2/720), depth 3 instead of 6
+    const double r2 = r * r;
+    const double a0 = fma(r, DREX_EXP_C[3], DREX_EXP_C[4]);   // 1/2 + r/6
+    const double a1 = fma(r, DREX_EXP_C[1], DREX_EXP_C[2]);   // 1/24 + r/120
+    const double a2 = fma(r2, DREX_EXP_C[0], a1);             // + r^2/720
+    const double r4 = r2 * r2;
+    double p = fma(r2, a0, r);
+    p = fma(r4, a2, p);  // e^r - 1
     const double tj = mt[n & 63];
     const double v = fma(tj, p, tj);
     const int m = max(n >> 6, -1022);  // keep the result a normal number
@@ -75,13 +77,15 @@ __device__ __forceinline__ double log_tab(double x, const double *__restrict__ m
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
     const double2 tab = *reinterpret_cast<const double2 *>(mt + 64 + 2 * j);  // {1/c_j, ln c_j}
     const double r = fma(m, tab.x, -1.0);
-    double q = fma(r, DREX_LOG_C[0], DREX_LOG_C[1]);
-    q = fma(q, r, DREX_LOG_C[2]);
-    q = fma(q, r, DREX_LOG_C[3]);
-    q = fma(q, r, DREX_LOG_C[4]);
-    q = fma(q, r, DREX_LOG_C[5]);
-    q = fma(q, r, DREX_LOG_C[6]);
+    // Estrin on q(r) = -1/2 + r/3 - r^2/4 + r^3/5 - r^4/6 + r^5/7 - r^6/8
     const double r2 = r * r;
+    const double b0 = fma(r, DREX_LOG_C[5], DREX_LOG_C[6]);  // -1/2 + r/3
+    const double b1 = fma(r, DREX_LOG_C[3], DREX_LOG_C[4]);  // -1/4 + r/5
+    const double b2 = fma(r, DREX_LOG_C[1], DREX_LOG_C[2]);  // -1/6 + r/7
+    const double r4 = r2 * r2;
+    const double b3 = fma(r2, DREX_LOG_C[0], b2);            // ... - r^2/8
+    double q = fma(r2, b1, b0);
+    q = fma(r4, b3, q);
     const double ed = (double)e;
     double res = fma(ed, DREX_LN2[3], tab.y);  // e * ln2_hi is exact (42 bits x 11 bits)
     res += fma(r2, q, r);
