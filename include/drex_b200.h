@@ -219,6 +219,21 @@ int drex_elasticity_components_f64(const double *voigt, int64_t P, double *out, 
 int drex_axis_scatter_f64(const double *o_soa, int64_t S, int64_t N, int row, double *out,
                           void *stream);
 
+/* ---- stats.resample_orientations (stats.py:14-64) ----------------------------------- */
+
+/* Volume-weighted resampling of S textures of N grains: sort by fraction ascending (ties by
+ * grain index, i.e. numpy.argsort(kind="stable")), sequential running sum with the last
+ * entry forced to 1, numpy.searchsorted(cumfrac, u) per uniform variate.  o_aos: [S][N][3][3]
+ * (the reference's layout), f: [S][N], uniforms: [S][n_samples] in [0,1) -- the caller draws
+ * them (numpy.random.default_rng(seed).random((S, n_samples)) reproduces the reference's
+ * stream).  out_o: [S][n_samples][3][3], out_f: [S][n_samples].  Workspace is only needed
+ * above 8192 grains per texture (query first; 0 otherwise). */
+size_t drex_resample_workspace_bytes(int64_t S, int64_t N);
+int drex_resample_orientations_f64(const double *o_aos, const double *f, const double *uniforms,
+                                   int64_t S, int64_t N, int64_t n_samples, double *out_o,
+                                   double *out_f, void *workspace, size_t workspace_bytes,
+                                   void *stream);
+
 /* ---- diagnostics.misorientation_index (diagnostics.py:332-367) -------------------- */
 
 size_t drex_mindex_workspace_bytes(int64_t S, int64_t N, int system_a, int system_b);

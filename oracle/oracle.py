@@ -305,3 +305,26 @@ def misorientation_index(orientations, system, return_hist=False):
     if return_hist:
         return M, hist, counts
     return M
+
+
+def resample_orientations(orientations, fractions, n_samples=None, seed=None):
+    """numpy restatement of stats.resample_orientations (reference stats.py:14-64) with the
+    one freedom the reference leaves open pinned down: grains of EQUAL fraction are ordered
+    by index (argsort kind="stable"; the reference's default argsort is unstable and its tie
+    order depends on the numpy build)."""
+    orientations = np.asarray(orientations, dtype=np.float64)
+    fractions = np.asarray(fractions, dtype=np.float64)
+    rng = np.random.default_rng(seed=seed)
+    if n_samples is None:
+        n_samples = fractions.shape[1]
+    out_o = np.empty((len(fractions), n_samples, 3, 3))
+    out_f = np.empty((len(fractions), n_samples))
+    for i, (frac, orient) in enumerate(zip(fractions, orientations)):
+        order = np.argsort(frac, kind="stable")
+        frac_ascending = frac[order]
+        cumfrac = frac_ascending.cumsum()
+        cumfrac[-1] = 1.0
+        picks = np.searchsorted(cumfrac, rng.random(n_samples))
+        out_o[i] = orient[order][picks]
+        out_f[i] = frac_ascending[picks]
+    return out_o, out_f

@@ -32,13 +32,13 @@ from .minerals import (
     update_all,
     voigt_averages,
 )
-from .stats import misorientation_hist, misorientations_random
+from .stats import misorientation_hist, misorientations_random, resample_orientations
 
 __all__ = [
     "DefaultParams", "DeformationRegime", "MineralFabric", "MineralPhase", "derivatives",
     "get_crss", "bingham_average", "elasticity_components", "symmetry_pgr", "misorientation_index", "misorientation_indices", "ParticleEnsemble",
     "gather_to_rank0", "shard_range", "Error", "IterationError", "LatticeSystem",
     "symmetry_operations", "Mineral", "StiffnessTensors", "update_all", "voigt_averages",
-    "misorientation_hist", "misorientations_random", "OLIVINE_PRIMARY_AXIS",
+    "misorientation_hist", "misorientations_random", "resample_orientations", "OLIVINE_PRIMARY_AXIS",
     "OLIVINE_SLIP_SYSTEMS",
 ]

@@ -33,6 +33,8 @@ EXPORTS = (
     "drex_integrate_workspace_bytes", "drex_integrate_f64",
     "drex_voigt_average_f64", "drex_elasticity_components_f64",
     "drex_axis_scatter_f64",
+    "drex_resample_workspace_bytes",
+    "drex_resample_orientations_f64",
     "drex_mindex_workspace_bytes", "drex_mindex_theory_host", "drex_mindex_f32",
     "drex_misorientations_random_host",
     "drex_fp64_peak_probe",
@@ -135,6 +137,9 @@ def _declare(lib):
     lib.drex_voigt_average_f64.argtypes = [vp, vp, vp, vp, i64, i64, vp, i32, vp]
     lib.drex_elasticity_components_f64.argtypes = [vp, i64, vp, vp]
     lib.drex_axis_scatter_f64.argtypes = [vp, i64, i64, i32, vp, vp]
+    lib.drex_resample_workspace_bytes.restype = szt
+    lib.drex_resample_workspace_bytes.argtypes = [i64, i64]
+    lib.drex_resample_orientations_f64.argtypes = [vp, vp, vp, i64, i64, i64, vp, vp, vp, szt, vp]
     lib.drex_mindex_workspace_bytes.restype = szt
     lib.drex_mindex_workspace_bytes.argtypes = [i64, i64, i32, i32]
     lib.drex_mindex_theory_host.argtypes = [i32, i32, c.POINTER(c.c_double)]

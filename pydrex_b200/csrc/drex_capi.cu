@@ -15,6 +15,7 @@
 #include "drex_derivatives.cuh"
 #include "drex_diagnostics.cuh"
 #include "drex_integrate.cuh"
+#include "drex_resample.cuh"
 
 namespace {
 
@@ -370,6 +371,39 @@ int drex_axis_scatter_f64(const double *o_soa, int64_t S, int64_t N, int row, do
     if (S == 0) return DREX_OK;
     if (!o_soa || !out) return fail(DREX_E_INVALID, "drex_axis_scatter_f64: null pointer");
     drex::axis_scatter_kernel<<<(unsigned)S, 256, 0, (cudaStream_t)stream>>>(o_soa, N, row, out);
+    DREX_CUDA_CHECK(cudaGetLastError());
+    return DREX_OK;
+}
+
+// ---- stats.resample_orientations ---------------------------------------------------------
+
+size_t drex_resample_workspace_bytes(int64_t S, int64_t N) {
+    if (S <= 0 || N <= 0) return 0;
+    const int64_t npad = drex::resample_npad(N);
+    return npad <= drex::RESAMPLE_SMEM_NPAD_MAX ? 0 : (size_t)S * (size_t)npad * 20;
+}
+
+int drex_resample_orientations_f64(const double *o_aos, const double *f, const double *uniforms,
+                                   int64_t S, int64_t N, int64_t n_samples, double *out_o,
+                                   double *out_f, void *workspace, size_t workspace_bytes,
+                                   void *stream) {
+    if (S < 0 || N < 0 || n_samples < 0) return fail(DREX_E_INVALID, "negative size");
+    if (S == 0 || n_samples == 0) return DREX_OK;
+    if (N == 0) return fail(DREX_E_INVALID, "drex_resample_orientations_f64: no grains to sample");
+    if (N > 0x7ffffffe) return fail(DREX_E_INVALID, "drex_resample_orientations_f64: too many grains");
+    if (!o_aos || !f || !uniforms || !out_o || !out_f)
+        return fail(DREX_E_INVALID, "drex_resample_orientations_f64: null pointer");
+    const size_t need = drex_resample_workspace_bytes(S, N);
+    if (need && (!workspace || workspace_bytes < need))
+        return fail(DREX_E_WORKSPACE, "drex_resample_orientations_f64: workspace too small (%zu < %zu)",
+                    workspace_bytes, need);
+    const int64_t npad = drex::resample_npad(N);
+    const size_t smem = need ? 0 : (size_t)npad * 20;
+    if (smem > 48 * 1024)
+        DREX_CUDA_CHECK(cudaFuncSetAttribute(drex::resample_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    drex::resample_kernel<<<(unsigned)S, drex::RESAMPLE_THREADS, smem, (cudaStream_t)stream>>>(
+        o_aos, f, uniforms, N, npad, n_samples, out_o, out_f, (unsigned char *)workspace);
     DREX_CUDA_CHECK(cudaGetLastError());
     return DREX_OK;
 }

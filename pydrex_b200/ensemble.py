@@ -322,18 +322,56 @@ class ParticleEnsemble:
                                               _lib.ptr(Cbar), 0, _lib.stream_ptr(torch)))
         return Cbar.reshape(self.P, self.n_phases, 6, 6).sum(dim=1)
 
-    def misorientation_indices(self, system, phase_slot=0, batch=256):
-        """M-index of every particle's texture for one phase slot, [P] (device tensor)."""
+    def resample(self, n_samples=None, seeds=None, phase_slot=0, lo=0, hi=None):
+        """Volume-weighted resample of the current texture of particles [lo, hi) for one phase
+        slot (stats.resample_orientations, stats.py:14-64, called once per particle with
+        that particle's seed like the reference drivers do, tests/test_simple_shear_3d.py:
+        194-202).  Returns device tensors ([n, n_samples, 3, 3], [n, n_samples])."""
+        lib, torch = _lib.load(), self._torch
+        hi = self.P if hi is None else hi
+        n = hi - lo
+        n_samples = self.N if n_samples is None else int(n_samples)
+        if seeds is None:
+            seeds = [None] * self.P
+        uniforms = np.stack([np.random.default_rng(seed=seeds[i]).random(n_samples)
+                             for i in range(lo, hi)]) if n else np.empty((0, n_samples))
+        uniforms = torch.as_tensor(uniforms).to(self.device)
+        o_soa = self.o.reshape(self.P, self.n_phases, 9, self.N)[lo:hi, phase_slot].contiguous()
+        f = self.f.reshape(self.P, self.n_phases, self.N)[lo:hi, phase_slot].contiguous()
+        o_aos = torch.empty((n, self.N, 3, 3), dtype=torch.float64, device=self.device)
+        out_o = torch.empty((n, n_samples, 3, 3), dtype=torch.float64, device=self.device)
+        out_f = torch.empty((n, n_samples), dtype=torch.float64, device=self.device)
+        st = _lib.stream_ptr(torch)
+        _lib.check(lib.drex_unpack_soa_f64(_lib.ptr(o_soa), _lib.ptr(o_aos), n, self.N, st))
+        nbytes = lib.drex_resample_workspace_bytes(n, self.N)
+        ws = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=self.device)
+        _lib.check(lib.drex_resample_orientations_f64(
+            _lib.ptr(o_aos), _lib.ptr(f), _lib.ptr(uniforms), n, self.N, n_samples,
+            _lib.ptr(out_o), _lib.ptr(out_f), _lib.ptr(ws), nbytes, st))
+        return out_o, out_f
+
+    def misorientation_indices(self, system, phase_slot=0, batch=256, n_samples=None, seeds=None):
+        """M-index of every particle's texture for one phase slot, [P] (device tensor): of
+        the full texture, or -- with `n_samples` -- of the volume-weighted resample drawn
+        with the per-particle `seeds`, which is what the reference's drivers feed to
+        `misorientation_index`."""
         lib, torch = _lib.load(), self._torch
         a, b = system.value
         o = self.o.reshape(self.P, self.n_phases, 9, self.N)[:, phase_slot]
         out = torch.empty(self.P, dtype=torch.float64, device=self.device)
+        st = _lib.stream_ptr(torch)
         for lo in range(0, self.P, batch):
-            chunk = o[lo:lo + batch].contiguous()
+            if n_samples is None:
+                chunk, N = o[lo:lo + batch].contiguous(), self.N
+            else:
+                ro, _ = self.resample(n_samples, seeds, phase_slot, lo, min(lo + batch, self.P))
+                N = int(ro.shape[1])
+                chunk = torch.empty((ro.shape[0], 9, N), dtype=torch.float64, device=self.device)
+                _lib.check(lib.drex_pack_soa_f64(_lib.ptr(ro), _lib.ptr(chunk), ro.shape[0], N, st))
             T = chunk.shape[0]
-            nbytes = lib.drex_mindex_workspace_bytes(T, self.N, a, b)
+            nbytes = lib.drex_mindex_workspace_bytes(T, N, a, b)
             ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-            rc = lib.drex_mindex_f32(_lib.ptr(chunk), T, self.N, a, b, _lib.ptr(out[lo:lo + T]),
-                                     None, _lib.ptr(ws), nbytes, _lib.stream_ptr(torch))
+            rc = lib.drex_mindex_f32(_lib.ptr(chunk), T, N, a, b, _lib.ptr(out[lo:lo + T]),
+                                     None, _lib.ptr(ws), nbytes, st)
             _lib.check(rc)
         return out

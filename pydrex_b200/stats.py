@@ -1,4 +1,4 @@
-"""Misorientation statistics (drop-in for the M-index part of pydrex.stats)."""
+"""Texture statistics (drop-in for pydrex.stats: resampling and the M-index parts)."""
 
 import ctypes
 
@@ -6,6 +6,66 @@ import numpy as np
 
 from . import _lib
 from . import geometry as _geo
+
+
+def resample_orientations(orientations, fractions, n_samples=None, seed=None):
+    """Return new samples from `orientations` weighted by the volume distribution
+    (stats.py:14-64).
+
+    - `orientations` — NxMx3x3 array of orientations
+    - `fractions` — NxM array of grain volume fractions
+    - `n_samples` — optional number of samples to return, default is M
+    - `seed` — optional seed for the random number generator
+
+    Returns the Nx`n_samples`x3x3 orientations and associated grain volumes.  numpy in,
+    numpy out; torch CUDA tensors in, torch CUDA tensors out.  The uniform variates are
+    numpy's `default_rng(seed).random` stream, drawn texture by texture like the reference;
+    sorting, running sum, search and gather run on the device.  Grains with EQUAL fractions
+    are ordered by index (numpy.argsort(kind="stable")); the reference's default argsort
+    leaves that order to the numpy build, see csrc/drex_resample.cuh.
+    """
+    is_torch = type(orientations).__module__.startswith("torch")
+    o_shape = tuple(orientations.shape) if is_torch else np.asarray(orientations).shape
+    f_shape = tuple(fractions.shape) if type(fractions).__module__.startswith("torch") \
+        else np.asarray(fractions).shape
+    if (
+        len(o_shape) != 4
+        or len(f_shape) != 2
+        or o_shape[0] != f_shape[0]
+        or o_shape[1] != f_shape[1]
+        or o_shape[2] != o_shape[3] != 3
+    ):
+        raise ValueError(
+            "invalid shape of input arrays,"
+            + f" got orientations of shape {o_shape}"
+            + f" and fractions of shape {f_shape}"
+        )
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    T, N = int(f_shape[0]), int(f_shape[1])
+    if n_samples is None:
+        n_samples = N
+    n_samples = int(n_samples)
+    rng = np.random.default_rng(seed=seed)
+    uniforms = torch.as_tensor(rng.random((T, n_samples))).to(dev)
+
+    def to_dev(x):
+        if not type(x).__module__.startswith("torch"):
+            x = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64))
+        return x.to(device=dev, dtype=torch.float64).contiguous()
+
+    o, f = to_dev(orientations), to_dev(fractions)
+    out_o = torch.empty((T, n_samples, 3, 3), dtype=torch.float64, device=dev)
+    out_f = torch.empty((T, n_samples), dtype=torch.float64, device=dev)
+    nbytes = lib.drex_resample_workspace_bytes(T, N)
+    ws = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=dev)
+    _lib.check(lib.drex_resample_orientations_f64(
+        _lib.ptr(o), _lib.ptr(f), _lib.ptr(uniforms), T, N, n_samples, _lib.ptr(out_o),
+        _lib.ptr(out_f), _lib.ptr(ws), nbytes, _lib.stream_ptr(torch)))
+    if is_torch:
+        return out_o, out_f
+    return out_o.cpu().numpy(), out_f.cpu().numpy()
 
 
 def _max_misorientation(system):

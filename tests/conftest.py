@@ -52,6 +52,11 @@ def golden_diagnostics():
 
 
 @pytest.fixture(scope="session")
+def golden_resample():
+    return _load("resample.npz")
+
+
+@pytest.fixture(scope="session")
 def golden_config1():
     return _load("config1_n5000.npz")
 

@@ -726,3 +726,84 @@ def test_symmetry_pgr_and_bingham_average_match_golden(drex):
             assert abs(abs(np.dot(v, g[f"{name}_bingham_{ax}"])) - 1.0) < 1e-9
     with pytest.raises(ValueError):
         drex.symmetry_pgr(g["start_o"], axis="d")
+
+
+# ------------------------------------------------------------------ resampling (f4)
+
+
+def test_resample_orientations_match_golden(drex, golden_resample, golden_integrate):
+    """stats.resample_orientations (stats.py:14-64): bit-exact against the reference where
+    its result does not hinge on the tie order of numpy's unstable argsort."""
+    g = golden_resample
+    o, f = g["d_orientations"], g["d_fractions"]
+    for tag in ("default", "n2000", "n10"):
+        n_samples, seed = (int(v) for v in g[f"d_{tag}_args"])
+        ro, rf = drex.stats.resample_orientations(o, f, None if n_samples < 0 else n_samples, seed)
+        assert np.array_equal(ro, g[f"d_{tag}_o"]), tag
+        assert np.array_equal(rf, g[f"d_{tag}_f"]), tag
+    eo, ef = golden_integrate["i1_default_o"], golden_integrate["i1_default_f"]
+    ro, rf = drex.stats.resample_orientations(eo, ef, n_samples=1000, seed=8816)
+    assert np.array_equal(rf, g["e_f"])
+    for t in range(len(ef)):
+        vals, counts = np.unique(ef[t], return_counts=True)
+        untied = np.isin(rf[t], vals[counts == 1])
+        assert np.array_equal(ro[t][untied], g["e_o"][t][untied])
+
+
+@pytest.mark.parametrize("n_grains,n_samples", [(1, 5), (2, 7), (5000, 1000), (8192, 8192), (9001, 500)])
+def test_resample_orientations_match_oracle(drex, oracle, n_grains, n_samples):
+    """Sizes around the shared-memory / workspace switch (8192 grains), heavy ties (GBS-like
+    floor) and a non-normalised fraction row; bit-exact against the oracle."""
+    from scipy.spatial.transform import Rotation
+
+    rng = np.random.default_rng(n_grains)
+    T = 3
+    o = Rotation.random(T * n_grains, random_state=5).as_matrix().reshape(T, n_grains, 3, 3)
+    f = rng.random((T, n_grains))
+    f[1, : n_grains // 2] = f[1].min()  # ties: half of the grains on a common floor
+    f /= f.sum(axis=1, keepdims=True)
+    f[2] *= 0.9  # the reference forces the last cumulative entry to 1 whatever the sum
+    ro, rf = drex.stats.resample_orientations(o, f, n_samples=n_samples, seed=42)
+    eo, ef = oracle.resample_orientations(o, f, n_samples=n_samples, seed=42)
+    assert ro.shape == (T, n_samples, 3, 3) and rf.shape == (T, n_samples)
+    assert np.array_equal(rf, ef)
+    assert np.array_equal(ro, eo)
+
+
+def test_resample_orientations_interface(drex):
+    import torch
+
+    o = np.tile(np.eye(3), (2, 50, 1, 1))
+    f = np.full((2, 50), 1 / 50)
+    with pytest.raises(ValueError, match="invalid shape"):
+        drex.stats.resample_orientations(o[0], f)
+    with pytest.raises(ValueError, match="invalid shape"):
+        drex.stats.resample_orientations(o, f[:, :49])
+    ro, rf = drex.stats.resample_orientations(torch.as_tensor(o).cuda(), torch.as_tensor(f).cuda(), seed=1)
+    assert ro.is_cuda and rf.is_cuda and tuple(ro.shape) == (2, 50, 3, 3)
+    assert torch.equal(rf.cpu(), torch.as_tensor(f))
+
+
+def test_ensemble_resampled_misorientation_indices(drex, golden_config1):
+    """Config 5's reference-style diagnostic: M-index of the volume-weighted resample, one
+    seed per particle -- batched path against the per-texture calls, and the single-texture
+    chain against the reference's own number for config 1."""
+    import torch
+
+    P, N = 5, 300
+    ens = drex.ParticleEnsemble(P, N, TWO_PHASE, seed=11)
+    L = np.zeros((3, 3)); L[1, 0] = 2.0
+    ens.update(0.0, 0.3, torch.as_tensor(np.tile(L, (P, 1, 1))))
+    seeds = [100 + p for p in range(P)]
+    system = drex.geometry.LatticeSystem.orthorhombic
+    M = ens.misorientation_indices(system, phase_slot=0, n_samples=200, seeds=seeds, batch=2).cpu().numpy()
+    o = ens.orientations().cpu().numpy()
+    f = ens.fractions().cpu().numpy()
+    for p in range(P):
+        ro, _ = drex.resample_orientations(o[p, 0][None], f[p, 0][None], n_samples=200, seed=seeds[p])
+        assert M[p] == drex.misorientation_index(ro[0], system)
+    full = ens.misorientation_indices(system, phase_slot=0).cpu().numpy()
+    assert np.all(M > full)  # volume weighting favours the grown, aligned grains
+    # the reference's own value for its resampled config-1 texture (SURVEY 8c)
+    g = golden_config1
+    assert abs(drex.misorientation_index(g["resampled_o"], system) - float(g["resampled_M"])) < 2e-4

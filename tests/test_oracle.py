@@ -193,3 +193,23 @@ def test_misorientation_index_matches_reference(oracle, golden_diagnostics):
         assert abs(M - float(g[key])) <= 2.5 / npairs, (tname, sname)
         n += 1
     assert n >= 9
+
+
+def test_resample_orientations_golden(oracle, golden_resample, golden_integrate):
+    """stats.resample_orientations (stats.py:14-64): exact where the reference is defined
+    independently of its argsort's tie order."""
+    g = golden_resample
+    o, f = g["d_orientations"], g["d_fractions"]
+    for tag in ("default", "n2000", "n10"):
+        n_samples, seed = (int(v) for v in g[f"d_{tag}_args"])
+        ro, rf = oracle.resample_orientations(o, f, None if n_samples < 0 else n_samples, seed)
+        assert np.array_equal(ro, g[f"d_{tag}_o"])
+        assert np.array_equal(rf, g[f"d_{tag}_f"])
+    i = golden_integrate
+    eo, ef = i["i1_default_o"], i["i1_default_f"]
+    ro, rf = oracle.resample_orientations(eo, ef, 1000, 8816)
+    assert np.array_equal(rf, g["e_f"])  # tied grains carry the same fraction
+    for t in range(len(ef)):
+        vals, counts = np.unique(ef[t], return_counts=True)
+        untied = np.isin(rf[t], vals[counts == 1])
+        assert np.array_equal(ro[t][untied], g["e_o"][t][untied])
