@@ -132,6 +132,30 @@ def corner_flow_tables(P, n_steps, seed, K=9, n_path_steps=50):
 
 
 
+def trace_pathlines_on_device(drex, torch, P, K=9, n_path_steps=50):
+    """the same particle cloud traced by the library's device tracer
+    (drex_pathlines_f64: pathlines + the L(t) tables of all 50 intervals in one launch).
+    Reported beside the bench, not inside the timed region: the timed workload keeps the
+    host-generated tables so that the GPU arm and the CPU arm integrate identical inputs."""
+    U, H, W = 2.0 / (100 * 365 * 86400), 2e5, 1e6
+    finals = np.zeros((P, 3))
+    finals[:, 0], finals[:, 2] = W, -np.linspace(0.05, 0.95, P) * H
+    u, L = drex.velocity.corner_2d("X", "Z", U)
+    x = torch.as_tensor(finals).cuda()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ms = []
+    for _ in range(4):
+        ev[0].record()
+        paths = drex.pathlines.get_pathlines(x, u, L, [0, 0, -H], [W, 0, 0], 10.0, n_path_steps,
+                                             n_nodes=K, check=False)
+        ev[1].record()
+        torch.cuda.synchronize()
+        ms.append(ev[0].elapsed_time(ev[1]))
+    return {"particles": P, "intervals": n_path_steps, "nodes_per_interval": K,
+            "ms_per_trace": min(ms[1:]), "failed": int((paths.status != 0).sum()),
+            "what": "drex_pathlines_f64: backward Dormand-Prince trace + L tables, one launch"}
+
+
 def make_workload(name, P, n_steps, seed):
     if name == "simple_shear":
         return simple_shear_tables(P, n_steps, seed)
@@ -312,6 +336,7 @@ def run_gpu(args):
         dist.destroy_process_group()
     if rank != 0:
         return
+    pathline_info = trace_pathlines_on_device(drex, torch, P) if args.workload == "corner_flow" else None
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -374,6 +399,7 @@ def run_gpu(args):
                               "per launch) scaled by evaluations per launch" if traffic else None,
         },
         "step_ms": step_ms,
+        "pathlines": pathline_info,
         "cpu_baseline": cpu,
         "clocks": clocks,
     }

@@ -256,6 +256,54 @@ int drex_mindex_f32(const double *o_soa, int64_t S, int64_t N, int system_a, int
                     double *M, int64_t *counts, void *workspace, size_t workspace_bytes,
                     void *stream);
 
+/* ---- steady flows and pathlines (velocity.py:17-97, pathlines.py:10-116) ---------- */
+
+#define DREX_FLOW_SIMPLE_SHEAR 0 /* velocity.simple_shear_2d: i0 = direction, i1 = deformation
+                                    plane (axis indices 0..2), a = strain_rate */
+#define DREX_FLOW_CELL 1         /* velocity.cell_2d: i0 = horizontal, i1 = vertical,
+                                    a = velocity_edge, b = edge_length */
+#define DREX_FLOW_CORNER 2       /* velocity.corner_2d: i0 = horizontal, i1 = vertical,
+                                    a = plate_speed */
+typedef struct drex_flow_field {
+    int32_t kind, i0, i1;
+    double a, b;
+} drex_flow_field_t;
+
+#define DREX_PATH_OK 0
+#define DREX_PATH_NOT_FINITE 1 /* the field is NaN on the path (corner origin, outside the cell) */
+#define DREX_PATH_MAX_STEPS 2
+#define DREX_PATH_EMPTY 3      /* final location outside the box, or no strain budget */
+#define DREX_PATH_TIME_LIMIT 4 /* no event before t_limit: the path starts there (usable) */
+
+/* get_velocity(t, x) / get_velocity_gradient(t, x) of the analytic flows at P points
+ * x[P][3]; v[P][3] and L[P][9] (row-major 3x3), either may be NULL.  Points where the
+ * reference returns NaN or raises (corner origin, outside the cell) give NaN. */
+int drex_flow_field_f64(const drex_flow_field_t *field, const double *x, int64_t P, double *v,
+                        double *L, void *stream);
+
+/* pathlines.get_pathline for P particles at once: trace each final location backwards in
+ * the steady flow until `max_strain` (tensorial strain, utils.strain_increment) has been
+ * accumulated, the path leaves the box [min_coords, max_coords] (host arrays of 3), or
+ * t_limit (< 0; the reference uses -100 Myr in seconds) is reached.  Dormand-Prince 5(4),
+ * error weights atol + rtol |y| on position and strain alike.
+ *   timestamps_given = 0: timestamps[j][p] = linspace(t_start[p], 0, n_intervals + 1)[j]
+ *   timestamps_given = 1: the caller's ascending stamps (<= 0) are used as they are
+ * Outputs are interval-major: timestamps [n_intervals+1][P], positions [n_intervals+1][P][3],
+ * strains [n_intervals+1][P] (accumulated since the first stamp; may be NULL), and -- when
+ * n_nodes >= 2 -- node_positions [n_intervals][P][n_nodes][3] and L_nodes
+ * [n_intervals][P][n_nodes][9] at the Chebyshev-Lobatto nodes of every interval, i.e. block j
+ * of L_nodes is the DREX_L_CHEBYSHEV table drex_integrate_f64 takes for the step from
+ * timestamps[j] to timestamps[j+1] (either may be NULL).  step_times [P][max_record]
+ * (optional) receives the accepted solver times of the first pass, descending, closed by
+ * t_start; n_taken [P] (optional) the number of times recorded.  status [P]: DREX_PATH_*. */
+int drex_pathlines_f64(const drex_flow_field_t *field, const double *final_locations, int64_t P,
+                       const double *min_coords, const double *max_coords, double max_strain,
+                       double t_limit, double rtol, double atol, int64_t n_intervals,
+                       int32_t n_nodes, int32_t timestamps_given, int32_t max_steps,
+                       double *t_start, double *timestamps, double *positions, double *strains,
+                       double *node_positions, double *L_nodes, double *step_times,
+                       int32_t max_record, int32_t *n_taken, int32_t *status, void *stream);
+
 /* ---- measurement helper ----------------------------------------------------------- */
 
 /* Runs a dependent-DFMA loop that saturates the FP64 pipe and returns the measured FP64

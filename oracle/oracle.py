@@ -328,3 +328,79 @@ def resample_orientations(orientations, fractions, n_samples=None, seed=None):
         out_o[i] = orient[order][picks]
         out_f[i] = frac_ascending[picks]
     return out_o, out_f
+
+
+# ---- steady flows and pathlines ------------------------------------------
+
+
+def flow_eval(desc, x):
+    """numpy restatement of velocity._simple_shear_2d/_cell_2d/_corner_2d and their gradients
+    (reference velocity.py:17-97).  desc = (kind, i0, i1, a, b) with kind 0 simple shear
+    (a = strain_rate), 1 convection cell (a = velocity_edge, b = edge_length), 2 corner flow
+    (a = plate_speed).  Returns (v[3], L[3,3]); NaN where the reference returns NaN or raises."""
+    kind, a, b = int(desc[0]), int(desc[1]), int(desc[2])
+    pa, pb = float(desc[3]), float(desc[4])
+    x = np.asarray(x, dtype=np.float64)
+    v, L = np.zeros(3), np.zeros((3, 3))
+    if kind == 0:
+        v[a] = x[b] * pa
+        L[a, b] = 2 * pa
+    elif kind == 1:
+        if abs(x[a]) > pb / 2 or abs(x[b]) > pb / 2:
+            return np.full(3, np.nan), np.full((3, 3), np.nan)
+        cx, cz = np.cos(np.pi * x[a] / pb), np.cos(np.pi * x[b] / pb)
+        sx, sz = np.sin(np.pi * x[a] / pb), np.sin(np.pi * x[b] / pb)
+        v[a], v[b] = pa * cx * sz, -pa * sx * cz
+        L[a, a], L[a, b] = -np.pi / pb * sz * sx, np.pi / pb * cz * cx
+        L[b, b], L[b, a] = -np.pi / pb * cz * cx, np.pi / pb * sz * sx
+        L *= pa
+    else:
+        h, w = x[a], x[b]
+        if abs(h) < 1e-15 and abs(w) < 1e-15:
+            return np.full(3, np.nan), np.full((3, 3), np.nan)
+        pf = 2 * pa / np.pi
+        v[a] = pf * (np.arctan2(h, -w) + h * w / (h**2 + w**2))
+        v[b] = pf * w**2 / (h**2 + w**2)
+        L[a, a], L[a, b] = -(h**2) * w, h**3
+        L[b, a], L[b, b] = -h * w**2, h**2 * w
+        L *= 4 * pa / (np.pi * (h**2 + w**2) ** 2)
+    return v, L
+
+
+def trace_pathline(desc, final_location, min_coords, max_coords, max_strain, regular_steps,
+                   rtol=1e-12, atol=None, t_limit=-100e6 * 365.25 * 8.64e4):
+    """Restatement of pathlines.get_pathline (reference pathlines.py:10-116) as a clean ODE
+    problem: the state is (x, remaining strain) with d(strain)/dt = max|eig(sym L)|
+    (utils.strain_increment, utils.py:144-156), integrated backwards from t = 0 by scipy's
+    DOP853 at tight tolerance; terminal events are "strain budget used up" and "left the box"
+    (pathlines._is_inside, pathlines.py:133-138).  The reference accumulates the strain with
+    a rectangle rule over LSODA's (rtol 1e-5) steps, so it agrees with this only to its own
+    accuracy -- see tests/test_oracle.py for the measured gap.
+    Returns (timestamps[S+1], positions[S+1,3], strains[S+1])."""
+    from scipy.integrate import solve_ivp
+
+    lo, hi = np.asarray(min_coords, float), np.asarray(max_coords, float)
+    if atol is None:
+        atol = 1e-13 * (hi - lo).max()
+
+    def rhs(t, y):
+        v, L = flow_eval(desc, y[:3])
+        return np.append(v, np.abs(np.linalg.eigvalsh((L + L.T) / 2)).max())
+
+    def budget(t, y):
+        return y[3]
+
+    def inside(t, y):  # >= 0 inside the box; degenerate (zero-width) axes do not count
+        d = np.concatenate([(y[:3] - lo), (hi - y[:3])])
+        wide = np.concatenate([hi > lo, hi > lo])
+        return d[wide].min() if wide.any() else 1.0
+
+    budget.terminal = inside.terminal = True
+    budget.direction = inside.direction = -1
+    y0 = np.append(np.asarray(final_location, float), float(max_strain))
+    sol = solve_ivp(rhs, [0.0, t_limit], y0, method="DOP853", rtol=rtol, atol=atol,
+                    events=[budget, inside], dense_output=True)
+    t_start = sol.t[-1]
+    ts = np.linspace(t_start, 0.0, regular_steps + 1)
+    ys = sol.sol(ts).T
+    return ts, ys[:, :3], ys[:, 3] - ys[0, 3]

@@ -33,6 +33,8 @@ EXPORTS = (
     "drex_integrate_workspace_bytes", "drex_integrate_f64",
     "drex_voigt_average_f64", "drex_elasticity_components_f64",
     "drex_axis_scatter_f64",
+    "drex_flow_field_f64",
+    "drex_pathlines_f64",
     "drex_resample_workspace_bytes",
     "drex_resample_orientations_f64",
     "drex_mindex_workspace_bytes", "drex_mindex_theory_host", "drex_mindex_f32",
@@ -79,6 +81,25 @@ class DrexTolerances(ctypes.Structure):
         ("max_steps", ctypes.c_int32),
         ("method", ctypes.c_int32),
     ]
+
+
+class DrexFlowField(ctypes.Structure):
+    _fields_ = [
+        ("kind", ctypes.c_int32),
+        ("i0", ctypes.c_int32),
+        ("i1", ctypes.c_int32),
+        ("a", ctypes.c_double),
+        ("b", ctypes.c_double),
+    ]
+
+
+FLOW_SIMPLE_SHEAR, FLOW_CELL, FLOW_CORNER = 0, 1, 2
+PATH_MESSAGES = {
+    1: "the velocity field is not finite on the pathline",
+    2: "pathline tracer exceeded its step budget",
+    3: "empty pathline: the final location is outside the domain or there is no strain budget",
+    4: "pathline reached the time limit before accumulating the target strain",
+}
 
 
 def sources():
@@ -137,6 +158,11 @@ def _declare(lib):
     lib.drex_voigt_average_f64.argtypes = [vp, vp, vp, vp, i64, i64, vp, i32, vp]
     lib.drex_elasticity_components_f64.argtypes = [vp, i64, vp, vp]
     lib.drex_axis_scatter_f64.argtypes = [vp, i64, i64, i32, vp, vp]
+    lib.drex_flow_field_f64.argtypes = [c.POINTER(DrexFlowField), vp, i64, vp, vp, vp]
+    lib.drex_pathlines_f64.argtypes = (
+        [c.POINTER(DrexFlowField), vp, i64, c.POINTER(c.c_double * 3), c.POINTER(c.c_double * 3)]
+        + [dbl] * 4 + [i64, i32, i32, i32] + [vp] * 7 + [i32, vp, vp, vp]
+    )
     lib.drex_resample_workspace_bytes.restype = szt
     lib.drex_resample_workspace_bytes.argtypes = [i64, i64]
     lib.drex_resample_orientations_f64.argtypes = [vp, vp, vp, i64, i64, i64, vp, vp, vp, szt, vp]

@@ -15,6 +15,7 @@
 #include "drex_derivatives.cuh"
 #include "drex_diagnostics.cuh"
 #include "drex_integrate.cuh"
+#include "drex_pathlines.cuh"
 #include "drex_resample.cuh"
 
 namespace {
@@ -404,6 +405,74 @@ int drex_resample_orientations_f64(const double *o_aos, const double *f, const d
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     drex::resample_kernel<<<(unsigned)S, drex::RESAMPLE_THREADS, smem, (cudaStream_t)stream>>>(
         o_aos, f, uniforms, N, npad, n_samples, out_o, out_f, (unsigned char *)workspace);
+    DREX_CUDA_CHECK(cudaGetLastError());
+    return DREX_OK;
+}
+
+// ---- steady flows and pathlines ------------------------------------------------------------
+
+static int make_flow_field(const drex_flow_field_t *field, drex::FlowField *out) {
+    if (!field) return fail(DREX_E_INVALID, "flow field: null pointer");
+    if (field->kind < 0 || field->kind > 2)
+        return fail(DREX_E_INVALID, "flow field: unknown kind %d", field->kind);
+    if (field->i0 < 0 || field->i0 > 2 || field->i1 < 0 || field->i1 > 2 || field->i0 == field->i1)
+        return fail(DREX_E_INVALID, "flow field: axes must be two different indices in 0..2");
+    if (field->kind == DREX_FLOW_CELL && !(field->b > 0.0))
+        return fail(DREX_E_INVALID, "edge length of 2D cell must be positive, not %g", field->b);
+    out->kind = field->kind; out->i0 = field->i0; out->i1 = field->i1;
+    out->a = field->a; out->b = field->b;
+    return DREX_OK;
+}
+
+int drex_flow_field_f64(const drex_flow_field_t *field, const double *x, int64_t P, double *v,
+                        double *L, void *stream) {
+    drex::FlowField fl;
+    if (int rc = make_flow_field(field, &fl)) return rc;
+    if (P < 0) return fail(DREX_E_INVALID, "negative size");
+    if (P == 0) return DREX_OK;
+    if (!x) return fail(DREX_E_INVALID, "drex_flow_field_f64: null pointer");
+    drex::flow_field_kernel<<<(unsigned)((P + 127) / 128), 128, 0, (cudaStream_t)stream>>>(fl, x, P, v, L);
+    DREX_CUDA_CHECK(cudaGetLastError());
+    return DREX_OK;
+}
+
+int drex_pathlines_f64(const drex_flow_field_t *field, const double *final_locations, int64_t P,
+                       const double *min_coords, const double *max_coords, double max_strain,
+                       double t_limit, double rtol, double atol, int64_t n_intervals,
+                       int32_t n_nodes, int32_t timestamps_given, int32_t max_steps,
+                       double *t_start, double *timestamps, double *positions, double *strains,
+                       double *node_positions, double *L_nodes, double *step_times,
+                       int32_t max_record, int32_t *n_taken, int32_t *status, void *stream) {
+    drex::PathlineArgs A;
+    if (int rc = make_flow_field(field, &A.field)) return rc;
+    if (P < 0 || n_intervals < 0) return fail(DREX_E_INVALID, "negative size");
+    if (P == 0) return DREX_OK;
+    if (!final_locations || !min_coords || !max_coords || !status)
+        return fail(DREX_E_INVALID, "drex_pathlines_f64: null pointer");
+    if (!(t_limit < 0.0)) return fail(DREX_E_INVALID, "drex_pathlines_f64: t_limit must be negative");
+    if (!(rtol > 0.0) || !(atol >= 0.0)) return fail(DREX_E_INVALID, "drex_pathlines_f64: bad tolerances");
+    if (n_nodes == 1 || n_nodes < 0 || n_nodes > 129)
+        return fail(DREX_E_INVALID, "drex_pathlines_f64: n_nodes must be 0 or in 2..129");
+    if ((positions || n_intervals > 0 || timestamps_given) && !timestamps)
+        return fail(DREX_E_INVALID, "drex_pathlines_f64: timestamps buffer required");
+    if ((node_positions || L_nodes) && (n_nodes < 2 || !positions))
+        return fail(DREX_E_INVALID, "drex_pathlines_f64: node tables need n_nodes >= 2 and positions");
+    if (step_times && max_record <= 0)
+        return fail(DREX_E_INVALID, "drex_pathlines_f64: max_record must be positive");
+    for (int i = 0; i < 3; ++i) {
+        if (!(min_coords[i] <= max_coords[i]))
+            return fail(DREX_E_INVALID, "drex_pathlines_f64: min_coords must not exceed max_coords");
+        A.box.lo[i] = min_coords[i];
+        A.box.hi[i] = max_coords[i];
+    }
+    A.final_locations = final_locations; A.P = P;
+    A.max_strain = max_strain; A.t_limit = t_limit; A.rtol = rtol; A.atol = atol;
+    A.n_intervals = n_intervals; A.n_nodes = (node_positions || L_nodes) ? n_nodes : 0;
+    A.timestamps_given = timestamps_given; A.max_steps = max_steps > 0 ? max_steps : 1000000;
+    A.t_start = t_start; A.timestamps = timestamps; A.positions = positions; A.strains = strains;
+    A.node_positions = node_positions; A.L_nodes = L_nodes; A.step_times = step_times;
+    A.max_record = max_record; A.n_taken = n_taken; A.status = status;
+    drex::pathlines_kernel<<<(unsigned)((P + 127) / 128), 128, 0, (cudaStream_t)stream>>>(A);
     DREX_CUDA_CHECK(cudaGetLastError());
     return DREX_OK;
 }

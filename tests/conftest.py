@@ -67,3 +67,8 @@ def oracle():
 
     _oracle.build()
     return _oracle
+
+
+@pytest.fixture(scope="session")
+def golden_pathlines():
+    return _load("pathlines.npz")

@@ -807,3 +807,187 @@ def test_ensemble_resampled_misorientation_indices(drex, golden_config1):
     # the reference's own value for its resampled config-1 texture
     g = golden_config1
     assert abs(drex.misorientation_index(g["resampled_o"], system) - float(g["resampled_M"])) < 2e-4
+
+
+# ------------------------------------------------------------------ flows and pathlines (f1)
+
+FLOW_NAMES = ("shear", "shear_zx", "cell", "cell_yx", "corner", "corner_zy")
+PATH_CASES = {"corner": 50, "cell": 20, "shear": 10}
+AXES = "XYZ"
+
+
+def _flow_from_desc(drex, desc):
+    kind, i0, i1 = (int(v) for v in desc[:3])
+    if kind == 0:
+        return drex.velocity.simple_shear_2d(AXES[i0], AXES[i1], float(desc[3]))
+    if kind == 1:
+        return drex.velocity.cell_2d(AXES[i0], AXES[i1], float(desc[3]), float(desc[4]))
+    return drex.velocity.corner_2d(AXES[i0], AXES[i1], float(desc[3]))
+
+
+def test_flow_fields_match_golden(drex, golden_pathlines):
+    """velocity.py:17-97: batched and single-point evaluation against the reference's values
+    (1e-13 relative: the reference is numba fastmath)."""
+    g = golden_pathlines
+    for name in FLOW_NAMES:
+        u, L = _flow_from_desc(drex, g[f"f_{name}_desc"])
+        x = g[f"f_{name}_x"]
+        v_all, L_all = drex.velocity.evaluate(u, x)
+        nt.assert_allclose(v_all, g[f"f_{name}_v"], rtol=1e-13, atol=1e-300, err_msg=name)
+        nt.assert_allclose(L_all, g[f"f_{name}_L"], rtol=1e-13, atol=1e-300, err_msg=name)
+        for k in (0, 1, 17):
+            nt.assert_array_equal(u(np.nan, x[k]), v_all[k])
+            nt.assert_array_equal(L(np.nan, x[k]), L_all[k])
+    # reference doctests (velocity.py:112-131, 180-201)
+    u, L = drex.velocity.simple_shear_2d("X", "Z", 1e-4)
+    nt.assert_array_equal(u(np.nan, np.array([0, 0, 1])), [1e-4, 0, 0])
+    nt.assert_array_equal(L(np.nan, np.array([0.0, 0.0, 1.0])), [[0, 0, 2e-4], [0, 0, 0], [0, 0, 0]])
+    u, L = drex.velocity.cell_2d("X", "Z", 1)
+    nt.assert_allclose(u(np.nan, np.array([-0.5, 0.0, 0.0])), [0, 0, 0.70710678], atol=1e-8)
+    nt.assert_allclose(L(np.nan, np.array([0.5, 0.0, 0.5])),
+                       [[-0.78539816, 0, 0.78539816], [0, 0, 0], [0.78539816, 0, -0.78539816]], atol=1e-8)
+    with pytest.raises(ValueError, match="outside domain"):
+        u(np.nan, np.array([1.5, 0.0, 0.0]))
+    with pytest.raises(ValueError, match="unsupported shear type"):
+        drex.velocity.simple_shear_2d("X", "X", 1.0)
+    with pytest.raises(ValueError, match="edge length"):
+        drex.velocity.cell_2d("X", "Z", 1.0, -2.0)
+    with pytest.raises(ValueError, match="no CPU fallback"):
+        drex.pathlines.get_pathline(np.zeros(3), lambda t, x: x, lambda t, x: np.eye(3),
+                                    -np.ones(3), np.ones(3), 1.0)
+
+
+def test_pathlines_match_oracle_and_reference(drex, oracle, golden_pathlines):
+    """pathlines.get_pathline batched on the device: against the oracle (DOP853 at 1e-12) to
+    1e-8 of the domain size / of the time span, and against the reference's own LSODA
+    pathlines at the accuracy those have (see tests/test_oracle.py)."""
+    g = golden_pathlines
+    for name, steps in PATH_CASES.items():
+        desc, box = g[f"p_{name}_desc"], g[f"p_{name}_box"]
+        finals, max_strain = g[f"p_{name}_final"], float(g[f"p_{name}_max_strain"])
+        scale = np.abs(box).max()
+        u, L = _flow_from_desc(drex, desc)
+        paths = drex.pathlines.get_pathlines(finals, u, L, box[0], box[1], max_strain, steps)
+        ts = paths.timestamps.cpu().numpy()
+        xs = paths.positions.cpu().numpy()
+        strains = paths.strains.cpu().numpy()
+        node_x = paths.node_positions.cpu().numpy()
+        node_L = paths.L_nodes.cpu().numpy()
+        assert ts.shape == (steps + 1, len(finals)) and np.all(ts[-1] == 0.0)
+        nt.assert_array_equal(paths.t_start.cpu().numpy(), ts[0])
+        nt.assert_array_equal(xs[-1], finals)
+        for p, final in enumerate(finals):
+            ots, oxs, ostr = oracle.trace_pathline(desc, final, box[0], box[1], max_strain, steps)
+            nt.assert_allclose(ts[0, p], ots[0], rtol=1e-8, err_msg=name)
+            nt.assert_array_equal(ts[:, p], np.linspace(ts[0, p], 0.0, steps + 1))
+            nt.assert_allclose(xs[:, p], oxs, rtol=0, atol=1e-8 * scale, err_msg=name)
+            nt.assert_allclose(strains[:, p], ostr, rtol=0, atol=1e-8 * max_strain, err_msg=name)
+            # tables: node 0 / K-1 are the stamps, L is the field's gradient at the node
+            nt.assert_array_equal(node_x[:, p, 0], xs[:-1, p])
+            nt.assert_array_equal(node_x[:, p, -1], xs[1:, p])
+            for j in (0, steps // 2, steps - 1):
+                for k in (0, 3, 8):
+                    _, L_ref = oracle.flow_eval(desc, node_x[j, p, k])
+                    nt.assert_allclose(node_L[j, p, k], L_ref, rtol=1e-13, atol=1e-300)
+            # the reference itself
+            t_ref, x_ref = g[f"p_{name}_t"][p], g[f"p_{name}_x"][p]
+            nt.assert_allclose(ts[0, p], t_ref[0], rtol=2e-2, err_msg=name)
+            get_position = paths.position_callable(p)
+            common = t_ref >= ts[0, p]
+            mine = np.array([get_position(t) for t in t_ref[common]])
+            nt.assert_allclose(mine, x_ref[common], rtol=0, atol=2e-4 * scale, err_msg=name)
+
+
+def test_get_pathline_drop_in(drex, oracle, golden_pathlines):
+    """Single-particle signature of the reference (pathlines.py:10-19): regular stamps, the
+    solver's own stamps, and the position callable."""
+    g = golden_pathlines
+    desc, box = g["p_corner_desc"], g["p_corner_box"]
+    u, L = _flow_from_desc(drex, desc)
+    final = g["p_corner_final"][1]
+    ts, get_position = drex.pathlines.get_pathline(final, u, L, box[0], box[1], 10, regular_steps=50)
+    assert ts.shape == (51,) and ts[-1] == 0.0 and np.all(np.diff(ts) > 0)
+    nt.assert_allclose(ts[0], g["p_corner_t"][1][0], rtol=1e-3)
+    fine_t, fine_x, _ = oracle.trace_pathline(desc, final, box[0], box[1], 10, 400)
+    for t, x in zip(fine_t[::7], fine_x[::7]):  # between the stamps: the Chebyshev interpolant
+        nt.assert_allclose(get_position(t), x, rtol=0, atol=1e-7 * 1e6)
+    nt.assert_array_equal(get_position(0.0), final)
+    # solver stamps: irregular, same span, a few dozen steps like the reference's 49
+    ts2, get_position2 = drex.pathlines.get_pathline(final, u, L, box[0], box[1], 10)
+    assert ts2[-1] == 0.0 and np.all(np.diff(ts2) > 0) and 10 < len(ts2) < 200
+    nt.assert_allclose(ts2[0], ts[0], rtol=1e-4)
+    nt.assert_allclose(get_position2(ts2[3]), get_position(ts2[3]), rtol=0, atol=1e-4 * 1e6)
+    # outside the box / no budget
+    with pytest.raises(ValueError, match="empty pathline"):
+        drex.pathlines.get_pathline(np.array([2e6, 0.0, -1e5]), u, L, box[0], box[1], 10, regular_steps=5)
+    with pytest.raises(ValueError, match="not finite"):
+        drex.pathlines.get_pathline(np.zeros(3), u, L, box[0], box[1], 10, regular_steps=5)
+
+
+def test_full_size_pathline_invariants(drex):
+    """Config 4's particle cloud (10^4 corner-flow exits): the stream function
+    psi = (2U/pi) z atan2(x, -z) is constant along every traced pathline, strains are
+    monotone, and a path either used its whole strain budget or starts on the box."""
+    import torch
+
+    U, H, W = 2.0 / (100 * 365 * 86400), 2.0e5, 1.0e6
+    u, L = drex.velocity.corner_2d("X", "Z", U)
+    P, S = 10000, 50
+    finals = np.zeros((P, 3))
+    finals[:, 0] = W
+    finals[:, 2] = np.linspace(-0.02, -0.98, P) * H
+    seen_used_up = seen_on_box = False
+    for max_strain in (10.0, 0.3):
+        paths = drex.pathlines.get_pathlines(finals, u, L, [0, 0, -H], [W, 0, 0], max_strain, S)
+        assert int(paths.status.abs().sum()) == 0
+        x = paths.positions
+        psi = x[..., 2] * torch.atan2(x[..., 0], -x[..., 2])
+        drift = (psi - psi[-1]).abs().max(dim=0).values / psi[-1].abs()
+        assert float(drift.max()) < 1e-8
+        strains = paths.strains
+        assert bool((strains[1:] >= strains[:-1]).all()) and bool((strains[0] == 0).all())
+        used_up = (strains[-1] - max_strain).abs() < 1e-7 * max_strain
+        on_box = ((x[0, :, 2] + H).abs() < 1e-6 * H) | (x[0, :, 0].abs() < 1e-6 * W)
+        assert bool((used_up | on_box).all())
+        assert bool((strains[-1] <= max_strain * (1 + 1e-7)).all())
+        seen_used_up |= bool(used_up.any())
+        seen_on_box |= bool(on_box.any())
+        assert bool((paths.timestamps[1:] > paths.timestamps[:-1]).all())
+    assert seen_used_up and seen_on_box
+
+
+def test_ensemble_along_device_pathlines_matches_mineral_path(drex):
+    """The device tables (traced pathline -> L at Chebyshev nodes) drive the integrator to the
+    same state as the reference-style driver loop (tests/test_corner_flow_2d.py:57-88) with
+    callables tabulated on the host."""
+    import torch
+    from scipy.spatial.transform import Rotation
+
+    U, H, W = 2.0 / (100 * 365 * 86400), 2.0e5, 1.0e6
+    u, L = drex.velocity.corner_2d("X", "Z", U)
+    P, N, S = 3, 128, 8
+    finals = np.array([[W, 0.0, -0.15 * H], [W, 0.0, -0.4 * H], [0.5 * W, 0.0, -0.7 * H]])
+    paths = drex.pathlines.get_pathlines(finals, u, L, [0, 0, -H], [W, 0, 0], 1.5, S)
+    o0 = np.stack([[Rotation.random(N, random_state=3 * p + k).as_matrix() for k in range(2)]
+                   for p in range(P)])
+    ens = drex.ParticleEnsemble(P, N, TWO_PHASE, orientations=o0)
+    tol = ens.tolerances(rtol=1e-11, atol_abs=1e-13, atol_rel=0.0)
+    for j in range(S):
+        t0, t1, L_nodes = paths.interval(j)
+        ens.update(t0, t1, L_nodes, kind=drex._lib.L_CHEBYSHEV, tol=tol)
+    o_dev = ens.orientations().cpu().numpy()
+    f_dev = ens.fractions().cpu().numpy()
+    F_dev = ens.deformation_gradients().cpu().numpy()
+    for p in (0, 2):
+        ts, get_position = drex.pathlines.get_pathline(finals[p], u, L, [0, 0, -H], [W, 0, 0], 1.5,
+                                                       regular_steps=S)
+        nt.assert_allclose(ts, paths.timestamps[:, p].cpu().numpy(), rtol=1e-12)
+        mins = [drex.Mineral(0, 0, 4, n_grains=N, orientations_init=o0[p, 0].copy()),
+                drex.Mineral(1, 5, 4, n_grains=N, orientations_init=o0[p, 1].copy())]
+        F = np.eye(3)
+        for j in range(S):
+            F = drex.update_all(mins, TWO_PHASE, F, L, (ts[j], ts[j + 1], get_position), **TIGHT)
+        for k in range(2):
+            nt.assert_allclose(o_dev[p, k], mins[k].orientations[-1], rtol=0, atol=2e-8)
+            nt.assert_allclose(f_dev[p, k], mins[k].fractions[-1], rtol=1e-6, atol=1e-10)
+        nt.assert_allclose(F_dev[p], F, rtol=1e-8, atol=1e-10)

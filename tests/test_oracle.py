@@ -213,3 +213,44 @@ def test_resample_orientations_golden(oracle, golden_resample, golden_integrate)
         vals, counts = np.unique(ef[t], return_counts=True)
         untied = np.isin(rf[t], vals[counts == 1])
         assert np.array_equal(ro[t][untied], g["e_o"][t][untied])
+
+
+FLOW_NAMES = ("shear", "shear_zx", "cell", "cell_yx", "corner", "corner_zy")
+PATH_CASES = {"corner": 50, "cell": 20, "shear": 10}
+
+
+def test_flow_fields_match_reference(oracle, golden_pathlines):
+    """velocity.py:17-97 closed forms (the reference is numba fastmath: ~1 ulp noise)."""
+    g = golden_pathlines
+    for name in FLOW_NAMES:
+        desc, x = g[f"f_{name}_desc"], g[f"f_{name}_x"]
+        for xi, v_ref, L_ref in zip(x, g[f"f_{name}_v"], g[f"f_{name}_L"]):
+            v, L = oracle.flow_eval(desc, xi)
+            nt.assert_allclose(v, v_ref, rtol=1e-13, atol=1e-300, err_msg=name)
+            nt.assert_allclose(L, L_ref, rtol=1e-13, atol=1e-300, err_msg=name)
+
+
+def test_pathlines_match_reference(oracle, golden_pathlines):
+    """pathlines.get_pathline (pathlines.py:10-116).  The reference's positions carry LSODA's
+    rtol = 1e-5 and its start time additionally a rectangle-rule strain sum and a crude
+    boundary event, so the comparison is made at that accuracy: the same point of the same
+    streamline at the same time."""
+    from scipy.interpolate import CubicSpline
+
+    g = golden_pathlines
+    for name, steps in PATH_CASES.items():
+        desc, box = g[f"p_{name}_desc"], g[f"p_{name}_box"]
+        scale = np.abs(box).max()
+        max_strain = float(g[f"p_{name}_max_strain"])
+        for final, t_ref, x_ref in zip(g[f"p_{name}_final"], g[f"p_{name}_t"], g[f"p_{name}_x"]):
+            ts, xs, strains = oracle.trace_pathline(desc, final, box[0], box[1], max_strain, steps)
+            assert ts.shape == t_ref.shape and ts[-1] == 0.0
+            print(name, final, "t_start oracle/reference - 1 =", ts[0] / t_ref[0] - 1)
+            nt.assert_allclose(ts[0], t_ref[0], rtol=2e-2, err_msg=name)
+            assert strains[0] == 0.0 and strains[-1] <= max_strain * (1 + 1e-9)
+            # positions along the common part of the path, at the reference's own times
+            common = t_ref >= ts[0]
+            fine_t, fine_x, _ = oracle.trace_pathline(desc, final, box[0], box[1], max_strain, 2000)
+            spline = CubicSpline(fine_t, fine_x)
+            nt.assert_allclose(spline(t_ref[common]), x_ref[common], atol=2e-4 * scale, rtol=0,
+                               err_msg=name)
