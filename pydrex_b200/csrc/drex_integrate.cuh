@@ -164,9 +164,11 @@ __device__ inline void eval_L(const IntegrateArgs &A, int64_t ip, double t, doub
 // One component c of L(t): lets 27 lanes (3 stage times x 9 components) evaluate the three
 // stage matrices in parallel instead of one lane looping over all of it -- this sits on the
 // serial path of every step while the other 15 warps wait at a barrier.
-__device__ inline double eval_L_component(const IntegrateArgs &A, int64_t ip, double t, double ta,
-                                          double tb, int c, const double *xnode) {
-    const double *nodes = A.L_nodes + ip * A.K * 9 + c;
+__device__ inline double eval_L_component(const IntegrateArgs &A, const double *table, double t,
+                                          double ta, double tb, int c, const double *xnode) {
+    // `table` is the particle's node table [K][9]: the shared-memory copy made once per
+    // system when K <= 33, otherwise the global one
+    const double *nodes = table + c;
     if (A.L_kind == 0 || A.K == 1) return nodes[0];
     const double span = tb - ta;
     const double x = (span != 0.0) ? (t - ta) / span : 0.0;
@@ -177,12 +179,19 @@ __device__ inline double eval_L_component(const IntegrateArgs &A, int64_t ip, do
         if (j > A.K - 2) j = A.K - 2;
         return nodes[j * 9] + (pos - j) * (nodes[(j + 1) * 9] - nodes[j * 9]);
     }
-    double numer = 0.0, denom = 0.0;
+    // barycentric form without an exit inside the loop, so that the K iterations overlap: a
+    // node hit (|x - x_j| < 1e-15) is remembered and its term replaced by a harmless one
+    double numer = 0.0, denom = 0.0, hit_value = 0.0;
+    bool hit = false;
     const int K = A.K;
     for (int j = 0; j < K; ++j) {
         const double xj = (j < 33) ? xnode[j] : 0.5 * (1.0 - cospi((double)j / (double)(K - 1)));
-        const double d = x - xj;
-        if (fabs(d) < 1e-15) return nodes[j * 9];
+        const double v = nodes[j * 9];
+        double d = x - xj;
+        const bool here = fabs(d) < 1e-15;
+        hit_value = (here && !hit) ? v : hit_value;
+        hit = hit || here;
+        d = here ? 1.0 : d;
         // 1/d by the hardware approximation + two Newton steps (full double accuracy; the
         // barycentric form uses the same weights above and below the fraction bar)
         double r;
@@ -192,9 +201,9 @@ __device__ inline double eval_L_component(const IntegrateArgs &A, int64_t ip, do
         double w = (j & 1) ? -r : r;
         if (j == 0 || j == K - 1) w *= 0.5;
         denom += w;
-        numer = fma(w, nodes[j * 9], numer);
+        numer = fma(w, v, numer);
     }
-    return numer / denom;
+    return hit ? hit_value : numer / denom;
 }
 
 // The flow quantities of `n` stage times (n = 1 or 3) evaluated cooperatively by warp 0:
@@ -202,9 +211,9 @@ __device__ inline double eval_L_component(const IntegrateArgs &A, int64_t ip, do
 // normalise.  This is serial work every other warp of the CTA waits for at a barrier, so
 // it is spread over the lanes instead of being looped by one thread.
 struct StageFlow;
-__device__ inline void warp_stage_flows(const IntegrateArgs &A, int64_t ip, StageFlow *st, int first,
-                                        int n, double t0s, double t1s, double t2s, double ta,
-                                        double tb, const double *xnode, int lane);
+__device__ inline void warp_stage_flows(const IntegrateArgs &A, const double *table, StageFlow *st,
+                                        int first, int n, double t0s, double t1s, double t2s,
+                                        double ta, double tb, const double *xnode, int lane);
 
 // Per-stage flow quantities shared by the CTA.
 struct StageFlow {
@@ -224,6 +233,7 @@ struct StepShared {
     double red[64];
     uint64_t mbar[INT_WARPS];
     double xnode[33];      // Chebyshev-Lobatto abscissae of the L(t) table (K <= 33)
+    double Ltab[33 * 9];   // this particle's L(t) node table (K <= 33; larger ones stay global)
     int sys, flag;
     int const_flow;        // L(t) constant over the interval: stage flows computed once
 };
@@ -239,14 +249,14 @@ struct StepShared {
 #define BS_E3 (1.0 / 9.0)
 #define BS_E4 (-1.0 / 8.0)
 
-__device__ inline void warp_stage_flows(const IntegrateArgs &A, int64_t ip, StageFlow *st, int first,
-                                        int n, double t0s, double t1s, double t2s, double ta,
-                                        double tb, const double *xnode, int lane) {
+__device__ inline void warp_stage_flows(const IntegrateArgs &A, const double *table, StageFlow *st,
+                                        int first, int n, double t0s, double t1s, double t2s,
+                                        double ta, double tb, const double *xnode, int lane) {
     const int si = lane / 9, c = lane - 9 * si;
     const bool active = lane < 9 * n;
     if (active) {
         const double t = (si == 0) ? t0s : ((si == 1) ? t1s : t2s);
-        st[first + si].Lraw[c] = eval_L_component(A, ip, t, ta, tb, c, xnode);
+        st[first + si].Lraw[c] = eval_L_component(A, table, t, ta, tb, c, xnode);
     }
     __syncwarp();
     if (lane < n) st[first + lane].s = strain_rate_max(st[first + lane].Lraw);
@@ -399,12 +409,15 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
         double *kf_cur = slot + SLOT_KFA * Npad, *kf_nxt = slot + SLOT_KFB * Npad;
 
         // ---- initial slope at t0 (one right-hand side) --------------------------------
+        const double *Ltable = (A.K <= 33) ? sh.Ltab : A.L_nodes + ip * A.K * 9;
         if (tid < 32) {
             if (A.L_kind == 2)
                 for (int j = lane; j < A.K && j < 33; j += 32)
                     sh.xnode[j] = 0.5 * (1.0 - cospi((double)j / (double)(A.K - 1)));
+            if (A.K <= 33)
+                for (int j = lane; j < A.K * 9; j += 32) sh.Ltab[j] = A.L_nodes[ip * A.K * 9 + j];
             __syncwarp();
-            warp_stage_flows(A, ip, sh.st, 2, 1, t_begin, t_begin, t_begin, t_begin, t_end, sh.xnode, lane);
+            warp_stage_flows(A, Ltable, sh.st, 2, 1, t_begin, t_begin, t_begin, t_begin, t_end, sh.xnode, lane);
         }
         if (tid == 0) {
             const double *L = sh.st[2].Lraw;
@@ -516,7 +529,7 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
 
             // stage flows at t + h/2, t + 3h/4, t + h (three lanes), then F by lane 0
             if (!sh.const_flow && tid < 32)
-                warp_stage_flows(A, ip, sh.st, 0, 3, sh.t + BS_A21 * sh.h, sh.t + BS_A32 * sh.h,
+                warp_stage_flows(A, Ltable, sh.st, 0, 3, sh.t + BS_A21 * sh.h, sh.t + BS_A32 * sh.h,
                                  sh.t + sh.h, t_begin, t_end, sh.xnode, lane);
             __syncthreads();
             if (tid == 0) {
