@@ -63,12 +63,13 @@ template <bool PROBE, int MODE = GRAIN_RUNTIME>
 __device__ __forceinline__ void grain_rhs(const double (&a)[9], const double (&D)[9],
                                           const double (&L)[9], const FabricConsts &fc,
                                           const double *__restrict__ mt, GrainOut &out,
-                                          GrainProbe *probe) {
-    // D.a_r for the three crystal axes (rows of a)
-    double Da0[3], Da1[3], Da2[3];
+                                          GrainProbe *probe, double half_scale = 0.5) {
+    const bool olivine = (MODE == GRAIN_RUNTIME) ? (fc.phase == 0) : (MODE != GRAIN_ENSTATITE);
+    const bool inf3 = fc.inf_index == 3;  // CTA-uniform
+    // D.a_r for the crystal axes (rows of a)
+    double Da1[3], Da2[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        Da0[i] = D[3 * i] * a[0] + D[3 * i + 1] * a[1] + D[3 * i + 2] * a[2];
         Da1[i] = D[3 * i] * a[3] + D[3 * i + 1] * a[4] + D[3 * i + 2] * a[5];
         Da2[i] = D[3 * i] * a[6] + D[3 * i + 1] * a[7] + D[3 * i + 2] * a[8];
     }
@@ -77,21 +78,28 @@ __device__ __forceinline__ void grain_rhs(const double (&a)[9], const double (&D
     const double I0 = a[0] * Da1[0] + a[1] * Da1[1] + a[2] * Da1[2];
     const double I1 = a[0] * Da2[0] + a[1] * Da2[1] + a[2] * Da2[2];
     const double I2 = a[6] * Da1[0] + a[7] * Da1[1] + a[8] * Da1[2];
-    const double I3 = a[6] * Da0[0] + a[7] * Da0[1] + a[8] * Da0[2];
+    // I3 = a2.D.a0 equals I1 = a0.D.a2 up to rounding (D is symmetric).  Olivine fabrics
+    // whose fourth system has infinite CRSS never use its value (only the all-zero test
+    // below looks at it), so the 12 operations are skipped there.
+    double I3 = I1;
+    if (PROBE || !olivine || !inf3) {
+        double Da0[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) Da0[i] = D[3 * i] * a[0] + D[3 * i + 1] * a[1] + D[3 * i + 2] * a[2];
+        I3 = a[6] * Da0[0] + a[7] * Da0[1] + a[8] * Da0[2];
+    }
     if (PROBE) {
         probe->inv[0] = I0; probe->inv[1] = I1; probe->inv[2] = I2; probe->inv[3] = I3;
     }
 
-    double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;  // relative slip rates by system
+    double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;  // 2 x relative slip rates by system
     double w0 = 0.0, w1 = 0.0, w2 = 0.0;            // |gamma_i|^(p/n) for i = 0..2
     const bool all_zero = (I0 == 0.0) & (I1 == 0.0) & (I2 == 0.0) & (I3 == 0.0);
-    const bool olivine = (MODE == GRAIN_RUNTIME) ? (fc.phase == 0) : (MODE != GRAIN_ENSTATITE);
     const bool default_exponents =
         (MODE == GRAIN_RUNTIME) ? (fc.default_exponents != 0) : (MODE == GRAIN_OLIVINE_DEFAULT);
 
     if (olivine) {
         // the three finite-CRSS systems (x, y, z); z is natural index 2 or 3 (CTA-uniform)
-        const bool inf3 = fc.inf_index == 3;
         const double vz = inf3 ? I2 : I3;
         const double rz = inf3 ? fc.inv_crss[2] : fc.inv_crss[3];
         const double cz = inf3 ? fc.crss[2] : fc.crss[3];
@@ -118,10 +126,11 @@ __device__ __forceinline__ void grain_rhs(const double (&a)[9], const double (&D
             rz_ = qz * pow_nonneg(az, fc.n_minus_1, mt);
             px = pow_nonneg(ax, fc.p, mt); py = pow_nonneg(ay, fc.p, mt); pz = pow_nonneg(az, fc.p, mt);
         }
-        // the softest system slips at rate exactly 1 (core.py:567)
-        g0 = x_max ? 1.0 : rx;
-        g1 = y_max ? 1.0 : ry;
-        const double gz = z_max ? 1.0 : rz_;
+        // the softest system slips at rate exactly 1 (core.py:567); g carries the factor 2
+        // of the Schmid tensor (exact scaling, G below is bit-identical to 2 (a0 u + a2 v))
+        g0 = x_max ? 2.0 : rx + rx;
+        g1 = y_max ? 2.0 : ry + ry;
+        const double gz = z_max ? 2.0 : rz_ + rz_;
         w0 = x_max ? 1.0 : px;
         w1 = y_max ? 1.0 : py;
         const double wz = z_max ? 1.0 : pz;
@@ -130,7 +139,7 @@ __device__ __forceinline__ void grain_rhs(const double (&a)[9], const double (&D
         w2 = inf3 ? wz : 0.0;  // C-type: natural index 2 is the infinite-CRSS system
     } else {
         // enstatite: only (100)[001] slips (core.py:731-739)
-        g3 = (fabs(I3) > 1e-15) ? 1.0 : 0.0;
+        g3 = (fabs(I3) > 1e-15) ? 2.0 : 0.0;
     }
 
     // Schmid tensor G = 2 sum_s gamma_s l_s (x) n_s = 2 [a0 (x) u + a2 (x) v],
@@ -142,37 +151,42 @@ __device__ __forceinline__ void grain_rhs(const double (&a)[9], const double (&D
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
-            for (int j = 0; j < 3; ++j) G[3 * i + j] = 2.0 * (a[i] * u[j] + a[6 + i] * v[j]);
+            for (int j = 0; j < 3; ++j) G[3 * i + j] = a[i] * u[j] + a[6 + i] * v[j];
     }
     // slip rate on the softest system (core.py:513-538)
     // three independent partial sums per row instead of one 12-term chain: the FP64 pipe has
     // a long dependent-issue latency and only four warps per scheduler to hide it
     double num, den;
+    double ga[3], wl[3];  // antisymmetric parts G_jk - G_kj and L_jk - L_kj, k = j + 1 (mod 3)
     {
         double nr[3], dr[3];
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
             const int k = (j + 1) % 3;
-            const double ga = G[3 * j + k] - G[3 * k + j];
+            ga[j] = G[3 * j + k] - G[3 * k + j];
+            wl[j] = L[3 * j + k] - L[3 * k + j];
             double n2 = G[3 * j] * L[3 * j], d2 = G[3 * j] * G[3 * j];
             n2 = fma(G[3 * j + 1], L[3 * j + 1], n2);
             d2 = fma(G[3 * j + 1], G[3 * j + 1], d2);
             n2 = fma(G[3 * j + 2], L[3 * j + 2], n2);
             d2 = fma(G[3 * j + 2], G[3 * j + 2], d2);
-            nr[j] = fma(2.0, n2, -(L[3 * j + k] - L[3 * k + j]) * ga);
-            dr[j] = fma(2.0, d2, -ga * ga);
+            nr[j] = fma(2.0, n2, -wl[j] * ga[j]);
+            dr[j] = fma(2.0, d2, -ga[j] * ga[j]);
         }
         num = (nr[0] + nr[1]) + nr[2];
         den = (dr[0] + dr[1]) + dr[2];
     }
     const double gamma0 = (den > -1e-15 && den < 1e-15) ? 0.0 : num / den;
 
-    // spin vector and da_p = omega x a_p (core.py:616-642)
+    // spin vector and da_p = omega x a_p (core.py:616-642):
+    // omega_j = ((L_sr - L_rs) - (G_sr - G_rs) gamma0) / 2 with r = j + 1, s = j + 2 (mod 3),
+    // i.e. minus the antisymmetric pair stored at index r; the caller's time scale rides
+    // along in half_scale (= scale / 2)
     double om[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-        const int r = (j + 1) % 3, s = (j + 2) % 3;
-        om[j] = 0.5 * ((L[3 * s + r] - L[3 * r + s]) - (G[3 * s + r] - G[3 * r + s]) * gamma0);
+        const int r = (j + 1) % 3;
+        om[j] = half_scale * fma(ga[r], gamma0, -wl[r]);
     }
 #pragma unroll
     for (int p = 0; p < 3; ++p) {
@@ -200,10 +214,10 @@ __device__ __forceinline__ void grain_rhs(const double (&a)[9], const double (&D
     }
     out.energy = energy;
     if (PROBE) {
-        probe->rates[0] = all_zero ? 0.0 : g0;
-        probe->rates[1] = all_zero ? 0.0 : g1;
-        probe->rates[2] = all_zero ? 0.0 : g2;
-        probe->rates[3] = all_zero ? 0.0 : g3;
+        probe->rates[0] = all_zero ? 0.0 : 0.5 * g0;  // g carries the Schmid factor 2
+        probe->rates[1] = all_zero ? 0.0 : 0.5 * g1;  // g carries the Schmid factor 2
+        probe->rates[2] = all_zero ? 0.0 : 0.5 * g2;  // g carries the Schmid factor 2
+        probe->rates[3] = all_zero ? 0.0 : 0.5 * g3;  // g carries the Schmid factor 2
 #pragma unroll
         for (int i = 0; i < 9; ++i) probe->G[i] = all_zero ? 0.0 : G[i];
         probe->gamma0 = all_zero ? 0.0 : gamma0;

@@ -292,9 +292,16 @@ __device__ __forceinline__ double clip_int(double x) {
     const int nlo = big ? 0 : __double2loint(x);
     return __hiloint2double(nhi, nlo);
 }
+// All nine components at once; every lane of the warp must call it.  The test is a running
+// integer maximum and one vote, the per-component clamp runs only if some lane needs it.
 __device__ __forceinline__ void clip9(double (&a)[9]) {
+    uint32_t m = 0;
 #pragma unroll
-    for (int c = 0; c < 9; ++c) a[c] = clip_int(a[c]);
+    for (int c = 0; c < 9; ++c) m = max(m, (uint32_t)__double2hiint(a[c]) & 0x7fffffffu);
+    if (__any_sync(0xffffffffu, m >= 0x3ff00000u)) {
+#pragma unroll
+        for (int c = 0; c < 9; ++c) a[c] = clip_int(a[c]);
+    }
 }
 
 // Rotation rate (already multiplied by strain_rate_max, minerals.py:450) and strain
@@ -314,10 +321,10 @@ __device__ __forceinline__ void stage_rhs(const double (&a)[9], const StageFlow 
             L[c] = sf.Ls[c];
         }
         GrainOut out;
-        grain_rhs<false, MODE>(a, D, L, fc, mt, out, nullptr);
         const double sc = (regime == 6) ? 0.3 * sf.s : sf.s;  // core.py:459
+        grain_rhs<false, MODE>(a, D, L, fc, mt, out, nullptr, 0.5 * sc);
 #pragma unroll
-        for (int c = 0; c < 9; ++c) k[c] = sc * out.da[c];
+        for (int c = 0; c < 9; ++c) k[c] = out.da[c];
         energy = out.energy;
     } else if (regime == 1) {  // core.py:392-405: every grain gets the stretch of L.F
 #pragma unroll
