@@ -219,6 +219,18 @@ int drex_elasticity_components_f64(const double *voigt, int64_t P, double *out, 
 int drex_axis_scatter_f64(const double *o_soa, int64_t S, int64_t N, int row, double *out,
                           void *stream);
 
+/* ---- tensors.py helpers (tensors.py:14-21, 167-203, 254-273) ---------------------- */
+
+/* B items at a time, row-major: op 0 tensors.rotate(tensor [81], rotation [9]) -> [81];
+ * op 1 tensors.voigt_to_elastic_tensor(matrix [36]) -> [81]; op 2
+ * tensors.elastic_tensor_to_voigt(tensor [81]) -> [36] (in1 is only read by op 0). */
+int drex_tensor_ops_f64(int op, const double *in0, const double *in1, int64_t B, double *out,
+                        void *stream);
+/* tensors.polar_decompose for B nonsingular 3x3 matrices: left != 0 gives M = V R
+ * (rotation, stretch) = (R, V = sqrt(M M^T)), left == 0 gives M = R U with U = sqrt(M^T M). */
+int drex_polar_decompose_f64(const double *matrices, int64_t B, int left, double *rotation,
+                             double *stretch, void *stream);
+
 /* ---- stats.resample_orientations (stats.py:14-64) ----------------------------------- */
 
 /* Volume-weighted resampling of S textures of N grains: sort by fraction ascending (ties by

@@ -35,6 +35,8 @@ EXPORTS = (
     "drex_axis_scatter_f64",
     "drex_flow_field_f64",
     "drex_pathlines_f64",
+    "drex_tensor_ops_f64",
+    "drex_polar_decompose_f64",
     "drex_resample_workspace_bytes",
     "drex_resample_orientations_f64",
     "drex_mindex_workspace_bytes", "drex_mindex_theory_host", "drex_mindex_f32",
@@ -163,6 +165,8 @@ def _declare(lib):
         [c.POINTER(DrexFlowField), vp, i64, c.POINTER(c.c_double * 3), c.POINTER(c.c_double * 3)]
         + [dbl] * 4 + [i64, i32, i32, i32] + [vp] * 7 + [i32, vp, vp, vp]
     )
+    lib.drex_tensor_ops_f64.argtypes = [i32, vp, vp, i64, vp, vp]
+    lib.drex_polar_decompose_f64.argtypes = [vp, i64, i32, vp, vp, vp]
     lib.drex_resample_workspace_bytes.restype = szt
     lib.drex_resample_workspace_bytes.argtypes = [i64, i64]
     lib.drex_resample_orientations_f64.argtypes = [vp, vp, vp, i64, i64, i64, vp, vp, vp, szt, vp]

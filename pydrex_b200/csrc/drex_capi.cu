@@ -376,6 +376,31 @@ int drex_axis_scatter_f64(const double *o_soa, int64_t S, int64_t N, int row, do
     return DREX_OK;
 }
 
+// ---- tensors.py helpers ---------------------------------------------------------------------
+
+int drex_tensor_ops_f64(int op, const double *in0, const double *in1, int64_t B, double *out,
+                        void *stream) {
+    if (op < 0 || op > 2) return fail(DREX_E_INVALID, "drex_tensor_ops_f64: unknown op %d", op);
+    if (B < 0) return fail(DREX_E_INVALID, "negative size");
+    if (B == 0) return DREX_OK;
+    if (!in0 || !out || (op == 0 && !in1)) return fail(DREX_E_INVALID, "drex_tensor_ops_f64: null pointer");
+    const int64_t n = B * ((op == 2) ? 36 : 81);
+    drex::tensor_ops_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(op, in0, in1, B, out);
+    DREX_CUDA_CHECK(cudaGetLastError());
+    return DREX_OK;
+}
+
+int drex_polar_decompose_f64(const double *matrices, int64_t B, int left, double *rotation,
+                             double *stretch, void *stream) {
+    if (B < 0) return fail(DREX_E_INVALID, "negative size");
+    if (B == 0) return DREX_OK;
+    if (!matrices || !rotation || !stretch) return fail(DREX_E_INVALID, "drex_polar_decompose_f64: null pointer");
+    drex::polar_decompose_kernel<<<(unsigned)((B + 63) / 64), 64, 0, (cudaStream_t)stream>>>(
+        matrices, B, left ? 1 : 0, rotation, stretch);
+    DREX_CUDA_CHECK(cudaGetLastError());
+    return DREX_OK;
+}
+
 // ---- stats.resample_orientations ---------------------------------------------------------
 
 size_t drex_resample_workspace_bytes(int64_t S, int64_t N) {

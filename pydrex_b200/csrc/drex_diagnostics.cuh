@@ -575,4 +575,87 @@ mindex_finalize_kernel(const unsigned long long *__restrict__ counts, const doub
     if (lane == 0) M[s] = ((double)theta_max / (2.0 * (double)theta_max)) * acc;
 }
 
+// ---- tensors.py helpers (reference src/pydrex/tensors.py) ----------------------------------
+
+// Voigt index of the pair (p, q): tensors.py:176-177
+__device__ __forceinline__ int voigt_index(int p, int q) { return (p == q) ? p : 6 - p - q; }
+
+// op 0  rotate(tensor[81], rotation[9]) -> [81]                        tensors.py:254-273
+// op 1  voigt_to_elastic_tensor(matrix[36]) -> [81]                    tensors.py:167-184
+// op 2  elastic_tensor_to_voigt(tensor[81]) -> [36]                    tensors.py:187-203
+// One thread per output element, B items.
+__global__ void tensor_ops_kernel(int op, const double *__restrict__ in0,
+                                  const double *__restrict__ in1, int64_t B,
+                                  double *__restrict__ out) {
+    const int n_out = (op == 2) ? 36 : 81;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= B * n_out) return;
+    const int64_t b = e / n_out;
+    const int o = (int)(e - b * n_out);
+    if (op == 0) {
+        const double *T = in0 + b * 81, *R = in1 + b * 9;
+        const int i = o / 27, j = (o / 9) % 3, k = (o / 3) % 3, l = o % 3;
+        double acc = 0.0;
+        for (int a = 0; a < 3; ++a)
+            for (int bb = 0; bb < 3; ++bb)
+                for (int c = 0; c < 3; ++c)
+                    for (int d = 0; d < 3; ++d)
+                        acc += R[3 * i + a] * R[3 * j + bb] * R[3 * k + c] * R[3 * l + d] *
+                               T[27 * a + 9 * bb + 3 * c + d];
+        out[e] = acc;
+    } else if (op == 1) {
+        const int p = o / 27, q = (o / 9) % 3, r = (o / 3) % 3, t = o % 3;
+        out[e] = in0[b * 36 + 6 * voigt_index(p, q) + voigt_index(r, t)];
+    } else {
+        // mean of the tensor entries that share Voigt indices (i, j), then symmetrised
+        const int i = o / 6, j = o % 6;
+        double sum_ij = 0.0, sum_ji = 0.0;
+        int n_ij = 0, n_ji = 0;
+        for (int p = 0; p < 3; ++p)
+            for (int q = 0; q < 3; ++q)
+                for (int r = 0; r < 3; ++r)
+                    for (int t = 0; t < 3; ++t) {
+                        const int vi = voigt_index(p, q), vj = voigt_index(r, t);
+                        const double v = in0[b * 81 + 27 * p + 9 * q + 3 * r + t];
+                        if (vi == i && vj == j) { sum_ij += v; ++n_ij; }
+                        if (vi == j && vj == i) { sum_ji += v; ++n_ji; }
+                    }
+        out[e] = (sum_ij / n_ij + sum_ji / n_ji) / 2;
+    }
+}
+
+// tensors.polar_decompose (tensors.py:14-21) of B nonsingular 3x3 matrices: M = V R (left,
+// V = sqrt(M M^T)) or M = R U (right, U = sqrt(M^T M)); rot[B][9], stretch[B][9].
+__global__ void polar_decompose_kernel(const double *__restrict__ M, int64_t B, int left,
+                                       double *__restrict__ rot, double *__restrict__ stretch) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double m[9], G[9], w[3], U[9], S[9], Sinv[9], R[9];
+    for (int c = 0; c < 9; ++c) m[c] = M[b * 9 + c];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double acc = 0.0;
+            for (int k = 0; k < 3; ++k)
+                acc += left ? m[3 * i + k] * m[3 * j + k] : m[3 * k + i] * m[3 * k + j];
+            G[3 * i + j] = acc;
+        }
+    jacobi_eig3(G, w, U);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double s = 0.0, si = 0.0;
+            for (int k = 0; k < 3; ++k) {
+                const double root = sqrt(fmax(w[k], 0.0));
+                s += U[3 * i + k] * root * U[3 * j + k];
+                si += U[3 * i + k] * (1.0 / root) * U[3 * j + k];
+            }
+            S[3 * i + j] = s;
+            Sinv[3 * i + j] = si;
+        }
+    if (left) matmul3(Sinv, m, R); else matmul3(m, Sinv, R);
+    for (int c = 0; c < 9; ++c) {
+        rot[b * 9 + c] = R[c];
+        stretch[b * 9 + c] = S[c];
+    }
+}
+
 }  // namespace drex

@@ -991,3 +991,37 @@ def test_ensemble_along_device_pathlines_matches_mineral_path(drex):
             nt.assert_allclose(o_dev[p, k], mins[k].orientations[-1], rtol=0, atol=2e-8)
             nt.assert_allclose(f_dev[p, k], mins[k].fractions[-1], rtol=1e-6, atol=1e-10)
         nt.assert_allclose(F_dev[p], F, rtol=1e-8, atol=1e-10)
+
+
+# ------------------------------------------------------------------ tensors helpers (a16, a19)
+
+
+def test_tensor_helpers_match_golden(drex):
+    """tensors.rotate / voigt_to_elastic_tensor / elastic_tensor_to_voigt / polar_decompose
+    (tensors.py:14-21, 167-203, 254-273) against the reference's values."""
+    import os
+
+    import torch
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "tensors.npz"))
+    t = drex.tensors
+    nt.assert_allclose(t.rotate(g["T"], g["R"]), g["rotated"], rtol=1e-12, atol=1e-13)
+    nt.assert_allclose(t.rotate(g["T"][2], g["R"][2]), g["rotated"][2], rtol=1e-12, atol=1e-13)
+    nt.assert_array_equal(t.voigt_to_elastic_tensor(g["V"]), g["v2t"])
+    nt.assert_allclose(t.elastic_tensor_to_voigt(g["T"]), g["t2v"], rtol=1e-14, atol=1e-15)
+    nt.assert_allclose(t.elastic_tensor_to_voigt(t.voigt_to_elastic_tensor(g["V"][0])),
+                       g["t2v_roundtrip"][0], rtol=1e-15, atol=0)
+    for left in (1, 0):
+        rot, stretch = t.polar_decompose(g["M"], left=bool(left))
+        nt.assert_allclose(rot, g[f"polar_rot_{left}"], rtol=0, atol=1e-13)
+        nt.assert_allclose(stretch, g[f"polar_stretch_{left}"], rtol=0, atol=1e-13)
+    rot, stretch = t.polar_decompose(torch.as_tensor(g["M"][1]).cuda())
+    assert rot.is_cuda
+    nt.assert_allclose((stretch @ rot).cpu().numpy(), g["M"][1], rtol=0, atol=1e-13)
+    # the Voigt average is rotate() under the hood: one grain, unit fraction
+    S = drex.StiffnessTensors().olivine
+    R = g["R"][0]
+    direct = t.elastic_tensor_to_voigt(t.rotate(t.voigt_to_elastic_tensor(S), R.T))
+    m = drex.Mineral(0, 0, 4, n_grains=1, orientations_init=R[None].copy())
+    avg = drex.voigt_averages([m], (0,), (1.0,))[0]
+    nt.assert_allclose(avg, direct, rtol=1e-12, atol=1e-12)
