@@ -217,8 +217,7 @@ __device__ inline void warp_stage_flows(const IntegrateArgs &A, const double *ta
 
 // Per-stage flow quantities shared by the CTA.
 struct StageFlow {
-    double D[9];     // sym(L)/s
-    double Ls[9];    // L/s
+    double2 DL[9];   // {sym(L)/s, L/s} per component: one 16-byte shared load each
     double V[9];     // left stretch of L.F_stage (regime matrix_diffusion only)
     double Lraw[9];  // L
     double s;        // strain_rate_max
@@ -265,8 +264,8 @@ __device__ inline void warp_stage_flows(const IntegrateArgs &A, const double *ta
         StageFlow &sf = st[first + si];
         const int ct = 3 * (c % 3) + c / 3;  // transposed component
         const double l = sf.Lraw[c], lt = sf.Lraw[ct], sc = sf.s;
-        sf.Ls[c] = l / sc;               // minerals.py:439
-        sf.D[c] = (0.5 * (l + lt)) / sc;  // minerals.py:421,438
+        sf.DL[c] = make_double2((0.5 * (l + lt)) / sc,  // minerals.py:421,438
+                                l / sc);                // minerals.py:439
     }
     __syncwarp();
 }
@@ -277,8 +276,8 @@ __device__ inline void fill_stage_flow(StageFlow &sf, const double *L) {
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j) {
             sf.Lraw[3 * i + j] = L[3 * i + j];
-            sf.Ls[3 * i + j] = L[3 * i + j] / s;                           // minerals.py:439
-            sf.D[3 * i + j] = (0.5 * (L[3 * i + j] + L[3 * j + i])) / s;   // minerals.py:421,438
+            sf.DL[3 * i + j] = make_double2((0.5 * (L[3 * i + j] + L[3 * j + i])) / s,  // minerals.py:421,438
+                                            L[3 * i + j] / s);                          // minerals.py:439
         }
 }
 
@@ -317,8 +316,9 @@ __device__ __forceinline__ void stage_rhs(const double (&a)[9], const StageFlow 
         double D[9], L[9];
 #pragma unroll
         for (int c = 0; c < 9; ++c) {
-            D[c] = sf.D[c];
-            L[c] = sf.Ls[c];
+            const double2 dl = sf.DL[c];
+            D[c] = dl.x;
+            L[c] = dl.y;
         }
         GrainOut out;
         const double sc = (regime == 6) ? 0.3 * sf.s : sf.s;  // core.py:459
@@ -583,16 +583,14 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                 mbar_wait(mbar, mbar_parity);
                 mbar_parity ^= 1u;
 #pragma unroll
-                for (int c = 0; c < 9; ++c) {
-                    const double ac = sa[c * 32], kc = sk[c * 32];
-                    sy[c * 32] = ac + (h * BS_B1) * kc;
-                    se[c * 32] = BS_E1 * kc;
-                    st[c] = ac + (h * BS_A21) * kc;
-                }
+                for (int c = 0; c < 9; ++c) st[c] = fma(h * BS_A21, sk[c * 32], sa[c * 32]);
                 // The three stages run as a ROLLED loop: one copy of the ~1300-instruction
                 // right-hand side in the hot loop keeps it inside the instruction cache
                 // (three inlined copies are ~80 KB of SASS and every warp streams them
-                // from L2 on every chunk).
+                // from L2 on every chunk).  The bookkeeping between the stages differs per
+                // stage and sits behind CTA-uniform branches: rows sy / se hold the partial
+                // new state y + h (b1 k1 + b2 k2) and the partial error e1 k1 + e2 k2 after
+                // stage 2, the full ones after stage 3.
 #pragma unroll 1
                 for (int stg = 0; stg < 3; ++stg) {
                     clip9(st);
@@ -601,21 +599,25 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                         double *Ep = (stg == 0) ? E2 : ((stg == 1) ? E3 : E4);
                         Ep[g] = e;
                     }
-                    if (stg == 2) break;
-                    const double cb = (stg == 0) ? (h * BS_B2) : (h * BS_B3);
-                    const double ce = (stg == 0) ? BS_E2 : BS_E3;
-#pragma unroll
-                    for (int c = 0; c < 9; ++c) {
-                        const double yn = sy[c * 32] + cb * k[c];
-                        sy[c * 32] = yn;
-                        se[c * 32] += ce * k[c];
-                        // stage 3 starts from y + 3h/4 k2, stage 4 from the new state itself
-                        st[c] = (stg == 0) ? sa[c * 32] + (h * BS_A32) * k[c] : yn;
-                    }
                     if (stg == 0) {
+#pragma unroll
+                        for (int c = 0; c < 9; ++c) {
+                            const double ac = sa[c * 32], kc = sk[c * 32];
+                            sy[c * 32] = fma(h * BS_B2, k[c], fma(h * BS_B1, kc, ac));
+                            se[c * 32] = fma(BS_E2, k[c], BS_E1 * kc);
+                            st[c] = fma(h * BS_A32, k[c], ac);  // stage 3 starts from y + 3h/4 k2
+                        }
                         // rows 0-17 are free now: fetch the next chunk behind stages 3 and 4
                         __syncwarp();
                         if (qn < n_chunks) issue_chunk(qn);
+                    } else if (stg == 1) {
+#pragma unroll
+                        for (int c = 0; c < 9; ++c) {
+                            const double yn = fma(h * BS_B3, k[c], sy[c * 32]);
+                            sy[c * 32] = yn;
+                            se[c * 32] = fma(BS_E3, k[c], se[c * 32]);
+                            st[c] = yn;  // stage 4 is evaluated at the new state itself
+                        }
                     }
                 }
                 {
