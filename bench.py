@@ -189,6 +189,11 @@ class ClockSampler:
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            # nvidia-smi attaching to the driver stalls running kernels for several ms: wait
+            # until it is past that (first sample printed) before any timed work starts
+            t_wait = time.time()
+            while not self.lines and time.time() - t_wait < 5.0:
+                time.sleep(0.01)
         except OSError:
             self.proc = None
 
@@ -286,11 +291,16 @@ def run_gpu(args):
     # state + scratch exceed L2 (126 MB) by far, so consecutive steps cannot hit in L2
     state_bytes = S * N * 10 * 8
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not args.no_clock_sampler:
         sampler.start()
+    # the warm-up runs exactly what a timed step runs, counter bookkeeping included: CUDA loads
+    # kernels lazily, and the first use of torch's small reduction kernel costs ~8 ms of host
+    # time that would otherwise land inside the first timed step
+    counters = torch.zeros((3,), dtype=torch.int64, device=dev)
     for k in range(W):
         ens.update(t_lo[k], t_hi[k], L_dev[k], kind, tol, check=False)
-    counters = torch.zeros((3,), dtype=torch.int64, device=dev)
+        counters += ens.stats[1:4].sum(dim=1)
+    counters.zero_()
     step_ms = []
     barrier()
     sampler.mark_start()
@@ -575,8 +585,8 @@ def cpu_run(args, n_particles, n_steps, cores):
 
 def cpu_baseline(args):
     cores = len(os.sched_getaffinity(0))
-    n_particles = 8 * cores  # ~10-20 s of wall time on all cores
-    n_steps = 4
+    n_particles = 16 * cores  # ~10-20 s of wall time on all cores
+    n_steps = 12
     v, evals, internal, wall = cpu_run(args, n_particles, n_steps, cores)
     return {"value": v, "unit": "grain-steps/s", "cores": cores, "kind": "port",
             "grain_evals_per_s": evals, "grain_internal_steps_per_s": internal,
@@ -594,7 +604,7 @@ def run_reference(args):
     n_particles = 8 * cores
     # bounded sample: each "step" advances n_particles particles through one outer interval;
     # the warm-up is the pool warm-up inside cpu_run
-    n_steps = min(K, 4)
+    n_steps = min(K, 30)
     v, evals, internal, wall = cpu_run(args, n_particles, n_steps, cores)
     sample = (f"{n_particles} particles x 2 phases x {args.grains} grains x {n_steps} outer steps "
               f"per timed run (bounded sample of the GPU arm's workload), oracle port "
@@ -624,6 +634,7 @@ def main():
     ap.add_argument("--grains", type=int, default=5000)
     ap.add_argument("--workload", default="corner_flow", choices=["simple_shear", "corner_flow"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clock-sampler", action="store_true", help="diagnostic: do not run nvidia-smi")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="pipeline depth of the host-buffer arm")
     args = ap.parse_args()
     if args.impl == "reference":
