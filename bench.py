@@ -635,7 +635,7 @@ def main():
     ap.add_argument("--workload", default="corner_flow", choices=["simple_shear", "corner_flow"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clock-sampler", action="store_true", help="diagnostic: do not run nvidia-smi")
-    ap.add_argument("--e2e-chunks", type=int, default=4, help="pipeline depth of the host-buffer arm")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="pipeline depth of the host-buffer arm")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

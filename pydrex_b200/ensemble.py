@@ -212,7 +212,7 @@ class ParticleEnsemble:
         return self.stats[0]
 
     def update_host(self, h_o, h_f, h_F, t0, t1, L_nodes, kind=_lib.L_CONSTANT, tol=None,
-                    h_stats=None, n_chunks=4):
+                    h_stats=None, n_chunks=8):
         """Advance particles whose state lives in (pinned) HOST memory in the reference's
         layout and write the new state back: the call a geodynamics code makes once per
         model time step (cf. the Fluidity coupling, examples/fluidity/corner2d).
@@ -230,11 +230,15 @@ class ParticleEnsemble:
         S, N, K_ph = self.S, self.N, self.n_phases
         if tol is None:
             tol = self.tolerances()
-        if getattr(self, "_pipe", None) is None:
-            per = -(-self.P // n_chunks) * K_ph
+        per = -(-self.P // n_chunks) * K_ph
+        if getattr(self, "_pipe", None) is None or self._pipe["per"] < per:
+            # separate double-buffered staging for arriving and leaving orientations: with
+            # one shared pair the copy-in of group c+2 had to wait for the copy-out of group c
             self._pipe = {
+                "per": per,
                 "streams": [torch.cuda.Stream(device=dev) for _ in range(3)],
-                "aos": [torch.empty((per, N, 9), dtype=f64, device=dev) for _ in range(2)],
+                "aos_in": [torch.empty((per, N, 9), dtype=f64, device=dev) for _ in range(2)],
+                "aos_out": [torch.empty((per, N, 9), dtype=f64, device=dev) for _ in range(2)],
             }
         s_in, s_run, s_out = self._pipe["streams"]
         main = torch.cuda.current_stream(dev)
@@ -261,17 +265,18 @@ class ParticleEnsemble:
         Pp = _lib.ptr
         m, mh = self.meta, self.meta_host
         per_p = -(-self.P // n_chunks)
-        out_done = [None, None]
+        out_done, packed = [None, None], [None, None]
         for c in range(n_chunks):
             p0, p1 = c * per_p, min(self.P, (c + 1) * per_p)
             if p0 >= p1:
                 break
             s0, s1 = p0 * K_ph, p1 * K_ph
             n = s1 - s0
-            aos = self._pipe["aos"][c % 2][:n]
+            aos = self._pipe["aos_in"][c % 2][:n]
+            aos_out = self._pipe["aos_out"][c % 2][:n]
             with torch.cuda.stream(s_in):
-                if out_done[c % 2] is not None:
-                    s_in.wait_event(out_done[c % 2])  # staging buffer free again
+                if packed[c % 2] is not None:
+                    s_in.wait_event(packed[c % 2])  # arrival buffer consumed by the pack kernel
                 aos.copy_(h_o3[s0:s1], non_blocking=True)
                 self.f[s0:s1].copy_(h_f[s0:s1], non_blocking=True)
                 self.F[s0:s1].copy_(h_F2[s0:s1], non_blocking=True)
@@ -281,6 +286,8 @@ class ParticleEnsemble:
                 s_run.wait_event(ev_in)
                 sp = _lib.stream_ptr(torch)
                 _lib.check(lib.drex_pack_soa_f64(Pp(aos), Pp(self.o[s0:s1]), n, N, sp))
+                packed[c % 2] = torch.cuda.Event()
+                packed[c % 2].record(s_run)
                 _lib.check(lib.drex_integrate_f64(
                     n, self.P, N, Pp(m[0][s0:s1]), Pp(m[1][s0:s1]), Pp(m[2][s0:s1]),
                     Pp(m[3][s0:s1]), Pp(self.vol_frac[s0:s1]), Pp(mh[1][s0:s1]), Pp(mh[2][s0:s1]),
@@ -289,12 +296,14 @@ class ParticleEnsemble:
                     Pp(L_nodes), ctypes.byref(prm), ctypes.byref(tol), Pp(self.h[s0:s1]), None,
                     Pp(self.stats[0][s0:s1]), Pp(self.stats[1][s0:s1]), Pp(self.stats[2][s0:s1]),
                     Pp(self.stats[3][s0:s1]), Pp(self._ws), self._ws.numel(), sp))
-                _lib.check(lib.drex_unpack_soa_f64(Pp(self.o[s0:s1]), Pp(aos), n, N, sp))
+                if out_done[c % 2] is not None:
+                    s_run.wait_event(out_done[c % 2])  # departure buffer copied out
+                _lib.check(lib.drex_unpack_soa_f64(Pp(self.o[s0:s1]), Pp(aos_out), n, N, sp))
                 ev_run = torch.cuda.Event()
                 ev_run.record(s_run)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_run)
-                h_o3[s0:s1].copy_(aos, non_blocking=True)
+                h_o3[s0:s1].copy_(aos_out, non_blocking=True)
                 h_f[s0:s1].copy_(self.f[s0:s1], non_blocking=True)
                 h_F2[s0:s1].copy_(self.F[s0:s1], non_blocking=True)
                 out_done[c % 2] = torch.cuda.Event()
