@@ -156,6 +156,36 @@ def trace_pathlines_on_device(drex, torch, P, K=9, n_path_steps=50):
             "what": "drex_pathlines_f64: backward Dormand-Prince trace + L tables, one launch"}
 
 
+def time_diagnostics(drex, torch, ens):
+    """BASELINE config 5 on this GPU's particles after the timed steps (outside the timed
+    region): Voigt averages over both phases, elasticity decomposition, and the olivine
+    M-index of every particle -- on the full 5000-grain texture and on the reference-style
+    volume-weighted resample of 1000 grains (tests/test_simple_shear_3d.py:194-202)."""
+    system = drex.LatticeSystem.orthorhombic
+    seeds = list(range(ens.P))
+
+    def timed(fn):
+        fn()  # warm-up (lazy kernel loading, workspace allocation)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), out
+
+    ms_voigt, C = timed(ens.voigt_averages)
+    ms_elast, _ = timed(lambda: drex.elasticity_components(C))
+    ms_full, M_full = timed(lambda: ens.misorientation_indices(system, phase_slot=0))
+    ms_res, M_res = timed(lambda: ens.misorientation_indices(system, phase_slot=0, n_samples=1000,
+                                                               seeds=seeds))
+    pairs = ens.P * ens.N * (ens.N - 1) / 2
+    return {"particles": ens.P, "voigt_averages_ms": ms_voigt, "elasticity_components_ms": ms_elast,
+            "mindex_full_texture_ms": ms_full, "mindex_pairs_per_s": pairs / (ms_full * 1e-3),
+            "mindex_resampled_1000_ms": ms_res,
+            "mindex_mean_full": float(M_full.mean()), "mindex_mean_resampled": float(M_res.mean())}
+
+
 def make_workload(name, P, n_steps, seed):
     if name == "simple_shear":
         return simple_shear_tables(P, n_steps, seed)
@@ -347,6 +377,7 @@ def run_gpu(args):
     if rank != 0:
         return
     pathline_info = trace_pathlines_on_device(drex, torch, P) if args.workload == "corner_flow" else None
+    diagnostics_info = time_diagnostics(drex, torch, ens)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -410,6 +441,7 @@ def run_gpu(args):
         },
         "step_ms": step_ms,
         "pathlines": pathline_info,
+        "diagnostics": diagnostics_info,
         "cpu_baseline": cpu,
         "clocks": clocks,
     }
