@@ -112,7 +112,7 @@ __device__ __forceinline__ void grain_rhs(const double (&a)[9], const double (&D
         const bool z_max = xz && yz;
         const double I_max = z_max ? vz : (y_max ? I1 : I0);
         const double c_max = z_max ? cz : (y_max ? fc.crss[1] : fc.crss[0]);
-        const double pre = c_max / I_max;  // core.py:560
+        const double pre = div_fast(c_max, I_max);  // core.py:560
         const double qx = pre * ux, qy = pre * uy, qz = pre * uz;
         const double ax = fabs(qx), ay = fabs(qy), az = fabs(qz);
         double rx, ry, rz_, px, py, pz;  // q|q|^(n-1) and |q|^p
@@ -176,7 +176,7 @@ __device__ __forceinline__ void grain_rhs(const double (&a)[9], const double (&D
         num = (nr[0] + nr[1]) + nr[2];
         den = (dr[0] + dr[1]) + dr[2];
     }
-    const double gamma0 = (den > -1e-15 && den < 1e-15) ? 0.0 : num / den;
+    const double gamma0 = (den > -1e-15 && den < 1e-15) ? 0.0 : div_fast(num, den);
 
     // spin vector and da_p = omega x a_p (core.py:616-642):
     // omega_j = ((L_sr - L_rs) - (G_sr - G_rs) gamma0) / 2 with r = j + 1, s = j + 2 (mod 3),

@@ -489,7 +489,9 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
             sum_clip = sumc;
             if (f_active) {
                 const double mean = sume / sumc;
-                const double pref = sh.st[2].s * gbm_scale;
+                // df = vf M* (f / sum f) (mean - E) s (core.py:431-436): the factor common to all
+                // grains of a stage, s vf M* / sum f, is formed once per thread
+                const double ps = sh.st[2].s * gbm_scale / sumc;
                 if (fast) {
                     double fr[MAXQ], er[MAXQ];
 #pragma unroll
@@ -502,12 +504,12 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
 #pragma unroll
                     for (int j = 0; j < MAXQ; ++j) {
                         const int64_t g = ((int64_t)warp + j * INT_WARPS) * 32 + lane;
-                        if (g < N) kf_cur[g] = pref * (fmax(fr[j], 0.0) / sumc) * (mean - er[j]);
+                        if (g < N) kf_cur[g] = (ps * fmax(fr[j], 0.0)) * (mean - er[j]);
                     }
                 } else {
                     for (int64_t q = warp; q < n_chunks; q += INT_WARPS) {
                         const int64_t g = q * 32 + lane;
-                        if (g < N) kf_cur[g] = pref * (fmax(f_in[g], 0.0) / sumc) * (mean - E4[g]);
+                        if (g < N) kf_cur[g] = (ps * fmax(f_in[g], 0.0)) * (mean - E4[g]);
                     }
                 }
             }
@@ -669,14 +671,14 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                     se_ += xr[j] * ((g < N) ? E2[g] : 0.0);
                 }
                 block_sum2<INT_BLOCK>(sc_, se_, sh.red);
-                double sumc = sc_, mean = se_ / sc_, pref = sh.st[0].s * gbm_scale;
+                double sumc = sc_, mean = se_ / sc_, ps = sh.st[0].s * gbm_scale / sumc;
                 sc_ = 0.0;
                 se_ = 0.0;
 #pragma unroll
                 for (int j = 0; j < MAXQ; ++j) {  // k2, stage 3 state
                     const int64_t g = ((int64_t)warp + j * INT_WARPS) * 32 + lane;
                     const bool ok = g < N;
-                    k2[j] = pref * (xr[j] / sumc) * (mean - (ok ? E2[g] : 0.0));
+                    k2[j] = (ps * xr[j]) * (mean - (ok ? E2[g] : 0.0));
                     xr[j] = fmax(fr[j] + (h * BS_A32) * k2[j], 0.0);
                     sc_ += xr[j];
                     se_ += xr[j] * (ok ? E3[g] : 0.0);
@@ -684,13 +686,13 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                 block_sum2<INT_BLOCK>(sc_, se_, sh.red);
                 sumc = sc_;
                 mean = se_ / sc_;
-                pref = sh.st[1].s * gbm_scale;
+                ps = sh.st[1].s * gbm_scale / sumc;
                 sc_ = 0.0;
                 se_ = 0.0;
 #pragma unroll
                 for (int j = 0; j < MAXQ; ++j) {  // k3, new state
                     const int64_t g = ((int64_t)warp + j * INT_WARPS) * 32 + lane;
-                    const double k3 = pref * (xr[j] / sumc) * (mean - ((g < N) ? E3[g] : 0.0));
+                    const double k3 = (ps * xr[j]) * (mean - ((g < N) ? E3[g] : 0.0));
                     const double fn = fr[j] + h * (BS_B1 * k1[j] + BS_B2 * k2[j] + BS_B3 * k3);
                     k1[j] = BS_E1 * k1[j] + BS_E2 * k2[j] + BS_E3 * k3;  // error combination
                     k2[j] = fn;                                           // new fraction
@@ -702,12 +704,12 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                 sumc = sc_;
                 sum_clip_new = sc_;
                 mean = se_ / sc_;
-                pref = sh.st[2].s * gbm_scale;
+                ps = sh.st[2].s * gbm_scale / sumc;
                 float ef = 0.0f, rf = 0.0f;
 #pragma unroll
                 for (int j = 0; j < MAXQ; ++j) {  // k4 (FSAL), error
                     const int64_t g = ((int64_t)warp + j * INT_WARPS) * 32 + lane;
-                    const double k4 = pref * (xr[j] / sumc) * (mean - e4[j]);
+                    const double k4 = (ps * xr[j]) * (mean - e4[j]);
                     if (g < N) {
                         kf_nxt[g] = k4;
                         f_nxt[g] = k2[j];
@@ -733,13 +735,13 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                     }
                 }
                 block_sum2<INT_BLOCK>(sc_, se_, sh.red);
-                double sumc = sc_, mean = se_ / sc_, pref = sh.st[0].s * gbm_scale;
+                double sumc = sc_, mean = se_ / sc_, ps = sh.st[0].s * gbm_scale / sumc;
                 sc_ = 0.0;
                 se_ = 0.0;
                 for (int64_t q = warp; q < n_chunks; q += INT_WARPS) {  // k2, stage 3 state
                     const int64_t g = q * 32 + lane;
                     if (g < N) {
-                        const double k2 = pref * (fs[g] / sumc) * (mean - E2[g]);
+                        const double k2 = (ps * fs[g]) * (mean - E2[g]);
                         kf2[g] = k2;  // E2[g] is dead from here
                         const double xc = fmax(f_cur[g] + (h * BS_A32) * k2, 0.0);
                         fs[g] = xc;
@@ -750,14 +752,14 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                 block_sum2<INT_BLOCK>(sc_, se_, sh.red);
                 sumc = sc_;
                 mean = se_ / sc_;
-                pref = sh.st[1].s * gbm_scale;
+                ps = sh.st[1].s * gbm_scale / sumc;
                 sc_ = 0.0;
                 se_ = 0.0;
                 for (int64_t q = warp; q < n_chunks; q += INT_WARPS) {  // k3, new state
                     const int64_t g = q * 32 + lane;
                     if (g < N) {
                         const double k1 = kf_cur[g], k2 = kf2[g];
-                        const double k3 = pref * (fs[g] / sumc) * (mean - E3[g]);
+                        const double k3 = (ps * fs[g]) * (mean - E3[g]);
                         const double fn = f_cur[g] + h * (BS_B1 * k1 + BS_B2 * k2 + BS_B3 * k3);
                         f_nxt[g] = fn;
                         fnew_s[g] = fn;  // E3[g] is dead from here
@@ -772,12 +774,12 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                 sumc = sc_;
                 sum_clip_new = sc_;
                 mean = se_ / sc_;
-                pref = sh.st[2].s * gbm_scale;
+                ps = sh.st[2].s * gbm_scale / sumc;
                 float ef = 0.0f, rf = 0.0f;
                 for (int64_t q = warp; q < n_chunks; q += INT_WARPS) {  // k4 (FSAL), error
                     const int64_t g = q * 32 + lane;
                     if (g < N) {
-                        const double k4 = pref * (fs[g] / sumc) * (mean - E4[g]);
+                        const double k4 = (ps * fs[g]) * (mean - E4[g]);
                         kf_nxt[g] = k4;
                         const double err = h * (acce[g] + BS_E4 * k4);
                         const float r = err_ratio(err, fnew_s[g], atol_abs, relw);
