@@ -219,6 +219,26 @@ int drex_elasticity_components_f64(const double *voigt, int64_t P, double *out, 
 int drex_axis_scatter_f64(const double *o_soa, int64_t S, int64_t N, int row, double *out,
                           void *stream);
 
+/* ---- utils.py / geometry.py helpers by name ------------------------------------------ */
+
+/* utils.extract_vars (utils.py:183-190) for S state vectors y[S][9 + 10 N]: F [S][9],
+ * orientations [S][N][9] clipped to [-1, 1], fractions [S][N] clipped at 0 and normalised. */
+int drex_extract_vars_f64(const double *y, int64_t S, int64_t N, double *F, double *o_aos, double *f,
+                          void *stream);
+/* utils.apply_gbs (utils.py:159-180), in place on o_aos [S][N][9] and f [S][N]: grains with
+ * f < gbs_threshold / N take their orientation from o_prev_aos and that size; f is
+ * normalised afterwards. */
+int drex_apply_gbs_f64(double *o_aos, double *f, const double *o_prev_aos, double gbs_threshold,
+                       int64_t S, int64_t N, void *stream);
+/* geometry.misorientation_angles (geometry.py:75-118): q1 [M][A][4], q2 [M][B][4] (float32
+ * when is_float32, else float64; scalar-last or scalar-first alike) -> angles [M] float64,
+ * the smallest 2 acos|q1_i . q2_j| in degrees, evaluated in the input precision. */
+int drex_misorientation_angles(const void *q1, const void *q2, int is_float32, int64_t M, int A,
+                               int B, double *angles, void *stream);
+/* max |eigenvalue| of (L + L^T) / 2 for P matrices L [P][9]: the eigvalsh call of
+ * minerals.py:421-422 and of utils.strain_increment (utils.py:144-156). */
+int drex_strain_rate_max_f64(const double *L, int64_t P, double *out, void *stream);
+
 /* ---- tensors.py helpers (tensors.py:14-21, 167-203, 254-273) ---------------------- */
 
 /* B items at a time, row-major: op 0 tensors.rotate(tensor [81], rotation [9]) -> [81];

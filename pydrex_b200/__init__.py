@@ -5,7 +5,7 @@ Drop-in for `pydrex.core.derivatives`, `pydrex.minerals.Mineral.update_orientati
 batched `ParticleEnsemble` fast path.  See DESIGN.md and INTEGRATION.md.
 """
 
-from . import _lib, geometry, pathlines, stats, tensors, velocity
+from . import _lib, geometry, pathlines, stats, tensors, utils, velocity
 from .core import (
     DefaultParams,
     DeformationRegime,
@@ -40,6 +40,6 @@ __all__ = [
     "get_crss", "bingham_average", "elasticity_components", "symmetry_pgr", "misorientation_index", "misorientation_indices", "ParticleEnsemble",
     "gather_to_rank0", "shard_range", "Error", "IterationError", "LatticeSystem",
     "symmetry_operations", "Mineral", "StiffnessTensors", "update_all", "voigt_averages",
-    "misorientation_hist", "misorientations_random", "resample_orientations", "get_pathline", "get_pathlines", "velocity", "pathlines", "tensors", "OLIVINE_PRIMARY_AXIS",
+    "misorientation_hist", "misorientations_random", "resample_orientations", "get_pathline", "get_pathlines", "velocity", "pathlines", "tensors", "utils", "OLIVINE_PRIMARY_AXIS",
     "OLIVINE_SLIP_SYSTEMS",
 ]

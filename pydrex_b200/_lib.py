@@ -35,6 +35,10 @@ EXPORTS = (
     "drex_axis_scatter_f64",
     "drex_flow_field_f64",
     "drex_pathlines_f64",
+    "drex_extract_vars_f64",
+    "drex_apply_gbs_f64",
+    "drex_misorientation_angles",
+    "drex_strain_rate_max_f64",
     "drex_tensor_ops_f64",
     "drex_polar_decompose_f64",
     "drex_resample_workspace_bytes",
@@ -165,6 +169,10 @@ def _declare(lib):
         [c.POINTER(DrexFlowField), vp, i64, c.POINTER(c.c_double * 3), c.POINTER(c.c_double * 3)]
         + [dbl] * 4 + [i64, i32, i32, i32] + [vp] * 7 + [i32, vp, vp, vp]
     )
+    lib.drex_extract_vars_f64.argtypes = [vp, i64, i64, vp, vp, vp, vp]
+    lib.drex_apply_gbs_f64.argtypes = [vp, vp, vp, dbl, i64, i64, vp]
+    lib.drex_misorientation_angles.argtypes = [vp, vp, i32, i64, i32, i32, vp, vp]
+    lib.drex_strain_rate_max_f64.argtypes = [vp, i64, vp, vp]
     lib.drex_tensor_ops_f64.argtypes = [i32, vp, vp, i64, vp, vp]
     lib.drex_polar_decompose_f64.argtypes = [vp, i64, i32, vp, vp, vp]
     lib.drex_resample_workspace_bytes.restype = szt

@@ -15,6 +15,16 @@ import numpy as np
 from . import _lib
 
 
+#: Levi-Civita symbol (core.py:25-31); the kernels use the equivalent cross products
+PERMUTATION_SYMBOL = np.array(
+    [
+        [[0.0, 0.0, 0.0], [0.0, 0.0, 1.0], [0.0, -1.0, 0.0]],
+        [[0.0, 0.0, -1.0], [0.0, 0.0, 0.0], [1.0, 0.0, 0.0]],
+        [[0.0, 1.0, 0.0], [-1.0, 0.0, 0.0], [0.0, 0.0, 0.0]],
+    ]
+)
+
+
 @unique
 class MineralPhase(IntEnum):
     """Supported mineral phases (core.py:35-47)."""

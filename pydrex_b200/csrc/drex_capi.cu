@@ -376,6 +376,54 @@ int drex_axis_scatter_f64(const double *o_soa, int64_t S, int64_t N, int row, do
     return DREX_OK;
 }
 
+// ---- utils.py / geometry.py helpers by name ----------------------------------------------------
+
+int drex_extract_vars_f64(const double *y, int64_t S, int64_t N, double *F, double *o_aos, double *f,
+                          void *stream) {
+    if (S < 0 || N < 0) return fail(DREX_E_INVALID, "negative size");
+    if (S == 0) return DREX_OK;
+    if (!y || !F || !o_aos || !f) return fail(DREX_E_INVALID, "drex_extract_vars_f64: null pointer");
+    drex::extract_vars_kernel<<<(unsigned)S, 256, 0, (cudaStream_t)stream>>>(y, N, F, o_aos, f);
+    DREX_CUDA_CHECK(cudaGetLastError());
+    return DREX_OK;
+}
+
+int drex_apply_gbs_f64(double *o_aos, double *f, const double *o_prev_aos, double gbs_threshold,
+                       int64_t S, int64_t N, void *stream) {
+    if (S < 0 || N < 0) return fail(DREX_E_INVALID, "negative size");
+    if (S == 0 || N == 0) return DREX_OK;
+    if (!o_aos || !f || !o_prev_aos) return fail(DREX_E_INVALID, "drex_apply_gbs_f64: null pointer");
+    drex::apply_gbs_kernel<<<(unsigned)S, 256, 0, (cudaStream_t)stream>>>(o_aos, f, o_prev_aos,
+                                                                         gbs_threshold, N);
+    DREX_CUDA_CHECK(cudaGetLastError());
+    return DREX_OK;
+}
+
+int drex_misorientation_angles(const void *q1, const void *q2, int is_float32, int64_t M, int A,
+                               int B, double *angles, void *stream) {
+    if (M < 0 || A <= 0 || B <= 0) return fail(DREX_E_INVALID, "drex_misorientation_angles: bad sizes");
+    if (M == 0) return DREX_OK;
+    if (!q1 || !q2 || !angles) return fail(DREX_E_INVALID, "drex_misorientation_angles: null pointer");
+    const unsigned grid = (unsigned)((M + 127) / 128);
+    if (is_float32)
+        drex::misorientation_angles_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>(
+            (const float *)q1, (const float *)q2, M, A, B, angles);
+    else
+        drex::misorientation_angles_kernel<double><<<grid, 128, 0, (cudaStream_t)stream>>>(
+            (const double *)q1, (const double *)q2, M, A, B, angles);
+    DREX_CUDA_CHECK(cudaGetLastError());
+    return DREX_OK;
+}
+
+int drex_strain_rate_max_f64(const double *L, int64_t P, double *out, void *stream) {
+    if (P < 0) return fail(DREX_E_INVALID, "negative size");
+    if (P == 0) return DREX_OK;
+    if (!L || !out) return fail(DREX_E_INVALID, "drex_strain_rate_max_f64: null pointer");
+    drex::strain_rate_max_kernel<<<(unsigned)((P + 127) / 128), 128, 0, (cudaStream_t)stream>>>(L, P, out);
+    DREX_CUDA_CHECK(cudaGetLastError());
+    return DREX_OK;
+}
+
 // ---- tensors.py helpers ---------------------------------------------------------------------
 
 int drex_tensor_ops_f64(int op, const double *in0, const double *in1, int64_t B, double *out,

@@ -658,4 +658,83 @@ __global__ void polar_decompose_kernel(const double *__restrict__ M, int64_t B, 
     }
 }
 
+// ---- utils.py / geometry.py helpers by name ------------------------------------------------
+
+// utils.extract_vars (utils.py:183-190): y = [F(9) | orientations(9N) | fractions(N)] ->
+// F, orientations clipped to [-1, 1], fractions clipped at 0 and normalised.  One CTA per
+// system.
+__global__ void extract_vars_kernel(const double *__restrict__ y, int64_t N, double *__restrict__ F,
+                                    double *__restrict__ o, double *__restrict__ f) {
+    __shared__ double red[64];
+    const int64_t s = blockIdx.x;
+    const double *ys = y + s * (9 + 10 * N);
+    if (threadIdx.x < 9) F[s * 9 + threadIdx.x] = ys[threadIdx.x];
+    for (int64_t i = threadIdx.x; i < 9 * N; i += blockDim.x)
+        o[s * 9 * N + i] = fmin(1.0, fmax(-1.0, ys[9 + i]));
+    double sum = 0.0, dummy = 0.0;
+    for (int64_t i = threadIdx.x; i < N; i += blockDim.x) sum += fmax(ys[9 + 9 * N + i], 0.0);
+    block_sum2<256>(sum, dummy, red);
+    for (int64_t i = threadIdx.x; i < N; i += blockDim.x)
+        f[s * N + i] = fmax(ys[9 + 9 * N + i], 0.0) / sum;
+}
+
+// utils.apply_gbs (utils.py:159-180), in place: grains smaller than threshold / N keep their
+// previous orientation and are set to that size, then the fractions are normalised.
+__global__ void apply_gbs_kernel(double *__restrict__ o, double *__restrict__ f,
+                                 const double *__restrict__ o_prev, double threshold, int64_t N) {
+    __shared__ double red[64];
+    const int64_t s = blockIdx.x;
+    const double floor_f = threshold / (double)N;
+    double sum = 0.0, dummy = 0.0;
+    for (int64_t g = threadIdx.x; g < N; g += blockDim.x) {
+        double v = f[s * N + g];
+        if (v < floor_f) {
+            for (int c = 0; c < 9; ++c) o[(s * N + g) * 9 + c] = o_prev[(s * N + g) * 9 + c];
+            v = floor_f;
+            f[s * N + g] = v;
+        }
+        sum += v;
+    }
+    block_sum2<256>(sum, dummy, red);
+    for (int64_t g = threadIdx.x; g < N; g += blockDim.x) f[s * N + g] /= sum;
+}
+
+// geometry.misorientation_angles (geometry.py:75-118): for each of M rows the smallest
+// 2 acos(|q1_i . q2_j|) in degrees over the A x B pairs of quaternions, evaluated in the
+// precision of the inputs like the reference (float32 on the M-index path), result float64.
+template <typename T>
+__global__ void misorientation_angles_kernel(const T *__restrict__ q1, const T *__restrict__ q2,
+                                             int64_t M, int A, int B, double *__restrict__ out) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    T best = (T)1e30;
+    for (int i = 0; i < A; ++i) {
+        const T *a = q1 + (m * A + i) * 4;
+        for (int j = 0; j < B; ++j) {
+            const T *b = q2 + (m * B + j) * 4;
+            T d = a[0] * b[0];
+            d += a[1] * b[1];
+            d += a[2] * b[2];
+            d += a[3] * b[3];
+            d = d < (T)-1 ? (T)-1 : (d > (T)1 ? (T)1 : d);
+            d = d < (T)0 ? -d : d;
+            T ang;
+            if (sizeof(T) == 4) ang = (T)2 * ((T)acosf((float)d) * (T)57.29577951308232f);
+            else ang = (T)(2.0 * (acos((double)d) * 57.29577951308232));
+            best = ang < best ? ang : best;
+        }
+    }
+    out[m] = (double)best;
+}
+
+// max |eigenvalue| of sym(L) for P matrices (utils.strain_increment, utils.py:144-156;
+// the eigvalsh call of minerals.py:421-422)
+__global__ void strain_rate_max_kernel(const double *__restrict__ L, int64_t P, double *__restrict__ out) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    double l[9];
+    for (int c = 0; c < 9; ++c) l[c] = L[p * 9 + c];
+    out[p] = strain_rate_max(l);
+}
+
 }  // namespace drex

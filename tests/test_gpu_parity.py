@@ -1025,3 +1025,37 @@ def test_tensor_helpers_match_golden(drex):
     m = drex.Mineral(0, 0, 4, n_grains=1, orientations_init=R[None].copy())
     avg = drex.voigt_averages([m], (0,), (1.0,))[0]
     nt.assert_allclose(avg, direct, rtol=1e-12, atol=1e-12)
+
+
+# ------------------------------------------------------------------ utils / geometry by name
+
+
+def test_utils_helpers_match_golden(drex):
+    """utils.extract_vars / apply_gbs / strain_increment / quat_product and
+    geometry.misorientation_angles (utils.py:144-190, 365-371, geometry.py:75-118)."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "utils.npz"))
+    N = g["ev_o"].shape[0]
+    F, o, f = drex.utils.extract_vars(g["ev_y"], N)
+    nt.assert_array_equal(F, g["ev_F"])
+    nt.assert_array_equal(o, g["ev_o"])
+    nt.assert_allclose(f, g["ev_f"], rtol=1e-14, atol=0)  # the sum is associated differently
+    F2, o2, f2 = drex.utils.extract_vars(np.stack([g["ev_y"], g["ev_y"]]), N)
+    nt.assert_array_equal(o2[1], o)
+    for chi in (0.0, 0.3, 0.9):
+        oo, ff = g["gbs_o_new"].copy(), g["gbs_f"].copy()
+        ro, rf = drex.utils.apply_gbs(oo, ff, chi, g["gbs_o_prev"], N)
+        assert ro is oo and rf is ff  # in place like the reference
+        nt.assert_array_equal(oo, g[f"gbs_{int(chi * 10)}_o"])
+        nt.assert_allclose(ff, g[f"gbs_{int(chi * 10)}_f"], rtol=1e-14, atol=0)
+    nt.assert_allclose(drex.utils.strain_increment(g["si_dt"], g["si_L"]), g["si"], rtol=1e-13)
+    nt.assert_allclose(drex.utils.strain_increment(g["si_dt"][2], g["si_L"][2]), g["si"][2], rtol=1e-13)
+    nt.assert_allclose(drex.utils.quat_product(g["qp_1"], g["qp_2"]), g["qp"], rtol=1e-15)
+    nt.assert_allclose(drex.geometry.misorientation_angles(g["ma_f64_a"], g["ma_f64_b"]), g["ma_f64"],
+                       rtol=1e-12, atol=1e-10)
+    nt.assert_allclose(drex.geometry.misorientation_angles(g["ma_f32_a"], g["ma_f32_b"]), g["ma_f32"],
+                       rtol=0, atol=2e-4)  # float32 acos chains
+    with pytest.raises(ValueError, match="first dimensions"):
+        drex.geometry.misorientation_angles(g["ma_f64_a"], g["ma_f64_b"][:10])
+    assert drex.core.PERMUTATION_SYMBOL[0, 1, 2] == 1 and drex.core.PERMUTATION_SYMBOL[2, 1, 0] == -1
