@@ -1,4 +1,4 @@
-import sys, time; sys.path.insert(0, '/root/repo')
+import sys, time; sys.path.insert(0, __import__('os').path.join(__import__('os').path.dirname(__import__('os').path.abspath(__file__)), '..'))
 import numpy as np, torch, bench
 import pydrex_b200 as drex
 dev = torch.device('cuda', 0)
