@@ -1,4 +1,9 @@
-import sys, time; sys.path.insert(0, __import__('os').path.join(__import__('os').path.dirname(__import__('os').path.abspath(__file__)), '..'))
+"""Per-step integrator time and right-hand sides per system at bench size."""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import numpy as np, torch, bench
 import pydrex_b200 as drex
 dev = torch.device('cuda', 0)
