@@ -365,6 +365,24 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
     __shared__ StepShared sh;
     __shared__ __align__(16) double math_tab[MATH_TABLE_DOUBLES];
     load_math_tables(math_tab);
+#ifdef DREX_PHASE_TIMERS
+    // development aid (scripts/phase_timers.py): thread 0's clock at the phase boundaries,
+    // summed per CTA and added to 8 counters behind the work queue
+    __shared__ long long ptimer[8];
+    __shared__ long long pmark;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 8; ++i) ptimer[i] = 0;
+        pmark = clock64();
+    }
+#define DREX_MARK(slot)                                  \
+    if (threadIdx.x == 0) {                              \
+        const long long now_ = clock64();                \
+        ptimer[slot] += now_ - pmark;                    \
+        pmark = now_;                                    \
+    }
+#else
+#define DREX_MARK(slot)
+#endif
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
     const int64_t N = A.N;
@@ -396,6 +414,7 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
         __syncthreads();
         const int64_t s = sh.sys;
         if (s >= A.S) break;
+        DREX_MARK(0)  // queue + end-of-system bookkeeping
 
         const int64_t ip = A.sys_particle[s];
         const int regime = A.sys_regime[s];
@@ -520,8 +539,10 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
         double h_carry = 0.0;
 
         // ---- adaptive steps -------------------------------------------------------------
+        DREX_MARK(1)  // initial slope
         while (!done) {
             __syncthreads();  // the state buffers of the previous step are complete
+            DREX_MARK(5)  // accept / controller of the previous step (or nothing)
             if (n_acc + n_rej >= A.tol.max_steps) {
                 status = 1;  // DREX_STATUS_MAX_STEPS
                 break;
@@ -541,7 +562,11 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                 warp_stage_flows(A, Ltable, sh.st, 0, 3, sh.t + BS_A21 * sh.h, sh.t + BS_A32 * sh.h,
                                  sh.t + sh.h, t_begin, t_end, sh.xnode, lane);
             __syncthreads();
-            if (tid == 0) {
+            // The deformation gradient is advanced by one thread of the LAST warp: chunks are
+            // dealt round-robin, so that warp owns the fewest (9 instead of 10 at N = 5000)
+            // and has the slack; on warp 0 these ~6000 serial cycles made it the warp every
+            // other one waits for at the next barrier.
+            if (tid == INT_BLOCK - 32) {
                 // dF/dt = L(t) F (minerals.py:426), same BS3(2) stages
                 const double h = sh.h;
                 double F2[9], F3[9], k2[9], k3[9];
@@ -566,6 +591,7 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                     left_stretch(sh.kFnew, sh.st[2].V);
                 }
             }
+            DREX_MARK(2)  // stage flows + F stages by thread 0
             // only the diffusion regime reads tid 0's results (V) during phase 1; errF and
             // Fnew are consumed after the block reductions below
             if (regime == 1) __syncthreads();
@@ -643,6 +669,7 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
             else if (fc.default_exponents) phase1(std::integral_constant<int, GRAIN_OLIVINE_DEFAULT>{});
             else phase1(std::integral_constant<int, GRAIN_OLIVINE_GENERIC>{});
             n_rhs += 3;
+            DREX_MARK(3)  // phase 1 (warp 0's own chunks)
             // the new state was written through the generic proxy and is read by TMA (async
             // proxy) in the next step
             asm volatile("fence.proxy.async;" ::: "memory");
@@ -790,6 +817,7 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                 emax = (rf < INFINITY) ? fmax(emax, (double)ef) : INFINITY;
             }
             emax = block_max<INT_BLOCK>(emax, sh.red);
+            DREX_MARK(4)  // waiting for the slowest warp + phase 2 + reductions
             emax = fmax(emax, sh.errF);
 
             // ---- accept / reject (uniform across the CTA: every thread holds emax) -------
@@ -850,6 +878,7 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
         }
         __syncthreads();
 
+        DREX_MARK(5)
         // ---- end of interval: extract_vars -> apply_gbs -> extract_vars ------------------
         // (minerals.py:464-474, 536-538; utils.py:159-190)
         double *o_out = A.o_out + s * 9 * N;
@@ -954,7 +983,15 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
             if (A.n_accept) A.n_accept[s] = n_acc;
             if (A.n_reject) A.n_reject[s] = n_rej;
         }
+        DREX_MARK(6)  // end-of-interval pass
     }
+#ifdef DREX_PHASE_TIMERS
+    if (threadIdx.x == 0) {
+        ptimer[7] += clock64() - pmark;  // waiting for the launch to end is not seen; tail only
+        unsigned long long *out = reinterpret_cast<unsigned long long *>(A.queue) + 8;
+        for (int i = 0; i < 8; ++i) atomicAdd(out + i, (unsigned long long)ptimer[i]);
+    }
+#endif
 }
 
 }  // namespace drex
