@@ -826,7 +826,7 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                 break;
             }
             const bool accept = emax <= 1.0;
-            double fac = (emax > 0.0) ? 0.9 * pow(emax, -1.0 / 3.0) : 5.0;
+            double fac = (emax > 0.0) ? 0.9 * rcbrt(emax) : 5.0;  // err^(-1/3), no general pow
             fac = fmin(accept ? (last_rejected ? 1.0 : 5.0) : 1.0, fmax(0.2, fac));
             double t_now = sh.t, h_next = h * fac;
             __syncthreads();  // all reads of sh.t / sh.h / sh.F done
