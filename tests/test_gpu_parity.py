@@ -1059,3 +1059,31 @@ def test_utils_helpers_match_golden(drex):
     with pytest.raises(ValueError, match="first dimensions"):
         drex.geometry.misorientation_angles(g["ma_f64_a"], g["ma_f64_b"][:10])
     assert drex.core.PERMUTATION_SYMBOL[0, 1, 2] == 1 and drex.core.PERMUTATION_SYMBOL[2, 1, 0] == -1
+
+
+def test_large_chebyshev_table_uses_the_same_interpolant(drex):
+    """L(t) tables with more than 33 nodes are read from global memory instead of the
+    shared-memory copy: a smooth flow tabulated with 9, 33 and 65 nodes integrates to the same
+    state (the interpolation error of 9 nodes is already below 1e-10 here)."""
+    import torch
+
+    P, N = 3, 200
+    rng = np.random.default_rng(5)
+    L0 = rng.normal(size=(P, 3, 3))
+    L0 -= np.eye(3)[None] * np.trace(L0, axis1=1, axis2=2)[:, None, None] / 3
+    L1 = rng.normal(size=(P, 3, 3)) * 0.3
+    L1 -= np.eye(3)[None] * np.trace(L1, axis1=1, axis2=2)[:, None, None] / 3
+    t0, t1 = 0.0, 0.15
+    results = []
+    for K in (9, 33, 65):
+        x = drex.flow.chebyshev_lobatto(K)  # nodes on [0, 1]
+        tables = L0[:, None] + np.sin(1.3 * x)[None, :, None, None] * L1[:, None]
+        ens = drex.ParticleEnsemble(P, N, TWO_PHASE, seed=2)
+        tol = ens.tolerances(rtol=1e-11, atol_abs=1e-13, atol_rel=0.0)
+        ens.update(t0, t1, torch.as_tensor(tables), kind=drex._lib.L_CHEBYSHEV, tol=tol)
+        results.append((ens.orientations().cpu().numpy(), ens.fractions().cpu().numpy(),
+                        ens.deformation_gradients().cpu().numpy()))
+    for o, f, F in results[1:]:
+        nt.assert_allclose(o, results[0][0], rtol=0, atol=1e-9)
+        nt.assert_allclose(f, results[0][1], rtol=1e-7, atol=1e-12)
+        nt.assert_allclose(F, results[0][2], rtol=0, atol=1e-10)
