@@ -343,6 +343,12 @@ int drex_pathlines_f64(const drex_flow_field_t *field, const double *final_locat
  * which MEASURED_PEAKS.json does not carry. */
 int drex_fp64_peak_probe(int device, double *flops_host);
 
+/* Compute-only ceiling of the per-grain physics: olivine right-hand sides per second when
+ * every thread re-evaluates register-resident data at the integrator's occupancy (512
+ * threads per SM): what the integrator's grain stages could reach with nothing else in the
+ * way.  Measurement aid like drex_fp64_peak_probe. */
+int drex_grain_rhs_ceiling_probe(int device, double *evals_per_s_host);
+
 #ifdef __cplusplus
 }
 #endif

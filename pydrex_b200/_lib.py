@@ -46,6 +46,7 @@ EXPORTS = (
     "drex_mindex_workspace_bytes", "drex_mindex_theory_host", "drex_mindex_f32",
     "drex_misorientations_random_host",
     "drex_fp64_peak_probe",
+    "drex_grain_rhs_ceiling_probe",
 )
 
 DREX_OK = 0
@@ -184,6 +185,7 @@ def _declare(lib):
     lib.drex_misorientations_random_host.argtypes = [dbl, dbl, i32, i32, c.POINTER(c.c_double)]
     lib.drex_mindex_f32.argtypes = [vp, i64, i64, i32, i32, vp, vp, vp, szt, vp]
     lib.drex_fp64_peak_probe.argtypes = [i32, c.POINTER(c.c_double)]
+    lib.drex_grain_rhs_ceiling_probe.argtypes = [i32, c.POINTER(c.c_double)]
     return lib
 
 

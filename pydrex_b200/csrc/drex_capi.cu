@@ -827,4 +827,75 @@ int drex_fp64_peak_probe(int device, double *flops_host) {
     return DREX_OK;
 }
 
+// ---- compute-only ceiling of the per-grain physics ---------------------------------------------
+
+// Each thread evaluates the olivine right-hand side `iters` times on data it keeps in
+// registers (the orientation drifts slowly so that nothing can be hoisted): what the
+// physics code reaches at the integrator's occupancy (512 threads per SM, 128 registers)
+// when nothing else is in the way -- no staging, no accumulators, no barriers.
+__global__ void __launch_bounds__(512, 1)
+grain_rhs_ceiling_kernel(drex::FabricConsts fc, const double *__restrict__ flow, double *out, int iters) {
+    __shared__ __align__(16) double math_tab[drex::MATH_TABLE_DOUBLES];
+    drex::load_math_tables(math_tab);
+    __syncthreads();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const double th = 0.37 + 1e-3 * (t % 1000), ph = 1.1 + 1e-3 * (t % 777);
+    double a[9] = {cos(th), sin(th) * cos(ph), sin(th) * sin(ph), -sin(th), cos(th) * cos(ph),
+                   cos(th) * sin(ph), 0.0, -sin(ph), cos(ph)};
+    double D[9], L[9];  // run-time values: nothing folds away
+    for (int c = 0; c < 9; ++c) {
+        D[c] = flow[c];
+        L[c] = flow[9 + c];
+    }
+    double acc = 0.0;
+    for (int i = 0; i < iters; ++i) {
+        drex::GrainOut o;
+        drex::grain_rhs<false, drex::GRAIN_OLIVINE_DEFAULT>(a, D, L, fc, math_tab, o, nullptr, 0.5);
+#pragma unroll
+        for (int c = 0; c < 9; ++c) a[c] = fma(1e-4, o.da[c], a[c]);
+        acc += o.energy;
+    }
+    out[t] = acc + a[0];
+}
+
+int drex_grain_rhs_ceiling_probe(int device, double *evals_per_s_host) {
+    if (!evals_per_s_host) return fail(DREX_E_INVALID, "null pointer");
+    DREX_CUDA_CHECK(cudaSetDevice(device));
+    int sms = 0;
+    DREX_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int blocks = sms, threads = 512, iters = 2000;
+    drex_params_t prm = {1.5, 3.5, 5.0, 125.0, 0.3};
+    const drex::FabricConsts fc = make_fabric_consts(0, prm);
+    double *buf = nullptr;
+    DREX_CUDA_CHECK(cudaMalloc(&buf, ((size_t)blocks * threads + 18) * sizeof(double)));
+    // a general (traceless, normalised) flow: D = sym(L), max |eigenvalue| 1
+    const double flow_h[18] = {0.6, 0.4, -0.2, 0.4, -0.9, 0.3, -0.2, 0.3, 0.3,
+                               0.6, 0.9, -0.5, -0.1, -0.9, 0.7, 0.1, -0.1, 0.3};
+    double *flow = buf + (size_t)blocks * threads;
+    DREX_CUDA_CHECK(cudaMemcpy(flow, flow_h, sizeof(flow_h), cudaMemcpyHostToDevice));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(e0);
+        grain_rhs_ceiling_kernel<<<blocks, threads>>>(fc, flow, buf, iters);
+        cudaEventRecord(e1);
+        cudaError_t e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) {
+            cudaFree(buf);
+            return fail(DREX_E_CUDA, "grain rhs probe failed: %s", cudaGetErrorString(e));
+        }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double rate = (double)iters * blocks * threads / (ms * 1e-3);
+        if (rep > 0 && rate > best) best = rate;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    *evals_per_s_host = best;
+    return DREX_OK;
+}
+
 }  // extern "C"
