@@ -418,7 +418,10 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
 
         const int64_t ip = A.sys_particle[s];
         const int regime = A.sys_regime[s];
-        const FabricConsts &fc = T.fab[A.sys_fabric[s]];
+        // broadcast from lane 0: provably warp-uniform, so the fabric constants are addressed
+        // through uniform registers / the constant bank instead of ~30 vector registers
+        const int fab_u = __shfl_sync(0xffffffffu, A.sys_fabric[s], 0);
+        const FabricConsts &fc = T.fab[fab_u];
         const double t_begin = A.t0[ip], t_end = A.t1[ip];
         const double span = t_end - t_begin;
         const double *o_in = A.o_in + s * 9 * N;
