@@ -10,11 +10,13 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "drex_derivatives.cuh"
 #include "drex_diagnostics.cuh"
 #include "drex_integrate.cuh"
+#include "drex_integrate_pipe.cuh"
 #include "drex_pathlines.cuh"
 #include "drex_resample.cuh"
 
@@ -120,6 +122,13 @@ size_t integrate_smem_bytes(int device, int64_t N, int *smem_arrays) {
     if (n < 0) n = 0;
     *smem_arrays = n;
     return stage_bytes + (size_t)n * array_bytes;
+}
+
+inline size_t integrate_slot_bytes(int64_t N) {
+    return align_up((size_t)drex::SLOT_ARRAYS * (size_t)((N + 31) / 32 * 32) * sizeof(double), 256);
+}
+inline size_t pipe_slot_bytes(int64_t N) {
+    return align_up((size_t)drex::PS_ARRAYS * (size_t)((N + 31) / 32 * 32) * sizeof(double), 256);
 }
 
 }  // namespace
@@ -273,8 +282,8 @@ size_t drex_integrate_workspace_bytes(int64_t S, int64_t N, int device) {
     int slots = integrate_slots(device);
     if (slots < 1) slots = 1;
     if ((int64_t)slots > S) slots = (int)S;
-    const size_t slot_bytes = align_up((size_t)drex::SLOT_ARRAYS * (size_t)((N + 31) / 32 * 32) * sizeof(double), 256);
-    return 256 + (size_t)slots * slot_bytes;
+    // either kernel may run (drex_integrate_f64 chooses): the two-slot pipeline needs the most
+    return 256 + (size_t)slots * 2 * pipe_slot_bytes(N);
 }
 
 int drex_integrate_f64(int64_t S, int64_t P, int64_t N, const int32_t *sys_particle,
@@ -299,7 +308,7 @@ int drex_integrate_f64(int64_t S, int64_t P, int64_t N, const int32_t *sys_parti
     if (!(tol->rtol >= 0.0) || !(tol->atol_abs >= 0.0) || !(tol->atol_rel >= 0.0) ||
         !(tol->rtol + tol->atol_abs + tol->atol_rel > 0.0))
         return fail(DREX_E_INVALID, "tolerances must be non-negative and not all zero");
-    if ((tol->method & 0xff) != 0) return fail(DREX_E_INVALID, "unknown integration method %d", tol->method);
+    if ((tol->method & 0xff) != 0 || (tol->method & ~0x7ff) != 0) return fail(DREX_E_INVALID, "unknown integration method %d", tol->method);
     if (S == 0 || N == 0) return DREX_OK;
     if (!sys_particle || !sys_phase || !sys_fabric || !sys_regime || !sys_vol_frac || !F || !o_in ||
         !f_in || !o_out || !f_out || !t0 || !t1 || !L_nodes || !status)
@@ -308,9 +317,21 @@ int drex_integrate_f64(int64_t S, int64_t P, int64_t N, const int32_t *sys_parti
     DREX_CUDA_CHECK(cudaGetDevice(&device));
     int slots = integrate_slots(device);
     if (slots < 1) return fail(DREX_E_CUDA, "could not query occupancy of the integrator kernel");
+    // Kernel choice: the two-slot pipeline (drex_integrate_pipe.cuh) once there are more
+    // systems than SMs, so that a CTA has a second system to overlap with; one CTA per
+    // system otherwise.  method bits force a choice (tests): 0x100 one-system kernel with the
+    // through-memory fraction stages, 0x200 one-system kernel, 0x400 pipeline.
+    int method = tol->method;
+    if (!(method & 0x700)) {  // testing aid: DREX_INTEGRATOR=pipe|single overrides the automatic choice
+        const char *env = getenv("DREX_INTEGRATOR");
+        if (env && !strcmp(env, "pipe")) method |= 0x400;
+        if (env && !strcmp(env, "single")) method |= 0x200;
+    }
+    const bool pipe = (method & 0x400) || (!(method & 0x300) && S > (int64_t)slots);
     if ((int64_t)slots > S) slots = (int)S;
-    const size_t slot_bytes = align_up((size_t)drex::SLOT_ARRAYS * (size_t)((N + 31) / 32 * 32) * sizeof(double), 256);
-    const size_t need = 256 + (size_t)slots * slot_bytes;
+    if ((method & 0x400) && (int64_t)slots * 2 > S) slots = (int)((S + 1) / 2);  // both slots in use
+    const size_t slot_bytes = pipe ? pipe_slot_bytes(N) : integrate_slot_bytes(N);
+    const size_t need = 256 + (size_t)slots * (pipe ? 2 : 1) * slot_bytes;
     if (!workspace || workspace_bytes < need)
         return fail(DREX_E_WORKSPACE, "drex_integrate_f64: workspace too small (%zu < %zu)",
                     workspace_bytes, need);
@@ -326,19 +347,28 @@ int drex_integrate_f64(int64_t S, int64_t P, int64_t N, const int32_t *sys_parti
     A.tol.rtol = tol->rtol; A.tol.atol_abs = tol->atol_abs; A.tol.atol_rel = tol->atol_rel;
     A.tol.first_step_frac = tol->first_step_frac; A.tol.max_step_frac = tol->max_step_frac;
     A.tol.max_steps = tol->max_steps > 0 ? tol->max_steps : 100000;
-    A.tol.method = tol->method;
+    A.tol.method = method;
     A.h_io = h_io; A.order = order; A.status = status; A.n_rhs = n_rhs; A.n_accept = n_accept; A.n_reject = n_reject;
     A.queue = (int *)workspace;
     A.scratch = (double *)((char *)workspace + 256);
     A.slot_doubles = (int64_t)(slot_bytes / sizeof(double));
-    int smem_arrays = 0;
-    const size_t dyn_smem = integrate_smem_bytes(device, N, &smem_arrays);
-    A.smem_arrays = smem_arrays;
-    DREX_CUDA_CHECK(cudaFuncSetAttribute(drex::integrate_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
     DREX_CUDA_CHECK(cudaMemsetAsync(workspace, 0, 256, st));
     const drex::FabricTable T = make_fabric_table(*params);
-    drex::integrate_kernel<<<(unsigned)slots, drex::INT_BLOCK, dyn_smem, st>>>(A, T);
+    if (pipe) {
+        const size_t dyn_smem =
+            ((size_t)drex::PIPE_CW * drex::STAGE_DOUBLES + drex::RING_DOUBLES) * sizeof(double);
+        A.smem_arrays = 0;
+        DREX_CUDA_CHECK(cudaFuncSetAttribute(drex::integrate_pipe_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+        drex::integrate_pipe_kernel<<<(unsigned)slots, drex::INT_BLOCK, dyn_smem, st>>>(A, T);
+    } else {
+        int smem_arrays = 0;
+        const size_t dyn_smem = integrate_smem_bytes(device, N, &smem_arrays);
+        A.smem_arrays = smem_arrays;
+        DREX_CUDA_CHECK(cudaFuncSetAttribute(drex::integrate_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+        drex::integrate_kernel<<<(unsigned)slots, drex::INT_BLOCK, dyn_smem, st>>>(A, T);
+    }
     DREX_CUDA_CHECK(cudaGetLastError());
     return DREX_OK;
 }
