@@ -162,10 +162,10 @@ typedef struct drex_tolerances {
     double max_step_frac;   /* cap on the step as a fraction of |t1 - t0| (<= 0: none) */
     int32_t max_steps;      /* attempted steps per system before DREX_STATUS_MAX_STEPS */
     int32_t method;         /* low byte 0: Bogacki-Shampine 3(2) with FSAL.  Kernel choice (testing
-                               aid; default: the two-slot pipelined kernel once there are more
-                               systems than SMs, one CTA per system otherwise): 0x200 forces the
-                               one-system kernel, 0x100 the same with the through-memory fraction
-                               stages it uses for N > 5120, 0x400 the pipelined kernel */
+                               aid; default: one CTA per system): 0x200 forces the one-system kernel,
+                               0x100 the same with the through-memory fraction stages it uses for
+                               N > 5120, 0x400 the two-slot pipelined kernel.  The environment
+                               variable DREX_INTEGRATOR=pipe|single overrides the default */
 } drex_tolerances_t;
 
 size_t drex_integrate_workspace_bytes(int64_t S, int64_t N, int device);

@@ -317,17 +317,18 @@ int drex_integrate_f64(int64_t S, int64_t P, int64_t N, const int32_t *sys_parti
     DREX_CUDA_CHECK(cudaGetDevice(&device));
     int slots = integrate_slots(device);
     if (slots < 1) return fail(DREX_E_CUDA, "could not query occupancy of the integrator kernel");
-    // Kernel choice: the two-slot pipeline (drex_integrate_pipe.cuh) once there are more
-    // systems than SMs, so that a CTA has a second system to overlap with; one CTA per
-    // system otherwise.  method bits force a choice (tests): 0x100 one-system kernel with the
-    // through-memory fraction stages, 0x200 one-system kernel, 0x400 pipeline.
+    // Kernel choice: one CTA per system (drex_integrate.cuh) unless the two-slot pipelined
+    // kernel (drex_integrate_pipe.cuh) is asked for.  Measured at bench size the two are within
+    // a few per cent of each other, so the simpler one is the default.
+    // method bits: 0x100 one-system kernel with the through-memory fraction stages, 0x200
+    // one-system kernel, 0x400 pipelined kernel.
     int method = tol->method;
     if (!(method & 0x700)) {  // testing aid: DREX_INTEGRATOR=pipe|single overrides the automatic choice
         const char *env = getenv("DREX_INTEGRATOR");
         if (env && !strcmp(env, "pipe")) method |= 0x400;
         if (env && !strcmp(env, "single")) method |= 0x200;
     }
-    const bool pipe = (method & 0x400) || (!(method & 0x300) && S > (int64_t)slots);
+    const bool pipe = (method & 0x400) != 0;
     if ((int64_t)slots > S) slots = (int)S;
     if ((method & 0x400) && (int64_t)slots * 2 > S) slots = (int)((S + 1) / 2);  // both slots in use
     const size_t slot_bytes = pipe ? pipe_slot_bytes(N) : integrate_slot_bytes(N);
@@ -355,12 +356,11 @@ int drex_integrate_f64(int64_t S, int64_t P, int64_t N, const int32_t *sys_parti
     DREX_CUDA_CHECK(cudaMemsetAsync(workspace, 0, 256, st));
     const drex::FabricTable T = make_fabric_table(*params);
     if (pipe) {
-        const size_t dyn_smem =
-            ((size_t)drex::PIPE_CW * drex::STAGE_DOUBLES + drex::RING_DOUBLES) * sizeof(double);
+        const size_t dyn_smem = (size_t)drex::PIPE_CW * drex::STAGE_DOUBLES * sizeof(double);
         A.smem_arrays = 0;
         DREX_CUDA_CHECK(cudaFuncSetAttribute(drex::integrate_pipe_kernel,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
-        drex::integrate_pipe_kernel<<<(unsigned)slots, drex::INT_BLOCK, dyn_smem, st>>>(A, T);
+        drex::integrate_pipe_kernel<<<(unsigned)slots, drex::PIPE_BLOCK, dyn_smem, st>>>(A, T);
     } else {
         int smem_arrays = 0;
         const size_t dyn_smem = integrate_smem_bytes(device, N, &smem_arrays);

@@ -7,29 +7,32 @@
 // In integrate_kernel one CTA owns one system, and about 40 % of its time goes to sections
 // that cannot fill the FP64 pipe: the coupled fraction stages with their block reductions,
 // the accept/reject decision, the stage flows L(t_i), barrier skew.  Here a CTA owns TWO
-// systems ("slots"):
-//   * 15 compute warps only ever run the data-parallel grain passes (initial slope, the
-//     three-stage phase 1, end-of-interval copy), alternating between the slots, and never
-//     meet at a CTA barrier: they wait on a per-slot "command" mbarrier and arrive on a
-//     per-slot "done" mbarrier;
-//   * one control warp does everything serial or coupled for BOTH slots while the compute
-//     warps are busy with the other slot: work queue, L(t) stage flows, the deformation
-//     gradient, the coupled fraction stages (core.py:431-436; four sweeps whose inputs
-//     stream through a shared-memory ring filled by TMA bulk copies, so the one warp has
-//     kilobytes in flight without holding them in registers), the error norm, the step
-//     controller and the fraction part of apply_gbs (utils.py:159-190).
-// Everything is in a fixed order, so results do not depend on which CTA or slot ran a system.
-// No size limit: the fraction stages always go through memory (L2-resident scratch).
+// systems ("slots") and no CTA-wide barrier after start-up:
+//   * 15 compute warps run the data-parallel passes.  LONG commands are the grain passes
+//     (initial slope, the three-stage phase 1, end-of-interval orientation copy); FRAGMENTS
+//     are the short per-grain sweeps of the coupled fraction stages (core.py:431-436) and of
+//     the fraction part of apply_gbs (utils.py:159-190), each ending in per-warp partial
+//     sums.  A warp waits on a per-slot "command" mbarrier and arrives on a per-slot "done"
+//     mbarrier; between the 32-grain chunks of a long command on one slot it polls the
+//     OTHER slot and runs its pending fragment, so the reductions of one system hide behind
+//     the phase 1 of the other;
+//   * one control warp owns everything serial for both slots: work queue, L(t) stage flows,
+//     the deformation gradient, combining the 15 partial sums in a fixed order, the error
+//     norm, the step controller, posting the next command.
+// A grain is always handled by the same thread (chunk q belongs to warp q mod 15, lane =
+// grain mod 32) in every pass, so per-grain scratch needs no synchronisation beyond program
+// order.  Sums are formed in a fixed order: results do not depend on which CTA or slot ran a
+// system, nor on how the two slots interleaved.  No size limit on N.
 #pragma once
 #include "drex_integrate.cuh"
 
 namespace drex {
 
-constexpr int PIPE_CW = INT_WARPS - 1;  // compute warps; warp PIPE_CW is the control warp
-constexpr int RING_TILE = 256;          // grains per ring tile (8 per lane)
-constexpr int RING_NT = 4;              // tiles in flight
-constexpr int RING_MAXIN = 5;           // input arrays per sweep
-constexpr int RING_DOUBLES = RING_NT * RING_MAXIN * RING_TILE;
+#ifndef DREX_PIPE_CW
+#define DREX_PIPE_CW 15
+#endif
+constexpr int PIPE_CW = DREX_PIPE_CW;  // compute warps; warp PIPE_CW is the control warp
+constexpr int PIPE_BLOCK = (PIPE_CW + 1) * 32;
 
 // per-slot global scratch, in units of Npad doubles (YK buffers: chunked SoA as in
 // drex_integrate.cuh)
@@ -37,17 +40,35 @@ constexpr int PS_YKA = 0, PS_YKB = 18, PS_FA = 36, PS_FB = 37, PS_KFA = 38, PS_K
 constexpr int PS_E2 = 40, PS_E3 = 41, PS_E4 = 42, PS_T1 = 43, PS_T2 = 44;
 constexpr int PS_ARRAYS = 45;
 
-#define PIPE_FENCE()                                   \
-    asm volatile("fence.proxy.async;" ::: "memory")
-enum { CMD_INIT = 1, CMD_STEP = 2, CMD_FINISH = 3, CMD_EXIT = 4 };
+enum { CMD_INIT = 1, CMD_STEP = 2, CMD_FINISH = 3, CMD_EXIT = 4, CMD_FRAG = 5 };
+// fragments, in the order a system meets them; slot state = ST_FRAG + fragment while one is out
+enum { FRAG_K0 = 0, FRAG_K1, FRAG_S1, FRAG_S2, FRAG_S3, FRAG_S4, FRAG_G1, FRAG_G2, FRAG_G3 };
+constexpr int ST_FRAG = 16;
+#ifndef DREX_FRAG_U
+#define DREX_FRAG_U 4
+#endif
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
+// non-blocking, warp-uniform: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity, int lane) {
+    uint32_t done = 0;
+    if (lane == 0)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_addr(bar)), "r"(parity)
+            : "memory");
+    done = __shfl_sync(0xffffffffu, done, 0);
+    __syncwarp();
+    return done != 0;
+}
 
 // normalised fraction before the sliding test (utils.py:188-189, 171): one expression shared
-// by the control warp (fractions) and the compute warps (orientations) so both agree on
-// which grains slide
+// by the fraction fragments and the orientation pass so both agree on which grains slide
 __device__ __forceinline__ double gbs_fraction(double f, double s1) { return fmax(f, 0.0) / s1; }
 
 struct PipeSlot {
@@ -57,15 +78,16 @@ struct PipeSlot {
     double Ltab[33 * 9];
     // command block: written by the control warp before it arrives on cmd_bar, read by the
     // compute warps after they pass it
-    double h, s1;
+    double h, s1, pa, pb;
     const double *yk_cur;
     double *yk_nxt;
-    const double *f_cur;
-    int cmd, sys, regime, fab, f_active;
-    float err[INT_WARPS];  // per compute warp: weighted error max of its grains (inf: not finite)
+    double *f_cur, *f_nxt, *kf_cur, *kf_nxt, *f_out;
+    int cmd, frag, sys, regime, fab, f_active;
+    // results of the compute warps
+    double part[PIPE_CW + 1][2];  // per-warp partial sums of a fragment
+    float err[PIPE_CW + 1];       // per-warp weighted error max (inf: not finite)
     // control warp's own bookkeeping
-    double t, t_begin, t_end, span, h_carry, sum_clip, gbm_scale, errF;
-    double *f_nxt, *kf_cur, *kf_nxt;
+    double t, t_begin, t_end, span, h_carry, sum_clip, sum_clip_new, gbm_scale, errF, emax_o;
     int64_t ip;
     int state, n_rhs, n_acc, n_rej, status, last_rejected, const_flow, done;
 };
@@ -73,60 +95,179 @@ struct PipeSlot {
 struct PipeShared {
     PipeSlot slot[2];
     uint64_t cmd_bar[2], done_bar[2];
-    uint64_t tma_bar[INT_WARPS];
-    uint64_t ring_bar[RING_NT];
+    uint64_t tma_bar[PIPE_CW + 1];
 };
 
-// One sweep of the control warp over NIN per-grain arrays of Npad doubles: tiles of
-// RING_TILE grains are fetched by TMA bulk copies RING_NT tiles ahead; body(t, v) gets the
-// tile in registers, v[i][j] = array i at grain t * RING_TILE + j * 32 + lane (the stage is
-// released for the next copy before the arithmetic starts, and the loads cannot alias the
-// body's global stores).  `seq` counts tiles over the whole launch (ring stage =
-// seq % RING_NT, mbarrier parity from seq / RING_NT).  Inputs written through the generic
-// proxy must have been fenced (fence.proxy.async) by their writers.
-constexpr int RING_J = RING_TILE / 32;
-template <int NIN, class Body>
-__device__ __forceinline__ void ring_sweep(const double *const (&in)[NIN], int64_t Npad, double *ring,
-                                           uint64_t *bars, uint32_t &seq, int lane, Body body) {
-    static_assert(NIN <= RING_MAXIN, "ring stage too small");
-    const int ntiles = (int)((Npad + RING_TILE - 1) / RING_TILE);
-    auto issue = [&](int t, uint32_t n) {
-        if (lane == 0) {
-            const int stg = (int)(n % RING_NT);
-            const int64_t g0 = (int64_t)t * RING_TILE;
-            const int64_t cnt = (Npad - g0 < RING_TILE) ? (Npad - g0) : RING_TILE;
-            const uint32_t bytes = (uint32_t)(cnt * sizeof(double));
-            mbar_expect_tx(&bars[stg], bytes * NIN);
+// One fragment over this thread's grains (chunks warp, warp + 15, ...; four chunks per trip so
+// that the loads of a trip are in flight together).  Per-warp partial sums go to C.part /
+// C.err.  Not inlined: it is called between the chunks of the long commands, whose hot loops
+// must stay small.
+__device__ __noinline__ void pipe_fragment(PipeSlot &C, double *slot, int64_t N, int warp, int lane,
+                                           double atol_abs, double relw) {
+    const int64_t n_chunks = (N + 31) / 32, Npad = n_chunks * 32;
+    const int frag = C.frag;
+    const double pa = C.pa, pb = C.pb, h = C.h;
+    const bool f_active = C.f_active != 0;
+    double *f = C.f_cur, *k1 = C.kf_cur, *fnx = C.f_nxt, *kfn = C.kf_nxt, *f_out = C.f_out;
+    double *E2 = slot + PS_E2 * Npad, *E3 = slot + PS_E3 * Npad, *E4 = slot + PS_E4 * Npad;
+    double *T1 = slot + PS_T1 * Npad, *T2 = slot + PS_T2 * Npad;
+    double sc = 0.0, se = 0.0;
+    float ef = 0.0f, rf = 0.0f;
+    constexpr int U = DREX_FRAG_U;
+    for (int64_t q0 = warp; q0 < n_chunks; q0 += U * PIPE_CW) {
+        int64_t g[U];
+        bool ok[U];
 #pragma unroll
-            for (int i = 0; i < NIN; ++i)
-                bulk_g2s(ring + (stg * RING_MAXIN + i) * RING_TILE, in[i] + g0, bytes, &bars[stg]);
+        for (int u = 0; u < U; ++u) {
+            const int64_t q = q0 + u * PIPE_CW;
+            g[u] = q * 32 + lane;
+            ok[u] = q < n_chunks && g[u] < N;
         }
-    };
-    const uint32_t base = seq;
-    for (int t = 0; t < ntiles && t < RING_NT; ++t) issue(t, base + t);
-    for (int t = 0; t < ntiles; ++t) {
-        const uint32_t n = base + (uint32_t)t;
-        const int stg = (int)(n % RING_NT);
-        mbar_wait(&bars[stg], (n / RING_NT) & 1u);
-        const double *tile = ring + stg * RING_MAXIN * RING_TILE + lane;
-        double v[NIN][RING_J];
+        double a[U], b[U], c[U], d[U], e[U];
+        switch (frag) {
+        case FRAG_K0:  // sum of max(f, 0) (utils.py:188-189) and of max(f, 0) E at t0
 #pragma unroll
-        for (int i = 0; i < NIN; ++i)
+            for (int u = 0; u < U; ++u) {
+                a[u] = ok[u] ? f[g[u]] : 0.0;
+                b[u] = (ok[u] && f_active) ? E4[g[u]] : 0.0;
+            }
 #pragma unroll
-            for (int j = 0; j < RING_J; ++j) v[i][j] = tile[i * RING_TILE + j * 32];
-        // The stage goes back to the async proxy before the arithmetic starts.  The bulk copy
-        // that refills it writes through the async proxy and is not ordered after these
-        // generic-proxy loads by __syncwarp alone (it was observed to overtake them under the
-        // compute warps' shared-memory traffic): the proxy fence orders them.
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (t + RING_NT < ntiles) issue(t + RING_NT, n + RING_NT);
-        body(t, v);
+            for (int u = 0; u < U; ++u) {
+                const double x = fmax(a[u], 0.0);
+                sc += x;
+                se += x * b[u];
+            }
+            break;
+        case FRAG_K1:  // df = vf M* (f / sum f) (mean - E) s (core.py:431-436) at t0
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                a[u] = ok[u] ? f[g[u]] : 0.0;
+                b[u] = ok[u] ? E4[g[u]] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (ok[u]) k1[g[u]] = (pa * fmax(a[u], 0.0)) * (pb - b[u]);
+            break;
+        case FRAG_S1:  // stage 2 state
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                a[u] = ok[u] ? f[g[u]] : 0.0;
+                b[u] = ok[u] ? k1[g[u]] : 0.0;
+                c[u] = ok[u] ? E2[g[u]] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const double x = fmax(a[u] + (h * BS_A21) * b[u], 0.0);
+                sc += x;
+                se += x * c[u];
+            }
+            break;
+        case FRAG_S2:  // k2, stage 3 state
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                a[u] = ok[u] ? f[g[u]] : 0.0;
+                b[u] = ok[u] ? k1[g[u]] : 0.0;
+                c[u] = ok[u] ? E2[g[u]] : 0.0;
+                d[u] = ok[u] ? E3[g[u]] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const double x2 = fmax(a[u] + (h * BS_A21) * b[u], 0.0);
+                const double k2 = (pa * x2) * (pb - c[u]);
+                if (ok[u]) T1[g[u]] = k2;
+                const double x3 = fmax(a[u] + (h * BS_A32) * k2, 0.0);
+                sc += x3;
+                se += x3 * d[u];
+            }
+            break;
+        case FRAG_S3:  // k3, new state, error combination
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                a[u] = ok[u] ? f[g[u]] : 0.0;
+                b[u] = ok[u] ? k1[g[u]] : 0.0;
+                c[u] = ok[u] ? T1[g[u]] : 0.0;
+                d[u] = ok[u] ? E3[g[u]] : 0.0;
+                e[u] = ok[u] ? E4[g[u]] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const double x3 = fmax(a[u] + (h * BS_A32) * c[u], 0.0);
+                const double k3 = (pa * x3) * (pb - d[u]);
+                const double fn = a[u] + h * (BS_B1 * b[u] + BS_B2 * c[u] + BS_B3 * k3);
+                if (ok[u]) {
+                    fnx[g[u]] = fn;
+                    T2[g[u]] = BS_E1 * b[u] + BS_E2 * c[u] + BS_E3 * k3;
+                }
+                const double xn = fmax(fn, 0.0);
+                sc += xn;
+                se += xn * e[u];
+            }
+            break;
+        case FRAG_S4:  // k4 (FSAL) and the error of the fractions
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                a[u] = ok[u] ? fnx[g[u]] : 0.0;
+                b[u] = ok[u] ? T2[g[u]] : 0.0;
+                c[u] = ok[u] ? E4[g[u]] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const double k4 = (pa * fmax(a[u], 0.0)) * (pb - c[u]);
+                if (ok[u]) {
+                    kfn[g[u]] = k4;
+                    const double err = h * (b[u] + BS_E4 * k4);
+                    const float r = err_ratio(err, a[u], atol_abs, relw);
+                    ef = fmaxf(ef, r);
+                    rf += r;
+                }
+            }
+            break;
+        case FRAG_G1:  // extract_vars, then the sliding floor (utils.py:171-176); pa = sum max(f, 0), pb = floor
+#pragma unroll
+            for (int u = 0; u < U; ++u) a[u] = ok[u] ? f[g[u]] : 0.0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                double x = gbs_fraction(a[u], pa);
+                x = (x < pb) ? pb : x;
+                x = ok[u] ? x : 0.0;
+                if (ok[u]) T1[g[u]] = x;
+                sc += x;
+            }
+            break;
+        case FRAG_G2:  // renormalise (utils.py:177-179), clip again (utils.py:188)
+#pragma unroll
+            for (int u = 0; u < U; ++u) a[u] = ok[u] ? T1[g[u]] : 0.0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const double x = fmax(a[u] / pa, 0.0);
+                if (ok[u]) T2[g[u]] = x;
+                sc += x;
+            }
+            break;
+        default:  // FRAG_G3: final normalisation (utils.py:189)
+#pragma unroll
+            for (int u = 0; u < U; ++u) a[u] = ok[u] ? T2[g[u]] : 0.0;
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (ok[u]) f_out[g[u]] = a[u] / pa;
+            break;
+        }
     }
-    seq = base + (uint32_t)ntiles;
+    sc = warp_sum(sc);
+    se = warp_sum(se);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ef = fmaxf(ef, __shfl_xor_sync(0xffffffffu, ef, o));
+        rf += __shfl_xor_sync(0xffffffffu, rf, o);
+    }
+    if (lane == 0) {
+        C.part[warp][0] = sc;
+        C.part[warp][1] = se;
+        C.err[warp] = (rf < INFINITY) ? ef : INFINITY;
+    }
 }
 
-__global__ void __launch_bounds__(INT_BLOCK, 1)
+__global__ void __launch_bounds__(PIPE_BLOCK, 1)
 integrate_pipe_kernel(const __grid_constant__ IntegrateArgs A, const __grid_constant__ FabricTable T) {
     extern __shared__ __align__(128) double dyn_smem[];
     __shared__ PipeShared sh;
@@ -142,31 +283,22 @@ integrate_pipe_kernel(const __grid_constant__ IntegrateArgs A, const __grid_cons
             mbar_init(&sh.cmd_bar[x], 1);
             mbar_init(&sh.done_bar[x], PIPE_CW);
         }
-        for (int w = 0; w < INT_WARPS; ++w) mbar_init(&sh.tma_bar[w], 1);
-        for (int i = 0; i < RING_NT; ++i) mbar_init(&sh.ring_bar[i], 1);
+        for (int w = 0; w < PIPE_CW; ++w) mbar_init(&sh.tma_bar[w], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();  // the only CTA-wide barrier of the kernel
     const double relw = A.tol.atol_rel + A.tol.rtol, atol_abs = A.tol.atol_abs;
 #ifdef DREX_PHASE_TIMERS
-    long long idle_clk = 0;
+    long long idle_clk = 0, frag_clk = 0;
     const long long start_clk = clock64();
-#define PIPE_IDLE(stmt)                        \
+#define PIPE_CLK(acc, stmt)                    \
     {                                          \
         const long long c0_ = clock64();       \
         stmt;                                  \
-        idle_clk += clock64() - c0_;           \
-    }
-    long long h_clk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#define PIPE_TIME(slot, stmt)                  \
-    {                                          \
-        const long long c0_ = clock64();       \
-        stmt;                                  \
-        h_clk[slot] += clock64() - c0_;        \
+        acc += clock64() - c0_;                \
     }
 #else
-#define PIPE_IDLE(stmt) stmt;
-#define PIPE_TIME(slot, stmt) stmt;
+#define PIPE_CLK(acc, stmt) stmt;
 #endif
 
     if (warp < PIPE_CW) {
@@ -175,12 +307,40 @@ integrate_pipe_kernel(const __grid_constant__ IntegrateArgs A, const __grid_cons
         uint64_t *mbar = &sh.tma_bar[warp];
         uint32_t mbar_parity = 0, cpar = 0;
         int dead = 0;
-        for (int X = 0; dead != 3; X ^= 1) {
-            if ((dead >> X) & 1) continue;
-            PIPE_IDLE(mbar_wait(&sh.cmd_bar[X], (cpar >> X) & 1u))
-            cpar ^= 1u << X;
+        auto slot_of = [&](int X) { return A.scratch + ((int64_t)blockIdx.x * 2 + X) * A.slot_doubles; };
+        auto finish_command = [&](int X) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh.done_bar[X]);
+        };
+        // run slot Y's pending command if it is a fragment (called between the chunks of a
+        // long command on the other slot, and from the main loop)
+        auto nested_fragment = [&](int Y) {
+            if ((dead >> Y) & 1) return;
+            if (!mbar_test(&sh.cmd_bar[Y], (cpar >> Y) & 1u, lane)) return;
+            PipeSlot &CY = sh.slot[Y];
+            if (CY.cmd != CMD_FRAG) return;  // a long command: the main loop takes it
+            cpar ^= 1u << Y;
+            PIPE_CLK(frag_clk, pipe_fragment(CY, slot_of(Y), N, warp, lane, atol_abs, relw))
+            finish_command(Y);
+        };
+        int next = 0;
+        while (dead != 3) {
+            int X = next;
+            if (((dead >> X) & 1) || !mbar_test(&sh.cmd_bar[X], (cpar >> X) & 1u, lane)) {
+                X ^= 1;
+                if (((dead >> X) & 1) || !mbar_test(&sh.cmd_bar[X], (cpar >> X) & 1u, lane)) {
+                    PIPE_CLK(idle_clk, __nanosleep(100))
+                    continue;
+                }
+            }
             PipeSlot &C = sh.slot[X];
             const int cmd = C.cmd;
+            if (cmd == CMD_FRAG) {
+                nested_fragment(X);
+                continue;
+            }
+            cpar ^= 1u << X;
+            next = X ^ 1;
             if (cmd == CMD_EXIT) {
                 dead |= 1 << X;
                 continue;
@@ -190,7 +350,7 @@ integrate_pipe_kernel(const __grid_constant__ IntegrateArgs A, const __grid_cons
             const int fab_u = __shfl_sync(0xffffffffu, C.fab, 0);
             const FabricConsts &fc = T.fab[fab_u];
             const bool f_active = C.f_active != 0;
-            double *slot = A.scratch + ((int64_t)blockIdx.x * 2 + X) * A.slot_doubles;
+            double *slot = slot_of(X);
             double *E2 = slot + PS_E2 * Npad, *E3 = slot + PS_E3 * Npad, *E4 = slot + PS_E4 * Npad;
             const double *o_in = A.o_in + s * 9 * N;
 
@@ -230,6 +390,7 @@ integrate_pipe_kernel(const __grid_constant__ IntegrateArgs A, const __grid_cons
 #pragma unroll
                     for (int c = 0; c < 9; ++c) blk[(9 + c) * 32] = k[c];
                     if (f_active && g < N) E4[g] = e;
+                    nested_fragment(X ^ 1);
                 }
             } else if (cmd == CMD_STEP) {
                 // ---- phase 1: every grain through all three stages ------------------------
@@ -298,6 +459,7 @@ integrate_pipe_kernel(const __grid_constant__ IntegrateArgs A, const __grid_cons
                             blk[c * 32] = yn;
                             blk[(9 + c) * 32] = k[c];
                         }
+                        nested_fragment(X ^ 1);
                     }
                 };
                 if (regime != 4 && regime != 6) phase1(std::integral_constant<int, STAGE_OTHER>{});
@@ -344,32 +506,60 @@ integrate_pipe_kernel(const __grid_constant__ IntegrateArgs A, const __grid_cons
 #pragma unroll
                         for (int c = 0; c < 9; ++c) o_out[c * N + g] = a[c];
                     }
+                    nested_fragment(X ^ 1);
                 }
             }
-            // this warp's global writes are read by TMA (async proxy) later
-            PIPE_FENCE();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sh.done_bar[X]);
+            // this warp's chunk writes are read back by its own TMA copies (async proxy) later
+            asm volatile("fence.proxy.async;" ::: "memory");
+            finish_command(X);
         }
 #ifdef DREX_PHASE_TIMERS
         if (tid == 0) {
             unsigned long long *out = reinterpret_cast<unsigned long long *>(A.queue) + 8;
             atomicAdd(out + 0, (unsigned long long)idle_clk);
             atomicAdd(out + 1, (unsigned long long)(clock64() - start_clk));
+            atomicAdd(out + 4, (unsigned long long)frag_clk);
         }
 #endif
         return;
     }
 
     // ================================== control warp =====================================
-    double *ring = dyn_smem + PIPE_CW * STAGE_DOUBLES;
-    uint32_t ring_seq = 0, dpar = 0;
+    uint32_t dpar = 0;
     const double floor_v = A.gbs_threshold / (double)N;
 
     auto slot_base = [&](int X) { return A.scratch + ((int64_t)blockIdx.x * 2 + X) * A.slot_doubles; };
     auto post = [&](int X) {  // publish the command block of slot X
         __syncwarp();
         if (lane == 0) mbar_arrive(&sh.cmd_bar[X]);
+    };
+    auto post_fragment = [&](int X, int frag, double pa, double pb) {
+        PipeSlot &C = sh.slot[X];
+        __syncwarp();  // every lane has read what it needs from the slot
+        if (lane == 0) {
+            C.cmd = CMD_FRAG;
+            C.frag = frag;
+            C.pa = pa;
+            C.pb = pb;
+            C.state = ST_FRAG + frag;
+        }
+        post(X);
+    };
+    // the 15 per-warp partial sums of the fragment that just finished, added in warp order
+    auto combine = [&](int X, double &sc, double &se) {
+        const PipeSlot &C = sh.slot[X];
+        sc = 0.0;
+        se = 0.0;
+        for (int w = 0; w < PIPE_CW; ++w) {
+            sc += C.part[w][0];
+            se += C.part[w][1];
+        }
+    };
+    auto combine_err = [&](int X) {
+        const PipeSlot &C = sh.slot[X];
+        float em = 0.0f;
+        for (int w = 0; w < PIPE_CW; ++w) em = fmaxf(em, C.err[w]);
+        return (double)em;
     };
 
     // stage flows and deformation-gradient stages for the step [t, t + h], then CMD_STEP
@@ -406,82 +596,29 @@ integrate_pipe_kernel(const __grid_constant__ IntegrateArgs A, const __grid_cons
                 left_stretch(C.kFnew, C.st[2].V);
             }
             C.cmd = CMD_STEP;
+            C.state = CMD_STEP;
         }
         post(X);
     };
 
-    // CMD_FINISH for the orientations, then the fraction part of
-    // extract_vars -> apply_gbs -> extract_vars (minerals.py:464-474, utils.py:159-190)
-    auto issue_finish = [&](int X) {
-        PipeSlot &C = sh.slot[X];
-        const double s1 = C.sum_clip;
-        if (lane == 0) {
-            C.s1 = s1;
-            C.cmd = CMD_FINISH;
-        }
-        post(X);
-        double *slot = slot_base(X);
-        double *T1 = slot + PS_T1 * Npad, *T2 = slot + PS_T2 * Npad;
-        double *f_out = A.f_out + (int64_t)C.sys * N;
-        double s2 = 0.0, s3 = 0.0;
-        {
-            const double *const in[1] = {C.f_cur};
-            ring_sweep<1>(in, Npad, ring, sh.ring_bar, ring_seq, lane, [&](int t, const double (&v)[1][RING_J]) {
-#pragma unroll
-                for (int j = 0; j < RING_J; ++j) {
-                    const int64_t g = (int64_t)t * RING_TILE + j * 32 + lane;
-                    double x = gbs_fraction(v[0][j], s1);
-                    x = (x < floor_v) ? floor_v : x;
-                    x = (g < N) ? x : 0.0;
-                    if (g < Npad) T1[g] = x;
-                    s2 += x;
-                }
-            });
-        }
-        s2 = warp_sum(s2);
-        PIPE_FENCE();
-        __syncwarp();
-        {
-            const double *const in[1] = {T1};
-            ring_sweep<1>(in, Npad, ring, sh.ring_bar, ring_seq, lane, [&](int t, const double (&v)[1][RING_J]) {
-#pragma unroll
-                for (int j = 0; j < RING_J; ++j) {
-                    const int64_t g = (int64_t)t * RING_TILE + j * 32 + lane;
-                    const double x = (g < Npad) ? fmax(v[0][j] / s2, 0.0) : 0.0;
-                    if (g < Npad) T2[g] = x;
-                    s3 += x;
-                }
-            });
-        }
-        s3 = warp_sum(s3);
-        PIPE_FENCE();
-        __syncwarp();
-        {
-            const double *const in[1] = {T2};
-            ring_sweep<1>(in, Npad, ring, sh.ring_bar, ring_seq, lane, [&](int t, const double (&v)[1][RING_J]) {
-#pragma unroll
-                for (int j = 0; j < RING_J; ++j) {
-                    const int64_t g = (int64_t)t * RING_TILE + j * 32 + lane;
-                    if (g < N) f_out[g] = v[0][j] / s3;
-                }
-            });
-        }
-        if (lane == 0) C.state = CMD_FINISH;
-        __syncwarp();
-    };
-
-    // next command of a slot whose state is consistent at time C.t
+    // next long command of a slot whose state is consistent at time C.t
     auto advance = [&](int X) {
         PipeSlot &C = sh.slot[X];
-        if (!C.done && C.status == 0 && C.n_acc + C.n_rej >= A.tol.max_steps) {
-            if (lane == 0) C.status = 1;  // DREX_STATUS_MAX_STEPS
-            __syncwarp();
-        }
-        if (C.done || C.status != 0) {
-            PIPE_TIME(3, issue_finish(X))
+        const bool out_of_steps = !C.done && C.status == 0 && C.n_acc + C.n_rej >= A.tol.max_steps;
+        const bool finish = C.done || C.status != 0 || out_of_steps;
+        __syncwarp();
+        if (finish) {
+            // end of interval: extract_vars -> apply_gbs -> extract_vars (minerals.py:464-474,
+            // utils.py:159-190); orientations in the long pass, fractions in fragments G1-G3
+            if (lane == 0) {
+                if (out_of_steps) C.status = 1;  // DREX_STATUS_MAX_STEPS
+                C.s1 = C.sum_clip;
+                C.cmd = CMD_FINISH;
+                C.state = CMD_FINISH;
+            }
+            post(X);
         } else {
-            if (lane == 0) C.state = CMD_STEP;
-            PIPE_TIME(4, issue_step(X))
+            issue_step(X);
         }
     };
 
@@ -520,7 +657,6 @@ integrate_pipe_kernel(const __grid_constant__ IntegrateArgs A, const __grid_cons
             for (int j = lane; j < A.K * 9; j += 32) C.Ltab[j] = A.L_nodes[ip * A.K * 9 + j];
         __syncwarp();
         warp_stage_flows(A, Ltable, C.st, 2, 1, t_begin, t_begin, t_begin, t_begin, t_end, C.xnode, lane);
-        double *fA = slot + PS_FA * Npad;  // the INIT pass copies the fractions here
         if (lane == 0) {
             const double *L = C.st[2].Lraw;
             C.const_flow = (A.L_kind == 0 || A.K == 1) ? 1 : 0;
@@ -544,7 +680,7 @@ integrate_pipe_kernel(const __grid_constant__ IntegrateArgs A, const __grid_cons
             C.t_end = t_end;
             C.span = span;
             C.h_carry = 0.0;
-            C.sum_clip = 0.0;  // set after the INIT pass
+            C.sum_clip = 0.0;  // set by fragment K0
             C.gbm_scale = gbm_scale;
             C.ip = ip;
             C.sys = sys;
@@ -553,10 +689,11 @@ integrate_pipe_kernel(const __grid_constant__ IntegrateArgs A, const __grid_cons
             C.f_active = f_active ? 1 : 0;
             C.yk_cur = slot + PS_YKA * Npad;
             C.yk_nxt = slot + PS_YKB * Npad;
-            C.f_cur = fA;
+            C.f_cur = slot + PS_FA * Npad;  // the INIT pass copies the fractions here
             C.f_nxt = slot + PS_FB * Npad;
             C.kf_cur = slot + PS_KFA * Npad;
             C.kf_nxt = slot + PS_KFB * Npad;
+            C.f_out = A.f_out + s * N;
             C.n_rhs = 1;
             C.n_acc = 0;
             C.n_rej = 0;
@@ -569,171 +706,12 @@ integrate_pipe_kernel(const __grid_constant__ IntegrateArgs A, const __grid_cons
         post(X);
     };
 
-    // sum of max(f, 0) (utils.py:188-189) and the initial slope of the fractions once the
-    // compute warps have copied the fractions and evaluated the energies at t0
-    auto after_init = [&](int X) {
-        PipeSlot &C = sh.slot[X];
-        double *slot = slot_base(X);
-        const double *E4 = slot + PS_E4 * Npad;
-        double sumc = 0.0, se = 0.0;
-        if (C.f_active) {
-            const double *const in[2] = {C.f_cur, E4};
-            ring_sweep<2>(in, Npad, ring, sh.ring_bar, ring_seq, lane, [&](int t, const double (&v)[2][RING_J]) {
-#pragma unroll
-                for (int j = 0; j < RING_J; ++j) {
-                    const int64_t g = (int64_t)t * RING_TILE + j * 32 + lane;
-                    const double x = (g < N) ? fmax(v[0][j], 0.0) : 0.0;
-                    sumc += x;
-                    se += (g < N) ? x * v[1][j] : 0.0;
-                }
-            });
-            sumc = warp_sum(sumc);
-            se = warp_sum(se);
-            // df = vf M* (f / sum f) (mean - E) s (core.py:431-436)
-            const double mean = se / sumc, ps = C.st[2].s * C.gbm_scale / sumc;
-            double *kf = C.kf_cur;
-            ring_sweep<2>(in, Npad, ring, sh.ring_bar, ring_seq, lane, [&](int t, const double (&v)[2][RING_J]) {
-#pragma unroll
-                for (int j = 0; j < RING_J; ++j) {
-                    const int64_t g = (int64_t)t * RING_TILE + j * 32 + lane;
-                    const double k1 = (g < N) ? (ps * fmax(v[0][j], 0.0)) * (mean - v[1][j]) : 0.0;
-                    if (g < Npad) kf[g] = k1;
-                }
-            });
-            PIPE_FENCE();
-        } else {
-            const double *const in[1] = {C.f_cur};
-            ring_sweep<1>(in, Npad, ring, sh.ring_bar, ring_seq, lane, [&](int t, const double (&v)[1][RING_J]) {
-#pragma unroll
-                for (int j = 0; j < RING_J; ++j) {
-                    const int64_t g = (int64_t)t * RING_TILE + j * 32 + lane;
-                    sumc += (g < N) ? fmax(v[0][j], 0.0) : 0.0;
-                }
-            });
-            sumc = warp_sum(sumc);
-        }
-        if (lane == 0) C.sum_clip = sumc;
-        __syncwarp();
-        advance(X);
-    };
-
-    // coupled fraction stages, error norm, accept / reject, step controller
-    auto after_step = [&](int X) {
+    // accept / reject and the step controller, once the weighted error of the whole state is known
+    auto decide = [&](int X, double emax, double sum_clip_new) {
         PipeSlot &C = sh.slot[X];
         const double h = C.h;
-        float em = 0.0f;
-        for (int w = 0; w < PIPE_CW; ++w) em = fmaxf(em, C.err[w]);
-        double emax = (double)em;
-        double sum_clip_new = C.sum_clip;
-        if (C.f_active) {
-            double *slot = slot_base(X);
-            const double *E2 = slot + PS_E2 * Npad, *E3 = slot + PS_E3 * Npad, *E4 = slot + PS_E4 * Npad;
-            double *T1 = slot + PS_T1 * Npad, *T2 = slot + PS_T2 * Npad;
-            const double *fc_ = C.f_cur, *k1p = C.kf_cur;
-            double *fnx = C.f_nxt, *kfn = C.kf_nxt;
-            const double gs = C.gbm_scale;
-            double sc = 0.0, se = 0.0;
-            {  // stage 2 state
-                const double *const in[3] = {fc_, k1p, E2};
-                ring_sweep<3>(in, Npad, ring, sh.ring_bar, ring_seq, lane, [&](int t, const double (&v)[3][RING_J]) {
-#pragma unroll
-                    for (int j = 0; j < RING_J; ++j) {
-                        const int64_t g = (int64_t)t * RING_TILE + j * 32 + lane;
-                        const bool ok = g < N;
-                        const double x = ok ? fmax(v[0][j] + (h * BS_A21) * v[1][j], 0.0) : 0.0;
-                        sc += x;
-                        se += ok ? x * v[2][j] : 0.0;
-                    }
-                });
-            }
-            sc = warp_sum(sc);
-            se = warp_sum(se);
-            const double mean2 = se / sc, ps2 = C.st[0].s * gs / sc;
-            sc = 0.0;
-            se = 0.0;
-            {  // k2, stage 3 state
-                const double *const in[4] = {fc_, k1p, E2, E3};
-                ring_sweep<4>(in, Npad, ring, sh.ring_bar, ring_seq, lane, [&](int t, const double (&v)[4][RING_J]) {
-#pragma unroll
-                    for (int j = 0; j < RING_J; ++j) {
-                        const int64_t g = (int64_t)t * RING_TILE + j * 32 + lane;
-                        const bool ok = g < N;
-                        const double f = v[0][j];
-                        const double x2 = fmax(f + (h * BS_A21) * v[1][j], 0.0);
-                        const double k2 = ok ? (ps2 * x2) * (mean2 - v[2][j]) : 0.0;
-                        if (g < Npad) T1[g] = k2;
-                        const double x3 = ok ? fmax(f + (h * BS_A32) * k2, 0.0) : 0.0;
-                        sc += x3;
-                        se += ok ? x3 * v[3][j] : 0.0;
-                    }
-                });
-            }
-            sc = warp_sum(sc);
-            se = warp_sum(se);
-            const double mean3 = se / sc, ps3 = C.st[1].s * gs / sc;
-            sc = 0.0;
-            se = 0.0;
-            PIPE_FENCE();
-            __syncwarp();
-            {  // k3, new state
-                const double *const in[5] = {fc_, k1p, T1, E3, E4};
-                ring_sweep<5>(in, Npad, ring, sh.ring_bar, ring_seq, lane, [&](int t, const double (&v)[5][RING_J]) {
-#pragma unroll
-                    for (int j = 0; j < RING_J; ++j) {
-                        const int64_t g = (int64_t)t * RING_TILE + j * 32 + lane;
-                        const bool ok = g < N;
-                        const double f = v[0][j], k1 = v[1][j], k2 = v[2][j];
-                        const double x3 = fmax(f + (h * BS_A32) * k2, 0.0);
-                        const double k3 = ok ? (ps3 * x3) * (mean3 - v[3][j]) : 0.0;
-                        const double fn = ok ? f + h * (BS_B1 * k1 + BS_B2 * k2 + BS_B3 * k3) : 0.0;
-                        if (g < Npad) {
-                            fnx[g] = fn;
-                            T2[g] = ok ? BS_E1 * k1 + BS_E2 * k2 + BS_E3 * k3 : 0.0;  // error combination
-                        }
-                        const double xn = fmax(fn, 0.0);
-                        sc += xn;
-                        se += ok ? xn * v[4][j] : 0.0;
-                    }
-                });
-            }
-            sc = warp_sum(sc);
-            se = warp_sum(se);
-            sum_clip_new = sc;
-            const double mean4 = se / sc, ps4 = C.st[2].s * gs / sc;
-            PIPE_FENCE();
-            __syncwarp();
-            float ef = 0.0f, rf = 0.0f;
-            {  // k4 (FSAL), error
-                const double *const in[3] = {fnx, T2, E4};
-                ring_sweep<3>(in, Npad, ring, sh.ring_bar, ring_seq, lane, [&](int t, const double (&v)[3][RING_J]) {
-#pragma unroll
-                    for (int j = 0; j < RING_J; ++j) {
-                        const int64_t g = (int64_t)t * RING_TILE + j * 32 + lane;
-                        const bool ok = g < N;
-                        const double fn = v[0][j];
-                        const double k4 = ok ? (ps4 * fmax(fn, 0.0)) * (mean4 - v[2][j]) : 0.0;
-                        if (g < Npad) kfn[g] = k4;
-                        if (ok) {
-                            const double err = h * (v[1][j] + BS_E4 * k4);
-                            const float r = err_ratio(err, fn, atol_abs, relw);
-                            ef = fmaxf(ef, r);
-                            rf += r;
-                        }
-                    }
-                });
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                ef = fmaxf(ef, __shfl_xor_sync(0xffffffffu, ef, o));
-                rf += __shfl_xor_sync(0xffffffffu, rf, o);
-            }
-            emax = (rf < INFINITY) ? fmax(emax, (double)ef) : INFINITY;
-            PIPE_FENCE();
-            __syncwarp();
-        }
         emax = fmax(emax, C.errF);
-
-        // ---- accept / reject (every lane computes the same values; lane 0 records them) ----
+        // every lane computes the same values; lane 0 records them
         int n_acc = C.n_acc, n_rej = C.n_rej, status = 0, done = 0, last_rejected = C.last_rejected;
         double t_now = C.t, h_carry = C.h_carry, h_next = h;
         const double t_end = C.t_end, span = C.span;
@@ -767,7 +745,6 @@ integrate_pipe_kernel(const __grid_constant__ IntegrateArgs A, const __grid_cons
         }
         __syncwarp();  // all lanes have read the slot
         if (lane == 0) {
-            C.n_rhs += 3;
             C.n_acc = n_acc;
             C.n_rej = n_rej;
             C.status = status;
@@ -784,7 +761,7 @@ integrate_pipe_kernel(const __grid_constant__ IntegrateArgs A, const __grid_cons
                 C.yk_cur = C.yk_nxt;
                 C.yk_nxt = const_cast<double *>(ykt);
                 if (C.f_active) {
-                    double *fo = const_cast<double *>(C.f_cur);
+                    double *fo = C.f_cur;
                     C.f_cur = C.f_nxt;
                     C.f_nxt = fo;
                     double *kft = C.kf_cur;
@@ -801,41 +778,113 @@ integrate_pipe_kernel(const __grid_constant__ IntegrateArgs A, const __grid_cons
         advance(X);
     };
 
-    auto after_finish = [&](int X) {
+    // the command of slot X has been executed by all compute warps: what comes next
+    auto handle = [&](int X) {
         PipeSlot &C = sh.slot[X];
-        if (lane == 0) {
-            const int64_t s = C.sys;
-            for (int c = 0; c < 9; ++c) A.F[s * 9 + c] = C.F[c];
-            if (A.h_io) A.h_io[s] = C.h;
-            A.status[s] = C.status;
-            if (A.n_rhs) A.n_rhs[s] = C.n_rhs;
-            if (A.n_accept) A.n_accept[s] = C.n_acc;
-            if (A.n_reject) A.n_reject[s] = C.n_rej;
+        const int state = C.state;
+        const double gs = C.gbm_scale;
+        double sc, se;
+        switch (state) {
+        case CMD_INIT:
+            post_fragment(X, FRAG_K0, 0.0, 0.0);
+            break;
+        case ST_FRAG + FRAG_K0: {
+            combine(X, sc, se);
+            const bool f_active = C.f_active != 0;
+            const double s2 = C.st[2].s;
+            __syncwarp();
+            if (lane == 0) C.sum_clip = sc;
+            __syncwarp();
+            if (f_active) post_fragment(X, FRAG_K1, s2 * gs / sc, se / sc);
+            else advance(X);
+            break;
         }
-        __syncwarp();
-        setup(X);
+        case ST_FRAG + FRAG_K1:
+            advance(X);
+            break;
+        case CMD_STEP: {
+            const double em = combine_err(X);
+            const bool f_active = C.f_active != 0;
+            const double sum_clip = C.sum_clip;
+            __syncwarp();
+            if (lane == 0) {
+                C.n_rhs += 3;
+                C.emax_o = em;
+            }
+            __syncwarp();
+            if (f_active) post_fragment(X, FRAG_S1, 0.0, 0.0);
+            else decide(X, em, sum_clip);
+            break;
+        }
+        case ST_FRAG + FRAG_S1:
+            combine(X, sc, se);
+            post_fragment(X, FRAG_S2, C.st[0].s * gs / sc, se / sc);
+            break;
+        case ST_FRAG + FRAG_S2:
+            combine(X, sc, se);
+            post_fragment(X, FRAG_S3, C.st[1].s * gs / sc, se / sc);
+            break;
+        case ST_FRAG + FRAG_S3: {
+            combine(X, sc, se);
+            const double s2 = C.st[2].s;
+            __syncwarp();
+            if (lane == 0) C.sum_clip_new = sc;
+            post_fragment(X, FRAG_S4, s2 * gs / sc, se / sc);
+            break;
+        }
+        case ST_FRAG + FRAG_S4: {
+            const double ef = combine_err(X);  // inf when a fraction error was not finite
+            decide(X, fmax(C.emax_o, ef), C.sum_clip_new);
+            break;
+        }
+        case CMD_FINISH:
+            post_fragment(X, FRAG_G1, C.s1, floor_v);
+            break;
+        case ST_FRAG + FRAG_G1:
+            combine(X, sc, se);
+            post_fragment(X, FRAG_G2, sc, 0.0);
+            break;
+        case ST_FRAG + FRAG_G2:
+            combine(X, sc, se);
+            post_fragment(X, FRAG_G3, sc, 0.0);
+            break;
+        default:  // ST_FRAG + FRAG_G3: the system is finished
+            if (lane == 0) {
+                const int64_t s = C.sys;
+                for (int c = 0; c < 9; ++c) A.F[s * 9 + c] = C.F[c];
+                if (A.h_io) A.h_io[s] = C.h;
+                A.status[s] = C.status;
+                if (A.n_rhs) A.n_rhs[s] = C.n_rhs;
+                if (A.n_accept) A.n_accept[s] = C.n_acc;
+                if (A.n_reject) A.n_reject[s] = C.n_rej;
+            }
+            __syncwarp();
+            setup(X);
+            break;
+        }
     };
 
     setup(0);
     setup(1);
-    for (int X = 0;; X ^= 1) {
+    for (;;) {
         const int st0 = sh.slot[0].state, st1 = sh.slot[1].state;
         if (st0 == CMD_EXIT && st1 == CMD_EXIT) break;
-        const int state = X ? st1 : st0;
-        if (state == CMD_EXIT) continue;
-        PIPE_IDLE(mbar_wait(&sh.done_bar[X], (dpar >> X) & 1u))
-        dpar ^= 1u << X;
-        PIPE_FENCE();
-        if (state == CMD_INIT) PIPE_TIME(0, after_init(X))
-        else if (state == CMD_STEP) PIPE_TIME(1, after_step(X))
-        else PIPE_TIME(2, after_finish(X))
+        bool any = false;
+#pragma unroll 1
+        for (int X = 0; X < 2; ++X) {
+            if ((X ? st1 : st0) == CMD_EXIT) continue;
+            if (!mbar_test(&sh.done_bar[X], (dpar >> X) & 1u, lane)) continue;
+            dpar ^= 1u << X;
+            any = true;
+            handle(X);
+        }
+        if (!any) PIPE_CLK(idle_clk, __nanosleep(40))
     }
 #ifdef DREX_PHASE_TIMERS
     if (lane == 0) {
         unsigned long long *out = reinterpret_cast<unsigned long long *>(A.queue) + 8;
         atomicAdd(out + 2, (unsigned long long)idle_clk);
         atomicAdd(out + 3, (unsigned long long)(clock64() - start_clk));
-        for (int i = 0; i < 5; ++i) atomicAdd(out + 4 + i, (unsigned long long)h_clk[i]);
     }
 #endif
 }

@@ -567,6 +567,54 @@ def test_generic_memory_path_is_bit_identical(drex):
     assert np.abs(np.einsum("pkgij,pkglj->pkgil", o, o) - np.eye(3)).max() < 5e-3
 
 
+def test_pipelined_integrator_matches_one_system_kernel(drex):
+    """The two-slot warp-specialised kernel (drex_integrate_pipe.cuh, method bit 0x400) against
+    the one-system-per-CTA kernel (0x200): same per-grain arithmetic, so orientations and F are
+    bit-identical; the fraction sums are added in a different (fixed) order, so fractions agree
+    to rounding.  Covers odd N, N below one chunk, both phases, carried step sizes, a
+    time-dependent (Chebyshev) L table, slot reuse (more systems than CTA slots), the
+    diffusion regime and run-to-run determinism."""
+    import torch
+
+    from pydrex_b200 import _lib
+
+    def run(method, P, N, n_updates, kind=_lib.L_CONSTANT, regime=4):
+        e = drex.ParticleEnsemble(P, N, TWO_PHASE, seed=5, regimes=(regime, regime))
+        tol = e.tolerances()
+        tol.method = method
+        for k in range(n_updates):
+            if kind == _lib.L_CONSTANT:
+                L = torch.zeros((P, 3, 3), dtype=torch.float64)
+                L[:, 1, 0] = torch.linspace(1.0, 3.0, P)
+            else:  # 5 Chebyshev-Lobatto nodes of a smoothly varying shear
+                x = 0.5 * (1.0 - torch.cos(torch.pi * torch.arange(5, dtype=torch.float64) / 4))
+                L = torch.zeros((P, 5, 3, 3), dtype=torch.float64)
+                L[:, :, 1, 0] = torch.linspace(1.0, 3.0, P)[:, None] * (1.0 + 0.5 * (k + x))[None, :]
+                L[:, :, 0, 2] = 0.3 * x[None, :]
+            e.update(0.05 * k, 0.05 * (k + 1), L, kind=kind, tol=tol)
+        return e
+
+    cases = [(3, 333, 4, _lib.L_CONSTANT, 4), (2, 31, 3, _lib.L_CONSTANT, 4),
+             (5, 1000, 3, _lib.L_CHEBYSHEV, 4), (200, 96, 3, _lib.L_CONSTANT, 4),
+             (3, 200, 2, _lib.L_CONSTANT, 1)]
+    for P, N, n, kind, regime in cases:
+        a, b, c = (run(m, P, N, n, kind, regime) for m in (0x200, 0x400, 0x400))
+        nt.assert_array_equal(a.o.cpu().numpy(), b.o.cpu().numpy())
+        nt.assert_array_equal(a.F.cpu().numpy(), b.F.cpu().numpy())
+        nt.assert_allclose(b.f.cpu().numpy(), a.f.cpu().numpy(), rtol=1e-12, atol=0)
+        nt.assert_array_equal(a.stats.cpu().numpy(), b.stats.cpu().numpy())
+        assert int(a.stats[1].sum()) > 4 * P  # steps were taken
+        # fixed summation order: a second run reproduces every bit
+        nt.assert_array_equal(b.o.cpu().numpy(), c.o.cpu().numpy())
+        nt.assert_array_equal(b.f.cpu().numpy(), c.f.cpu().numpy())
+    # failure status travels through the pipelined kernel too
+    e = drex.ParticleEnsemble(2, 64, TWO_PHASE, seed=1)
+    tol = e.tolerances()
+    tol.method = 0x400
+    with pytest.raises(drex.IterationError, match="non-finite"):
+        e.update(0.0, 0.1, torch.zeros((2, 3, 3), dtype=torch.float64), tol=tol)
+
+
 def test_backward_interval_and_status_codes(drex):
     """t1 < t0 integrates backwards (LSODA allows it); max_steps exhaustion raises."""
     m = drex.Mineral(n_grains=128, seed=4)
