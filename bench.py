@@ -283,6 +283,7 @@ def run_gpu(args):
 
     import pydrex_b200 as drex
     from pydrex_b200 import _lib
+    from pydrex_b200.ensemble import bind_host_to_gpu
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -291,6 +292,9 @@ def run_gpu(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    # one process per GPU: keep each rank (and the pinned buffers of its host-buffer arm) on
+    # the GPU's own NUMA node
+    numa_cores = bind_host_to_gpu(local_rank) if world > 1 and not args.no_numa_bind else []
     P, N, K, W = args.particles, args.grains, args.steps, args.warmup
     n_total = K + W
     kind, tables, t_edges = make_workload(args.workload, P, n_total, seed=1000 + rank)
@@ -415,6 +419,8 @@ def run_gpu(args):
             "cache": f"inputs larger than L2: {state_bytes / 1e6:.0f} MB state + "
                      f"{ens._ws.numel() / 1e6:.0f} MB scratch per GPU vs 126 MB L2",
             "parallelism": f"particles sharded over {world} GPU(s), no data-path collective",
+            "host_binding": (f"rank 0 pinned to {len(numa_cores)} cores near its GPU (NVML affinity)"
+                             if numa_cores else "none"),
         },
         "grain_evals_per_s": evals / secs,
         "grain_internal_steps_per_s": internal / secs,
@@ -667,6 +673,7 @@ def main():
     ap.add_argument("--workload", default="corner_flow", choices=["simple_shear", "corner_flow"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clock-sampler", action="store_true", help="diagnostic: do not run nvidia-smi")
+    ap.add_argument("--no-numa-bind", action="store_true", help="diagnostic: do not pin ranks to their GPU's cores")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="pipeline depth of the host-buffer arm")
     args = ap.parse_args()
     if args.impl == "reference":
