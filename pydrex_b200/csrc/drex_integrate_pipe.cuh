@@ -674,6 +674,7 @@ integrate_pipe_kernel(const __grid_constant__ IntegrateArgs A, const __grid_cons
                 h = A.tol.max_step_frac * span;
             // a step carried over from a longer interval must not leave this one
             if (!(fabs(h) < fabs(span))) h = span;
+            if (DREX_STRETCH > 1.0) h = plan_step(h, span);
             C.h = h;
             C.t = t_begin;
             C.t_begin = t_begin;
@@ -720,7 +721,7 @@ integrate_pipe_kernel(const __grid_constant__ IntegrateArgs A, const __grid_cons
             status = 3;  // DREX_STATUS_NOT_FINITE
         } else {
             accept = emax <= 1.0;
-            double fac = (emax > 0.0) ? 0.9 * rcbrt(emax) : 5.0;  // err^(-1/3)
+            double fac = (emax > 0.0) ? DREX_SAFETY * rcbrt(emax) : 5.0;  // err^(-1/3)
             fac = fmin(accept ? (last_rejected ? 1.0 : 5.0) : 1.0, fmax(0.2, fac));
             h_next = h * fac;
             if (accept) {
@@ -735,6 +736,7 @@ integrate_pipe_kernel(const __grid_constant__ IntegrateArgs A, const __grid_cons
                     if (A.tol.max_step_frac > 0.0 && fabs(h_next) > A.tol.max_step_frac * fabs(span))
                         h_next = A.tol.max_step_frac * span;
                     if (fabs(h_next) >= fabs(remaining) * (1.0 - 1e-10)) h_next = remaining;
+                    else if (DREX_STRETCH > 1.0) h_next = plan_step(h_next, remaining);
                 }
             } else {
                 ++n_rej;
