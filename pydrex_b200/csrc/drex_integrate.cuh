@@ -231,6 +231,7 @@ struct StepShared {
     double t, h, tend;
     double red[64];
     uint64_t mbar[INT_WARPS];
+    uint64_t mbar2[INT_WARPS];  // second in-flight chunk of the end-of-interval pass
     double xnode[33];      // Chebyshev-Lobatto abscissae of the L(t) table (K <= 33)
     double Ltab[33 * 9];   // this particle's L(t) node table (K <= 33; larger ones stay global)
     int sys, flag;
@@ -420,8 +421,11 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
     double *fs = (3 < A.smem_arrays) ? p2_smem + 3 * Npad : slot + (SLOT_P2 + 3) * Npad;
 
     uint64_t *mbar = &sh.mbar[warp];
-    uint32_t mbar_parity = 0;
-    if (lane == 0) mbar_init(mbar, 1);
+    uint32_t mbar_parity = 0, mbar2_parity = 0;
+    if (lane == 0) {
+        mbar_init(mbar, 1);
+        mbar_init(&sh.mbar2[warp], 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
@@ -943,7 +947,56 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                 const int64_t g = ((int64_t)warp + j * INT_WARPS) * 32 + lane;
                 if (g < N) f_out[g] = fa[j] / s3;
             }
-            // orientations: sliding grains get the interval-start orientation back;
+            DREX_MARK(7)  // end-of-interval pass, fraction part (development builds only)
+            // orientations: sliding grains get the interval-start orientation back.  This pass is
+            // pure data movement and latency-bound with one chunk of loads in flight per thread,
+            // so when the rows are 16-byte aligned both candidates of a chunk -- the new
+            // orientation (9 rows of the chunked buffer, contiguous) and the interval-start one
+            // (9 rows of o_in) -- come in by TMA bulk copies, two chunks ahead, into the two halves
+            // of the warp's stage; no registers are tied up by loads in flight.
+            const bool rows_aligned = ((N & 1) == 0) && ((reinterpret_cast<uintptr_t>(o_in) & 15) == 0);
+            if (rows_aligned) {
+                auto issue_end = [&](int64_t q, int half) {
+                    if (lane == 0) {
+                        const int64_t g0 = q * 32;
+                        const uint32_t row_bytes = (uint32_t)(((N - g0 < 32) ? (N - g0) : 32) * sizeof(double));
+                        uint64_t *bar = half ? &sh.mbar2[warp] : mbar;
+                        double *dst = stage + half * 18 * 32;
+                        mbar_expect_tx(bar, (uint32_t)(9 * 32 * sizeof(double)) + 9 * row_bytes);
+                        bulk_g2s(dst, yk_cur + q * CHUNK_DOUBLES, (uint32_t)(9 * 32 * sizeof(double)), bar);
+                        for (int c = 0; c < 9; ++c) bulk_g2s(dst + (9 + c) * 32, o_in + c * N + g0, row_bytes, bar);
+                    }
+                };
+                if (warp < n_chunks) issue_end(warp, 0);
+                if (warp + INT_WARPS < n_chunks) issue_end(warp + INT_WARPS, 1);
+                int j = 0;
+                for (int64_t q = warp; q < n_chunks; q += INT_WARPS, ++j) {
+                    const int64_t g = q * 32 + lane;
+                    const int half = j & 1;
+                    if (half) {
+                        mbar_wait(&sh.mbar2[warp], mbar2_parity);
+                        mbar2_parity ^= 1u;
+                    } else {
+                        mbar_wait(mbar, mbar_parity);
+                        mbar_parity ^= 1u;
+                    }
+                    const double *base = stage + half * 18 * 32 + lane;
+                    const bool sl = ((slide_mask >> j) & 1u) != 0;
+                    double a[9];
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) a[c] = sl ? base[(9 + c) * 32] : base[c * 32];
+                    clip9(a);
+                    // generic-proxy loads, then an async-proxy overwrite of the same rows: the
+                    // proxy fence orders them
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (q + 2 * INT_WARPS < n_chunks) issue_end(q + 2 * INT_WARPS, half);
+                    if (g < N) {
+#pragma unroll
+                        for (int c = 0; c < 9; ++c) o_out[c * N + g] = a[c];
+                    }
+                }
+            } else {
             // pipelined so the next chunk's loads overlap this chunk's stores
             double an[9];
             {
@@ -973,6 +1026,7 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
 #pragma unroll
                     for (int c = 0; c < 9; ++c) o_out[c * N + g] = a[c];
                 }
+            }
             }
         } else {
             double s2 = 0.0, dummy = 0.0;
