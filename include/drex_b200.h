@@ -164,7 +164,8 @@ typedef struct drex_tolerances {
     int32_t method;         /* low byte 0: Bogacki-Shampine 3(2) with FSAL.  Kernel choice (testing
                                aid; default: one CTA per system): 0x200 forces the one-system kernel,
                                0x100 the same with the through-memory fraction stages it uses for
-                               N > 5120, 0x400 the two-slot pipelined kernel.  The environment
+                               N > 5120, 0x400 the two-slot pipelined kernel; 0x800 runs the initial slope as a
+                               separate pass instead of fusing it into the first step.  The environment
                                variable DREX_INTEGRATOR=pipe|single overrides the default */
 } drex_tolerances_t;
 

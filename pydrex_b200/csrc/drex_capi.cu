@@ -308,7 +308,7 @@ int drex_integrate_f64(int64_t S, int64_t P, int64_t N, const int32_t *sys_parti
     if (!(tol->rtol >= 0.0) || !(tol->atol_abs >= 0.0) || !(tol->atol_rel >= 0.0) ||
         !(tol->rtol + tol->atol_abs + tol->atol_rel > 0.0))
         return fail(DREX_E_INVALID, "tolerances must be non-negative and not all zero");
-    if ((tol->method & 0xff) != 0 || (tol->method & ~0x7ff) != 0) return fail(DREX_E_INVALID, "unknown integration method %d", tol->method);
+    if ((tol->method & 0xff) != 0 || (tol->method & ~0xfff) != 0) return fail(DREX_E_INVALID, "unknown integration method %d", tol->method);
     if (S == 0 || N == 0) return DREX_OK;
     if (!sys_particle || !sys_phase || !sys_fabric || !sys_regime || !sys_vol_frac || !F || !o_in ||
         !f_in || !o_out || !f_out || !t0 || !t1 || !L_nodes || !status)

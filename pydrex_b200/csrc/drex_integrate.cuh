@@ -81,7 +81,8 @@ struct IntegrateArgs {
 constexpr int SLOT_YKA = 0, SLOT_YKB = 18;
 constexpr int SLOT_FA = 36, SLOT_FB = 37, SLOT_KFA = 38, SLOT_KFB = 39;
 constexpr int SLOT_P2 = 40;  // 4 fraction-stage arrays when they do not fit in shared memory
-constexpr int SLOT_ARRAYS = 44;
+constexpr int SLOT_E1 = 44;  // strain energies at the interval start (fused first step)
+constexpr int SLOT_ARRAYS = 45;
 constexpr int CHUNK_DOUBLES = 18 * 32;
 
 // ---- TMA bulk copy + mbarrier (sm_90+/sm_100a PTX) ------------------------------------
@@ -224,7 +225,7 @@ struct StageFlow {
 };
 
 struct StepShared {
-    StageFlow st[3];       // stage times t + h/2, t + 3h/4, t + h
+    StageFlow st[4];       // stage times t + h/2, t + 3h/4, t + h; [3]: the interval start t0
     double F[9], kF[9];    // deformation gradient and its FSAL slope L(t).F
     double Fnew[9], kFnew[9];
     double errF;           // weighted error of the F block
@@ -470,18 +471,19 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
             if (A.K <= 33)
                 for (int j = lane; j < A.K * 9; j += 32) sh.Ltab[j] = A.L_nodes[ip * A.K * 9 + j];
             __syncwarp();
-            warp_stage_flows(A, Ltable, sh.st, 2, 1, t_begin, t_begin, t_begin, t_begin, t_end, sh.xnode, lane);
+            warp_stage_flows(A, Ltable, sh.st, 3, 1, t_begin, t_begin, t_begin, t_begin, t_end, sh.xnode, lane);
         }
         if (tid == 0) {
-            const double *L = sh.st[2].Lraw;
+            const double *L = sh.st[3].Lraw;
             sh.const_flow = (A.L_kind == 0 || A.K == 1) ? 1 : 0;
             if (sh.const_flow) {
-                sh.st[0] = sh.st[2];
-                sh.st[1] = sh.st[2];
+                sh.st[0] = sh.st[3];
+                sh.st[1] = sh.st[3];
+                sh.st[2] = sh.st[3];
             }
             for (int c = 0; c < 9; ++c) sh.F[c] = A.F[s * 9 + c];
             matmul3(L, sh.F, sh.kF);
-            if (regime == 1) left_stretch(sh.kF, sh.st[2].V);
+            if (regime == 1) left_stretch(sh.kF, sh.st[3].V);
             sh.t = t_begin;
             sh.tend = t_end;
             double h = (A.h_io != nullptr) ? A.h_io[s] : 0.0;
@@ -496,7 +498,17 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
         }
         __syncthreads();
         double sum_clip = 0.0;  // sum of max(f, 0) of the current state (utils.py:188-189)
-        {
+        // FUSED FIRST STEP.  A separate initial-slope pass moves every orientation through the
+        // SM twice more (o_in in, state + slope out to the chunked buffer: ~1.1 MB per system,
+        // as long as a right-hand side takes).  Instead the first step of the interval reads
+        // o_in directly and runs FOUR stages per chunk (slope at t0, then the three stages);
+        // nothing is written back for it: a rejected first step is simply redone, slope
+        // included.  Needs 16-byte aligned o_in rows (TMA) and the register-resident fraction
+        // stages; otherwise, and for a zero-length interval, the separate pass below runs.
+        double *E1 = slot + SLOT_E1 * Npad;
+        const bool fused = fast && span != 0.0 && ((N & 1) == 0) &&
+                           ((reinterpret_cast<uintptr_t>(o_in) & 15) == 0) && !(A.tol.method & 0x800);
+        if (!fused) {
             // software-pipelined: the next chunk's loads are in flight during this chunk's math
             double sumc = 0.0, sume = 0.0, an[9], fn = 0.0;
             {
@@ -523,7 +535,7 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
 #pragma unroll
                 for (int c = 0; c < 9; ++c) blk[c * 32] = a[c];  // idle lanes of the tail: zeros
                 clip9(a);
-                stage_rhs<GRAIN_RUNTIME>(a, sh.st[2], regime, fc, math_tab, k, e);
+                stage_rhs<GRAIN_RUNTIME>(a, sh.st[3], regime, fc, math_tab, k, e);
 #pragma unroll
                 for (int c = 0; c < 9; ++c) blk[(9 + c) * 32] = k[c];
                 if (g < N) {
@@ -538,7 +550,7 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                 const double mean = sume / sumc;
                 // df = vf M* (f / sum f) (mean - E) s (core.py:431-436): the factor common to all
                 // grains of a stage, s vf M* / sum f, is formed once per thread
-                const double ps = sh.st[2].s * gbm_scale / sumc;
+                const double ps = sh.st[3].s * gbm_scale / sumc;
                 if (fast) {
                     double fr[MAXQ], er[MAXQ];
 #pragma unroll
@@ -561,7 +573,7 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                 }
             }
         }
-        int n_rhs = 1, n_acc = 0, n_rej = 0, status = 0;
+        int n_rhs = fused ? 0 : 1, n_acc = 0, n_rej = 0, status = 0;
         bool done = (span == 0.0);
         bool last_rejected = false;
         double h_carry = 0.0;
@@ -582,8 +594,22 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                     bulk_g2s(stage, yk_cur + q * CHUNK_DOUBLES, (uint32_t)(CHUNK_DOUBLES * sizeof(double)), mbar);
                 }
             };
+            // until a step has been accepted the state is still o_in: fused first step
+            const bool first = fused && n_acc == 0;
+            auto issue_first = [&](int64_t q) {
+                // the nine 256 B rows of o_in for chunk q into rows 0-8
+                if (lane == 0) {
+                    const int64_t g0 = q * 32;
+                    const uint32_t row_bytes = (uint32_t)(((N - g0 < 32) ? (N - g0) : 32) * sizeof(double));
+                    mbar_expect_tx(mbar, 9 * row_bytes);
+                    for (int c = 0; c < 9; ++c) bulk_g2s(stage + c * 32, o_in + c * N + g0, row_bytes, mbar);
+                }
+            };
             // prefetch this warp's first chunk while the stage flows are being set up
-            if (warp < n_chunks) issue_chunk(warp);
+            if (warp < n_chunks) {
+                if (first) issue_first(warp);
+                else issue_chunk(warp);
+            }
 
             // stage flows at t + h/2, t + 3h/4, t + h (three lanes), then F by lane 0
             if (!sh.const_flow && tid < 32)
@@ -638,8 +664,17 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                 double k[9], st[9], e = 0.0;
                 mbar_wait(mbar, mbar_parity);
                 mbar_parity ^= 1u;
+                if (first) {
+                    // rows 0-8 hold o_in; lanes past the end of a ragged last chunk carry zeros
 #pragma unroll
-                for (int c = 0; c < 9; ++c) st[c] = fma(h * BS_A21, sk[c * 32], sa[c * 32]);
+                    for (int c = 0; c < 9; ++c) {
+                        if (!live) sa[c * 32] = 0.0;
+                        st[c] = live ? sa[c * 32] : 0.0;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) st[c] = fma(h * BS_A21, sk[c * 32], sa[c * 32]);
+                }
                 // The three stages run as a ROLLED loop: one copy of the ~1300-instruction
                 // right-hand side in the hot loop keeps it inside the instruction cache
                 // (three inlined copies are ~80 KB of SASS and every warp streams them
@@ -648,14 +683,21 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                 // new state y + h (b1 k1 + b2 k2) and the partial error e1 k1 + e2 k2 after
                 // stage 2, the full ones after stage 3.
 #pragma unroll 1
-                for (int stg = 0; stg < 3; ++stg) {
+                for (int stg = first ? -1 : 0; stg < 3; ++stg) {
                     clip9(st);
-                    stage_rhs<MODE>(st, sh.st[stg], regime, fc, math_tab, k, e);
+                    stage_rhs<MODE>(st, sh.st[stg & 3], regime, fc, math_tab, k, e);  // -1 -> [3]: t0
                     if (f_active && live) {
-                        double *Ep = (stg == 0) ? E2 : ((stg == 1) ? E3 : E4);
+                        double *Ep = (stg == 0) ? E2 : ((stg == 1) ? E3 : ((stg == 2) ? E4 : E1));
                         Ep[g] = e;
                     }
-                    if (stg == 0) {
+                    if (stg < 0) {
+                        // slope at t0 (the FSAL slope of a later step): rows 9-17, then stage 2
+#pragma unroll
+                        for (int c = 0; c < 9; ++c) {
+                            sk[c * 32] = k[c];
+                            st[c] = fma(h * BS_A21, k[c], sa[c * 32]);
+                        }
+                    } else if (stg == 0) {
 #pragma unroll
                         for (int c = 0; c < 9; ++c) {
                             const double ac = sa[c * 32], kc = sk[c * 32];
@@ -665,7 +707,10 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                         }
                         // rows 0-17 are free now: fetch the next chunk behind stages 3 and 4
                         __syncwarp();
-                        if (qn < n_chunks) issue_chunk(qn);
+                        if (qn < n_chunks) {
+                            if (first) issue_first(qn);
+                            else issue_chunk(qn);
+                        }
                     } else if (stg == 1) {
 #pragma unroll
                         for (int c = 0; c < 9; ++c) {
@@ -696,7 +741,7 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
             else if (fc.phase != 0) phase1(std::integral_constant<int, GRAIN_ENSTATITE>{});
             else if (fc.default_exponents) phase1(std::integral_constant<int, GRAIN_OLIVINE_DEFAULT>{});
             else phase1(std::integral_constant<int, GRAIN_OLIVINE_GENERIC>{});
-            n_rhs += 3;
+            n_rhs += first ? 4 : 3;
             DREX_MARK(3)  // phase 1 (warp 0's own chunks)
             // the new state was written through the generic proxy and is read by TMA (async
             // proxy) in the next step
@@ -714,10 +759,27 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                     const int64_t g = ((int64_t)warp + j * INT_WARPS) * 32 + lane;
                     const bool ok = g < N;
                     fr[j] = ok ? f_cur[g] : 0.0;
-                    k1[j] = ok ? kf_cur[g] : 0.0;
+                    k1[j] = ok ? (first ? E1[g] : kf_cur[g]) : 0.0;  // first step: energy at t0 for now
                     e4[j] = ok ? E4[g] : 0.0;
                 }
                 double sc_ = 0.0, se_ = 0.0;
+                if (first) {
+                    // initial slope of the fractions (core.py:431-436 at t0), which the separate
+                    // initial pass computes otherwise
+#pragma unroll
+                    for (int j = 0; j < MAXQ; ++j) {
+                        const double xc = fmax(fr[j], 0.0);
+                        sc_ += xc;
+                        se_ += xc * k1[j];
+                    }
+                    block_sum2<INT_BLOCK>(sc_, se_, sh.red);
+                    sum_clip = sc_;
+                    const double mean0 = se_ / sc_, ps0 = sh.st[3].s * gbm_scale / sc_;
+#pragma unroll
+                    for (int j = 0; j < MAXQ; ++j) k1[j] = (ps0 * fmax(fr[j], 0.0)) * (mean0 - k1[j]);
+                    sc_ = 0.0;
+                    se_ = 0.0;
+                }
 #pragma unroll
                 for (int j = 0; j < MAXQ; ++j) {  // stage 2 state
                     const int64_t g = ((int64_t)warp + j * INT_WARPS) * 32 + lane;
@@ -913,7 +975,7 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
         double *o_out = A.o_out + s * 9 * N;
         double *f_out = A.f_out + s * N;
         const double floor_v = A.gbs_threshold / (double)N;
-        const double s1 = sum_clip;  // sum of max(f, 0), carried from the last accepted step
+        double s1 = sum_clip;  // sum of max(f, 0), carried from the last accepted step
         if (fast) {
             double fa[MAXQ];
             uint32_t slide_mask = 0;
@@ -922,6 +984,15 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
             for (int j = 0; j < MAXQ; ++j) {
                 const int64_t g = ((int64_t)warp + j * INT_WARPS) * 32 + lane;
                 fa[j] = (g < N) ? f_cur[g] : 0.0;
+            }
+            if (fused && (!f_active || n_acc == 0)) {
+                // no fraction stage has summed the (unchanged) fractions yet
+                double sc_ = 0.0;
+#pragma unroll
+                for (int j = 0; j < MAXQ; ++j) sc_ += fmax(fa[j], 0.0);
+                block_sum2<INT_BLOCK>(sc_, dummy, sh.red);
+                s1 = sc_;
+                dummy = 0.0;
             }
 #pragma unroll
             for (int j = 0; j < MAXQ; ++j) {
@@ -933,6 +1004,8 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                 fa[j] = (g < N) ? v : 0.0;
                 s2 += fa[j];
             }
+            // no accepted step with the fused first step: the state is still o_in for every grain
+            if (fused && n_acc == 0) slide_mask = 0xffffffffu;
             block_sum2<INT_BLOCK>(s2, dummy, sh.red);
             double s3 = 0.0;
             dummy = 0.0;
