@@ -212,7 +212,7 @@ __device__ inline double eval_L_component(const IntegrateArgs &A, const double *
 // normalise.  This is serial work every other warp of the CTA waits for at a barrier, so
 // it is spread over the lanes instead of being looped by one thread.
 struct StageFlow;
-__device__ inline void warp_stage_flows(const IntegrateArgs &A, const double *table, StageFlow *st,
+__device__ __noinline__ void warp_stage_flows(const IntegrateArgs &A, const double *table, StageFlow *st,
                                         int first, int n, double t0s, double t1s, double t2s,
                                         double ta, double tb, const double *xnode, int lane);
 
@@ -270,24 +270,83 @@ __device__ __forceinline__ double plan_step(double h_prop, double remaining) {
 #define BS_E3 (1.0 / 9.0)
 #define BS_E4 (-1.0 / 8.0)
 
-__device__ inline void warp_stage_flows(const IntegrateArgs &A, const double *table, StageFlow *st,
+// strain_rate_max (drex_common.cuh) with the divisions and the square root of the serial path
+// replaced by the ~1 ulp fast versions of drex_math.cuh: this runs on one lane per stage time
+// while the rest of the CTA waits.
+__device__ inline double strain_rate_max_fast(const double *L) {
+    const double d00 = L[0], d11 = L[4], d22 = L[8];
+    const double d01 = 0.5 * (L[1] + L[3]), d02 = 0.5 * (L[2] + L[6]), d12 = 0.5 * (L[5] + L[7]);
+    const double p1 = d01 * d01 + d02 * d02 + d12 * d12;
+    const double q = (d00 + d11 + d22) * (1.0 / 3.0);
+    const double b00 = d00 - q, b11 = d11 - q, b22 = d22 - q;
+    const double p2 = b00 * b00 + b11 * b11 + b22 * b22 + 2.0 * p1;
+    const double p = sqrt_fast(p2 * (1.0 / 6.0));
+    if (!(p > 0.0)) return fabs(q);  // multiple of the identity (or NaN, which propagates)
+    const double ip = div_fast(1.0, p);
+    const double c00 = b00 * ip, c11 = b11 * ip, c22 = b22 * ip;
+    const double c01 = d01 * ip, c02 = d02 * ip, c12 = d12 * ip;
+    double r = 0.5 * (c00 * (c11 * c22 - c12 * c12) - c01 * (c01 * c22 - c12 * c02) +
+                      c02 * (c01 * c12 - c11 * c02));
+    r = fmin(1.0, fmax(-1.0, r));
+    const double cphi = cos(acos(r) * (1.0 / 3.0));  // phi in [0, pi/3]
+    const double sphi = sqrt_fast(fmax(0.0, 1.0 - cphi * cphi));
+    const double e_hi = q + 2.0 * p * cphi;
+    const double e_lo = q - p * (cphi + 1.7320508075688772935 * sphi);
+    return fmax(fabs(e_hi), fabs(e_lo));
+}
+
+__device__ __noinline__ void warp_stage_flows(const IntegrateArgs &A, const double *table, StageFlow *st,
                                         int first, int n, double t0s, double t1s, double t2s,
                                         double ta, double tb, const double *xnode, int lane) {
     const int si = lane / 9, c = lane - 9 * si;
     const bool active = lane < 9 * n;
-    if (active) {
-        const double t = (si == 0) ? t0s : ((si == 1) ? t1s : t2s);
+    const double t = (si == 0) ? t0s : ((si == 1) ? t1s : t2s);
+    if (A.L_kind == 2 && A.K > 1 && A.K <= 9) {
+        // Chebyshev table with at most nine nodes: the barycentric weights of the n stage times
+        // are formed by 9 n lanes in parallel (one reciprocal each) and handed round by
+        // shuffles, instead of every lane walking all nodes on its own (3300 -> ~700 cycles of
+        // the serial section).  Same operations in the same order per component as
+        // eval_L_component: bit-identical.
+        const int K = A.K;
+        const double span = tb - ta;
+        const double x = (span != 0.0) ? (t - ta) / span : 0.0;
+        double w = 0.0;
+        bool here = false;
+        if (active && c < K) {
+            double d = x - xnode[c];
+            here = fabs(d) < 1e-15;
+            d = here ? 1.0 : d;
+            double r;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+            r = fma(r, fma(-d, r, 1.0), r);
+            r = fma(r, fma(-d, r, 1.0), r);
+            w = (c & 1) ? -r : r;
+            if (c == 0 || c == K - 1) w *= 0.5;
+        }
+        const unsigned hits = __ballot_sync(0xffffffffu, here);
+        const int base = active ? 9 * si : 0;
+        double numer = 0.0, denom = 0.0;
+        for (int j = 0; j < K; ++j) {
+            const double wj = __shfl_sync(0xffffffffu, w, base + j);
+            denom += wj;
+            if (active) numer = fma(wj, table[j * 9 + c], numer);
+        }
+        if (active) {
+            const unsigned mine = (hits >> (9 * si)) & 0x1ffu;  // nodes this stage time sits on
+            st[first + si].Lraw[c] = mine ? table[(__ffs(mine) - 1) * 9 + c] : numer / denom;
+        }
+    } else if (active) {
         st[first + si].Lraw[c] = eval_L_component(A, table, t, ta, tb, c, xnode);
     }
     __syncwarp();
-    if (lane < n) st[first + lane].s = strain_rate_max(st[first + lane].Lraw);
+    if (lane < n) st[first + lane].s = strain_rate_max_fast(st[first + lane].Lraw);
     __syncwarp();
     if (active) {
         StageFlow &sf = st[first + si];
         const int ct = 3 * (c % 3) + c / 3;  // transposed component
         const double l = sf.Lraw[c], lt = sf.Lraw[ct], sc = sf.s;
-        sf.DL[c] = make_double2((0.5 * (l + lt)) / sc,  // minerals.py:421,438
-                                l / sc);                // minerals.py:439
+        sf.DL[c] = make_double2(div_fast(0.5 * (l + lt), sc),  // minerals.py:421,438
+                                div_fast(l, sc));              // minerals.py:439
     }
     __syncwarp();
 }
