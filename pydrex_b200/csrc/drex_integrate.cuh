@@ -656,13 +656,14 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
             // until a step has been accepted the state is still o_in: fused first step
             const bool first = fused && n_acc == 0;
             auto issue_first = [&](int64_t q) {
-                // the nine 256 B rows of o_in for chunk q into rows 0-8
-                if (lane == 0) {
-                    const int64_t g0 = q * 32;
-                    const uint32_t row_bytes = (uint32_t)(((N - g0 < 32) ? (N - g0) : 32) * sizeof(double));
-                    mbar_expect_tx(mbar, 9 * row_bytes);
-                    for (int c = 0; c < 9; ++c) bulk_g2s(stage + c * 32, o_in + c * N + g0, row_bytes, mbar);
-                }
+                // the nine 256 B rows of o_in for chunk q into rows 0-8: one copy per lane, issued
+                // by nine lanes at once (nine copies in a row from one lane showed up as the
+                // top stall of the kernel)
+                const int64_t g0 = q * 32;
+                const uint32_t row_bytes = (uint32_t)(((N - g0 < 32) ? (N - g0) : 32) * sizeof(double));
+                if (lane == 0) mbar_expect_tx(mbar, 9 * row_bytes);
+                __syncwarp();
+                if (lane < 9) bulk_g2s(stage + lane * 32, o_in + lane * N + g0, row_bytes, mbar);
             };
             // prefetch this warp's first chunk while the stage flows are being set up
             if (warp < n_chunks) {
@@ -1089,15 +1090,14 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
             const bool rows_aligned = ((N & 1) == 0) && ((reinterpret_cast<uintptr_t>(o_in) & 15) == 0);
             if (rows_aligned) {
                 auto issue_end = [&](int64_t q, int half) {
-                    if (lane == 0) {
-                        const int64_t g0 = q * 32;
-                        const uint32_t row_bytes = (uint32_t)(((N - g0 < 32) ? (N - g0) : 32) * sizeof(double));
-                        uint64_t *bar = half ? &sh.mbar2[warp] : mbar;
-                        double *dst = stage + half * 18 * 32;
-                        mbar_expect_tx(bar, (uint32_t)(9 * 32 * sizeof(double)) + 9 * row_bytes);
-                        bulk_g2s(dst, yk_cur + q * CHUNK_DOUBLES, (uint32_t)(9 * 32 * sizeof(double)), bar);
-                        for (int c = 0; c < 9; ++c) bulk_g2s(dst + (9 + c) * 32, o_in + c * N + g0, row_bytes, bar);
-                    }
+                    const int64_t g0 = q * 32;
+                    const uint32_t row_bytes = (uint32_t)(((N - g0 < 32) ? (N - g0) : 32) * sizeof(double));
+                    uint64_t *bar = half ? &sh.mbar2[warp] : mbar;
+                    double *dst = stage + half * 18 * 32;
+                    if (lane == 0) mbar_expect_tx(bar, (uint32_t)(9 * 32 * sizeof(double)) + 9 * row_bytes);
+                    __syncwarp();
+                    if (lane < 9) bulk_g2s(dst + (9 + lane) * 32, o_in + lane * N + g0, row_bytes, bar);
+                    if (lane == 9) bulk_g2s(dst, yk_cur + q * CHUNK_DOUBLES, (uint32_t)(9 * 32 * sizeof(double)), bar);
                 };
                 if (warp < n_chunks) issue_end(warp, 0);
                 if (warp + INT_WARPS < n_chunks) issue_end(warp + INT_WARPS, 1);
