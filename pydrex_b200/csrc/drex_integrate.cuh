@@ -1089,18 +1089,23 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
             // of the warp's stage; no registers are tied up by loads in flight.
             const bool rows_aligned = ((N & 1) == 0) && ((reinterpret_cast<uintptr_t>(o_in) & 15) == 0);
             if (rows_aligned) {
-                auto issue_end = [&](int64_t q, int half) {
+                // jj: index of the chunk among this warp's chunks (bit of slide_mask).  The o_in rows
+                // are fetched only for chunks in which some grain slides: enstatite never does
+                // (its fractions stay 1/N), olivine not before the texture has evolved.
+                auto issue_end = [&](int64_t q, int half, int jj) {
                     const int64_t g0 = q * 32;
                     const uint32_t row_bytes = (uint32_t)(((N - g0 < 32) ? (N - g0) : 32) * sizeof(double));
                     uint64_t *bar = half ? &sh.mbar2[warp] : mbar;
                     double *dst = stage + half * 18 * 32;
-                    if (lane == 0) mbar_expect_tx(bar, (uint32_t)(9 * 32 * sizeof(double)) + 9 * row_bytes);
+                    const bool need = __any_sync(0xffffffffu, ((slide_mask >> jj) & 1u) != 0);
+                    if (lane == 0)
+                        mbar_expect_tx(bar, (uint32_t)(9 * 32 * sizeof(double)) + (need ? 9 * row_bytes : 0u));
                     __syncwarp();
-                    if (lane < 9) bulk_g2s(dst + (9 + lane) * 32, o_in + lane * N + g0, row_bytes, bar);
+                    if (need && lane < 9) bulk_g2s(dst + (9 + lane) * 32, o_in + lane * N + g0, row_bytes, bar);
                     if (lane == 9) bulk_g2s(dst, yk_cur + q * CHUNK_DOUBLES, (uint32_t)(9 * 32 * sizeof(double)), bar);
                 };
-                if (warp < n_chunks) issue_end(warp, 0);
-                if (warp + INT_WARPS < n_chunks) issue_end(warp + INT_WARPS, 1);
+                if (warp < n_chunks) issue_end(warp, 0, 0);
+                if (warp + INT_WARPS < n_chunks) issue_end(warp + INT_WARPS, 1, 1);
                 int j = 0;
                 for (int64_t q = warp; q < n_chunks; q += INT_WARPS, ++j) {
                     const int64_t g = q * 32 + lane;
@@ -1122,7 +1127,7 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
                     // proxy fence orders them
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
-                    if (q + 2 * INT_WARPS < n_chunks) issue_end(q + 2 * INT_WARPS, half);
+                    if (q + 2 * INT_WARPS < n_chunks) issue_end(q + 2 * INT_WARPS, half, j + 2);
                     if (g < N) {
 #pragma unroll
                         for (int c = 0; c < 9; ++c) o_out[c * N + g] = a[c];
