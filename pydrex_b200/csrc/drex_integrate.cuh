@@ -805,7 +805,7 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
             DREX_MARK(3)  // phase 1 (warp 0's own chunks)
             // the new state was written through the generic proxy and is read by TMA (async
             // proxy) in the next step
-            asm volatile("fence.proxy.async;" ::: "memory");
+            asm volatile("fence.proxy.async.global;" ::: "memory");
             double emax = (racc < INFINITY) ? (double)emax_f : INFINITY;
             double sum_clip_new = sum_clip;
 
