@@ -253,6 +253,25 @@ ORACLE_API int oracle_rotation_and_strain(int phase, int fabric, const double *a
     return 0;
 }
 
+/* core._get_rotation_and_strain (core.py:687-760) for G grains, each with ITS OWN flow:
+ * Ls[g] = L / strain_rate_max of grain g (D is formed here as its symmetric part,
+ * minerals.py:421,438-439).  Used by oracle/device_model.py, where chunks of grains of one
+ * system sit at different times of the interval. */
+ORACLE_API int oracle_grain_batch(int phase, int fabric, int64_t G, const double *o,
+                                  const double *Ls, double p, double n, double lambda,
+                                  double *da, double *energy) {
+    for (int64_t g = 0; g < G; ++g) {
+        const double *L = Ls + 9 * g;
+        double D[9];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) D[3 * i + j] = 0.5 * (L[3 * i + j] + L[3 * j + i]);
+        int rc = oracle_rotation_and_strain(phase, fabric, o + 9 * g, D, L, p, n, lambda,
+                                            da + 9 * g, energy + g, NULL, NULL, NULL, NULL);
+        if (rc != 0) return -1;
+    }
+    return 0;
+}
+
 /* core.py:347-474.  Returns 0; -1 bad phase/fabric; -2 unsupported regime; -3 bad regime. */
 ORACLE_API int oracle_derivatives(int regime, int phase, int fabric, int64_t n_grains,
                                   const double *o, const double *f, const double *D,

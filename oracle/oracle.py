@@ -65,6 +65,9 @@ def lib():
             [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64]
             + [_dp] * 5 + [ctypes.c_double] * 5 + [_dp, _dp]
         )
+        L.oracle_grain_batch.argtypes = (
+            [ctypes.c_int, ctypes.c_int, ctypes.c_int64, _dp, _dp] + [ctypes.c_double] * 3 + [_dp, _dp]
+        )
         L.oracle_extract_vars.argtypes = [_dp, ctypes.c_int64, _dp, _dp, _dp]
         L.oracle_apply_gbs.argtypes = [_dp, _dp, ctypes.c_double, _dp, ctypes.c_int64]
         L.oracle_eval_rhs.argtypes = (
