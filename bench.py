@@ -330,10 +330,15 @@ def run_gpu(args):
     # the warm-up runs exactly what a timed step runs, counter bookkeeping included: CUDA loads
     # kernels lazily, and the first use of torch's small reduction kernel costs ~8 ms of host
     # time that would otherwise land inside the first timed step
-    counters = torch.zeros((3,), dtype=torch.int64, device=dev)
+    counters = torch.zeros((4,), dtype=torch.int64, device=dev)
+
+    def count():  # grain right-hand sides; chunk-summed n_rhs, n_accept, n_reject (torch, tiny)
+        counters[0] += ens.grain_evals.sum()
+        counters[1:] += ens.stats[1:4].sum(dim=1)
+
     for k in range(W):
         ens.update(t_lo[k], t_hi[k], L_dev[k], kind, tol, check=False)
-        counters += ens.stats[1:4].sum(dim=1)
+        count()
     counters.zero_()
     step_ms = []
     barrier()
@@ -342,7 +347,7 @@ def run_gpu(args):
     ev[0].record()
     for k in range(W, n_total):
         ens.update(t_lo[k], t_hi[k], L_dev[k], kind, tol, check=False)
-        counters += ens.stats[1:4].sum(dim=1)  # n_rhs, n_accept, n_reject (torch, tiny)
+        count()
         ev[k - W + 1].record()
     barrier()
     sampler.mark_end()
@@ -350,9 +355,9 @@ def run_gpu(args):
     total_ms = max_over_ranks(ev[0].elapsed_time(ev[K]))
     step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(K)]
     status_bad = int((ens.stats[0] != 0).sum().item())
-    n_rhs, n_acc, n_rej = (int(c) for c in counters.cpu())
-    evals = sum_over_ranks(n_rhs * N)
-    internal = sum_over_ranks(n_acc * N)
+    g_evals, n_rhs, n_acc, n_rej = (int(c) for c in counters.cpu())
+    evals = sum_over_ranks(g_evals)
+    internal = sum_over_ranks(n_acc * N / ens.n_chunks)  # steps are per chunk of 32 grains
     outer = float(world * S * N * K)
     secs = total_ms * 1e-3
     value = outer / secs
@@ -360,7 +365,7 @@ def run_gpu(args):
     # kernel-only duration: the integrator launch is the whole step on the stream, so the
     # per-step CUDA-event time IS the kernel's launch duration (plus a 256 B memset)
     kernel_ms = float(np.mean(step_ms))
-    evals_per_launch = n_rhs * N / K
+    evals_per_launch = g_evals / K
     fp64_peak = None
     if rank == 0:
         import ctypes
@@ -392,9 +397,7 @@ def run_gpu(args):
     # bytes the integrator moves per grain per attempted step (csrc/drex_integrate.cuh):
     # orientation + FSAL slope in, both out (4 x 72 B), 3 stage energies, 10 fraction-stage
     # doubles for olivine; enstatite skips the fraction stages.  Averaged over both phases.
-    bytes_per_attempt = 288.0 + 0.5 * (24.0 + 10 * 8.0 * 2)
-    attempts = (n_acc + n_rej) * N / K
-    hbm_gbs = bytes_per_attempt * attempts / (kernel_ms * 1e-3) / 1e9
+    hbm_gbs = 160.0 * S * N / (kernel_ms * 1e-3) / 1e9
     # DRAM traffic of the integrator from the committed ncu capture (profiles/), scaled by
     # right-hand sides per launch: the capture's launch and this run's launches differ only
     # in how many evaluations the step-size control needed
@@ -424,7 +427,7 @@ def run_gpu(args):
         },
         "grain_evals_per_s": evals / secs,
         "grain_internal_steps_per_s": internal / secs,
-        "rhs_per_outer_step": n_rhs / (S * K), "rejected_steps": n_rej,
+        "rhs_per_outer_step": g_evals / (S * N * K), "rejected_chunk_steps": n_rej,
         "failed_systems": status_bad,
         "gpu_launches": K,
         "e2e": e2e,

@@ -32,7 +32,7 @@ extern "C" {
 #endif
 
 #define DREX_VERSION_MAJOR 0
-#define DREX_VERSION_MINOR 1
+#define DREX_VERSION_MINOR 2
 
 /* error codes */
 #define DREX_OK 0
@@ -153,53 +153,74 @@ int drex_grain_helper_f64(int op, const double *in0, const double *in1, const do
 typedef struct drex_tolerances {
     /* error weight of component i: atol_abs + (atol_rel + rtol) * |y_new_i|;
      * reference default (minerals.py:523-524): rtol 1e-6, atol 1e-4 + 1e-6 |y0_i|;
-     * weighted MAX norm as in ODEPACK lsoda */
+     * weighted MAX norm as in ODEPACK lsoda, taken per chunk of 32 grains (see below) */
     double rtol;
-    double atol_abs;
+    double atol_abs;        /* orientation components */
     double atol_rel;
+    double atol_abs_F;      /* the nine deformation-gradient components (LSODA takes one atol per
+                               component, minerals.py:523; the blocks of y may differ) */
+    double atol_abs_f;      /* the N volume fractions */
     double first_step_frac; /* first trial step = frac * |t1 - t0| when h_io is NULL or <= 0;
                                0 selects the whole interval */
     double max_step_frac;   /* cap on the step as a fraction of |t1 - t0| (<= 0: none) */
-    int32_t max_steps;      /* attempted steps per system before DREX_STATUS_MAX_STEPS */
-    int32_t method;         /* low byte 0: Bogacki-Shampine 3(2) with FSAL.  Kernel choice (testing
-                               aid; default: one CTA per system): 0x200 forces the one-system kernel,
-                               0x100 the same with the through-memory fraction stages it uses for
-                               N > 5120, 0x400 the two-slot pipelined kernel; 0x800 runs the initial slope as a
-                               separate pass instead of fusing it into the first step.  The environment
-                               variable DREX_INTEGRATOR=pipe|single overrides the default */
+    int32_t max_steps;      /* attempted steps per chunk before DREX_STATUS_MAX_STEPS */
+    int32_t method;         /* 0: Bogacki-Shampine 3(2) with FSAL (the only method) */
 } drex_tolerances_t;
 
-size_t drex_integrate_workspace_bytes(int64_t S, int64_t N, int device);
+/* Workspace of drex_integrate_f64.  in_place != 0: the call may be made with o_out == o_in
+ * (the library then keeps a copy of the interval-start orientations in the workspace, which
+ * grain-boundary sliding needs: S * 9 * N doubles more). */
+size_t drex_integrate_workspace_bytes(int64_t S, int64_t N, int device, int in_place);
 
-/* Advance S systems from t0 to t1 (per particle) with per-system adaptive steps, then
- * apply grain-boundary sliding once against the interval-start orientations
- * (minerals.py:464-474, utils.apply_gbs utils.py:159-180) and the final clip/renormalise
- * (utils.extract_vars utils.py:183-190).
+/* Advance S systems from t0 to t1 (per particle), then apply grain-boundary sliding once
+ * against the interval-start orientations (minerals.py:464-474, utils.apply_gbs
+ * utils.py:159-180) and the final clip/renormalise (utils.extract_vars utils.py:183-190).
+ *
+ * The ODE of minerals.py:388-453 is solved in its decoupled form: the volume fractions follow
+ * a replicator equation, f_g(t) ~ f_g(t0) exp(v_g(t)) with dv_g/dt = -s vf M* E_g, so every
+ * grain is integrated on its own (nine direction cosines and v_g) and one normalisation at t1
+ * recovers the fractions.  Grains are stepped in chunks of 32 (chunk q = grains 32 q ... 32 q +
+ * 31), each chunk with its own adaptive steps under the weighted max norm of its components;
+ * the deformation gradient is integrated separately with the same tolerances.
  *
  * sys_particle [S]  index into the per-particle arrays t0/t1/L_nodes
  * sys_phase/sys_fabric/sys_regime [S]  int32; *_host copies are validated before launch
  * sys_vol_frac [S]  phase volume fraction (minerals.py:412-415)
  * F [S][9]          deformation gradient, in/out (each phase integrates it, minerals.py:426)
- * o_in/f_in         state at t0; o_out/f_out state at t1 (may alias the inputs)
+ * o_in/f_in         state at t0; o_out/f_out state at t1.  f_out may alias f_in; o_out may
+ *                   alias o_in if the workspace was sized with in_place != 0 (costs one
+ *                   device-to-device copy of the orientations per call)
+ * o_prev            orientations that grain-boundary sliding restores (utils.py:170); NULL:
+ *                   o_in.  Differs from o_in when a caller splits one reference interval into
+ *                   several calls (a deformation regime that changes inside it): the inner
+ *                   calls run with gbs_threshold = 0, the last one with o_prev = the
+ *                   orientations at the start of the whole interval.  Must not alias o_out.
  * L_kind, K, L_nodes [P][K][9]  velocity-gradient provider (DREX_L_*)
- * h_io [S]          in: first trial step (<= 0: use first_step_frac); out: next suggested
- *                   step; may be NULL
+ * h_io [S][ceil(N/32)]  per chunk, in: first trial step (<= 0: use first_step_frac); out: next
+ *                   suggested step; may be NULL
  * order [S]         optional (may be NULL) permutation of 0..S-1: the order in which the
  *                   persistent CTAs pull systems from the work queue.  Results do not
  *                   depend on it; putting expensive systems first (longest-processing-
  *                   time-first) shortens the tail of the launch.
- * status, n_rhs, n_accept, n_reject  int32 [S] outputs (n_* may be NULL)
+ * status [S]        int32 output: the worst DREX_STATUS_* over the system's chunks and its
+ *                   deformation gradient
+ * n_rhs, n_accept, n_reject [S]  int32 outputs (may be NULL): right-hand-side evaluations,
+ *                   accepted and rejected steps SUMMED OVER THE SYSTEM'S CHUNKS
+ * grain_evals [S]   int64 output (may be NULL): per-grain right-hand sides actually evaluated,
+ *                   i.e. sum over chunks of (evaluations x grains in the chunk)
  */
 int drex_integrate_f64(int64_t S, int64_t P, int64_t N, const int32_t *sys_particle,
                        const int32_t *sys_phase, const int32_t *sys_fabric,
                        const int32_t *sys_regime, const double *sys_vol_frac,
                        const int32_t *sys_phase_host, const int32_t *sys_fabric_host,
                        const int32_t *sys_regime_host, double *F, const double *o_in,
-                       const double *f_in, double *o_out, double *f_out, const double *t0,
-                       const double *t1, int L_kind, int K, const double *L_nodes,
-                       const drex_params_t *params, const drex_tolerances_t *tol, double *h_io,
-                       const int32_t *order, int32_t *status, int32_t *n_rhs, int32_t *n_accept,
-                       int32_t *n_reject, void *workspace, size_t workspace_bytes, void *stream);
+                       const double *f_in, const double *o_prev, double *o_out, double *f_out,
+                       const double *t0, const double *t1, int L_kind, int K,
+                       const double *L_nodes, const drex_params_t *params,
+                       const drex_tolerances_t *tol, double *h_io, const int32_t *order,
+                       int32_t *status, int32_t *n_rhs, int32_t *n_accept, int32_t *n_reject,
+                       int64_t *grain_evals, void *workspace, size_t workspace_bytes,
+                       void *stream);
 
 /* ---- minerals.voigt_averages (minerals.py:688-740) -------------------------------- */
 
@@ -349,7 +370,7 @@ int drex_fp64_peak_probe(int device, double *flops_host);
 
 /* Compute-only ceiling of the per-grain physics: olivine right-hand sides per second when
  * every thread re-evaluates register-resident data at the integrator's occupancy (512
- * threads per SM): what the integrator's grain stages could reach with nothing else in the
+ * threads per SM): what the integrator's stage loop could reach with nothing else in the
  * way.  Measurement aid like drex_fp64_peak_probe. */
 int drex_grain_rhs_ceiling_probe(int device, double *evals_per_s_host);
 

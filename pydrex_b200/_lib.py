@@ -83,6 +83,8 @@ class DrexTolerances(ctypes.Structure):
         ("rtol", ctypes.c_double),
         ("atol_abs", ctypes.c_double),
         ("atol_rel", ctypes.c_double),
+        ("atol_abs_F", ctypes.c_double),
+        ("atol_abs_f", ctypes.c_double),
         ("first_step_frac", ctypes.c_double),
         ("max_step_frac", ctypes.c_double),
         ("max_steps", ctypes.c_int32),
@@ -157,10 +159,10 @@ def _declare(lib):
     )
     lib.drex_grain_helper_f64.argtypes = [i32, vp, vp, vp, vp, dbl, dbl, dbl, dbl, vp, vp]
     lib.drex_integrate_workspace_bytes.restype = szt
-    lib.drex_integrate_workspace_bytes.argtypes = [i64, i64, i32]
+    lib.drex_integrate_workspace_bytes.argtypes = [i64, i64, i32, i32]
     lib.drex_integrate_f64.argtypes = (
-        [i64, i64, i64] + [vp] * 5 + [vp] * 3 + [vp] * 5 + [vp, vp, i32, i32, vp]
-        + [c.POINTER(DrexParams), c.POINTER(DrexTolerances)] + [vp] * 6 + [vp, szt, vp]
+        [i64, i64, i64] + [vp] * 5 + [vp] * 3 + [vp] * 6 + [vp, vp, i32, i32, vp]
+        + [c.POINTER(DrexParams), c.POINTER(DrexTolerances)] + [vp] * 7 + [vp, szt, vp]
     )
     lib.drex_voigt_average_f64.argtypes = [vp, vp, vp, vp, i64, i64, vp, i32, vp]
     lib.drex_elasticity_components_f64.argtypes = [vp, i64, vp, vp]

@@ -16,7 +16,6 @@
 #include "drex_derivatives.cuh"
 #include "drex_diagnostics.cuh"
 #include "drex_integrate.cuh"
-#include "drex_integrate_pipe.cuh"
 #include "drex_pathlines.cuh"
 #include "drex_resample.cuh"
 
@@ -107,28 +106,15 @@ int integrate_slots(int device) {
     return sms * drex::INT_CTAS_PER_SM;
 }
 
-// Dynamic shared memory of the integrator: the per-warp TMA stages plus as many of the four
-// fraction-stage arrays as fit under the opt-in limit.
-size_t integrate_smem_bytes(int device, int64_t N, int *smem_arrays) {
-    int optin = 0;
-    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-    if (drex::INT_CTAS_PER_SM > 1) optin = (optin + 1024) / drex::INT_CTAS_PER_SM - 1024;  // 1 KB reserved per CTA
-    const size_t stage_bytes = (size_t)drex::INT_WARPS * drex::STAGE_DOUBLES * sizeof(double);
-    const size_t static_bytes = sizeof(drex::StepShared) + drex::MATH_TABLE_DOUBLES * sizeof(double) + 256;
-    const size_t array_bytes = (size_t)((N + 31) / 32 * 32) * sizeof(double);
-    size_t avail = (size_t)optin > stage_bytes + static_bytes ? (size_t)optin - stage_bytes - static_bytes : 0;
-    int n = (int)(avail / array_bytes);
-    if (n > 4) n = 4;
-    if (n < 0) n = 0;
-    *smem_arrays = n;
-    return stage_bytes + (size_t)n * array_bytes;
+// Dynamic shared memory of the integrator: the per-warp state / prefetch rows and stage flows.
+inline size_t integrate_smem_bytes() {
+    return (size_t)drex::INT_WARPS * (drex::WARP_DOUBLES * sizeof(double) + 4 * sizeof(drex::ChunkFlow));
 }
 
-inline size_t integrate_slot_bytes(int64_t N) {
-    return align_up((size_t)drex::SLOT_ARRAYS * (size_t)((N + 31) / 32 * 32) * sizeof(double), 256);
-}
-inline size_t pipe_slot_bytes(int64_t N) {
-    return align_up((size_t)drex::PS_ARRAYS * (size_t)((N + 31) / 32 * 32) * sizeof(double), 256);
+// Per-CTA scratch: the per-chunk partial sums of the systems in flight.
+inline int64_t integrate_chunk_cap(int64_t N) { return ((N + 31) / 32 + 31) / 32 * 32; }
+inline size_t integrate_scratch_bytes(int slots, int64_t N) {
+    return align_up((size_t)slots * drex::INT_NCTX * (size_t)integrate_chunk_cap(N) * sizeof(double), 256);
 }
 
 }  // namespace
@@ -277,13 +263,16 @@ int drex_grain_helper_f64(int op, const double *in0, const double *in1, const do
     return DREX_OK;
 }
 
-size_t drex_integrate_workspace_bytes(int64_t S, int64_t N, int device) {
+size_t drex_integrate_workspace_bytes(int64_t S, int64_t N, int device, int in_place) {
     if (S <= 0 || N <= 0) return 256;
     int slots = integrate_slots(device);
     if (slots < 1) slots = 1;
     if ((int64_t)slots > S) slots = (int)S;
-    // either kernel may run (drex_integrate_f64 chooses): the two-slot pipeline needs the most
-    return 256 + (size_t)slots * 2 * pipe_slot_bytes(N);
+    size_t need = 256 + integrate_scratch_bytes(slots, N);
+    // o_out == o_in: grain-boundary sliding restores interval-start orientations that the
+    // integration has already overwritten, so the call keeps a copy of them here
+    if (in_place) need += (size_t)S * 9 * (size_t)N * sizeof(double);
+    return need;
 }
 
 int drex_integrate_f64(int64_t S, int64_t P, int64_t N, const int32_t *sys_particle,
@@ -291,12 +280,13 @@ int drex_integrate_f64(int64_t S, int64_t P, int64_t N, const int32_t *sys_parti
                        const int32_t *sys_regime, const double *sys_vol_frac,
                        const int32_t *sys_phase_host, const int32_t *sys_fabric_host,
                        const int32_t *sys_regime_host, double *F, const double *o_in,
-                       const double *f_in, double *o_out, double *f_out, const double *t0,
-                       const double *t1, int L_kind, int K, const double *L_nodes,
-                       const drex_params_t *params, const drex_tolerances_t *tol, double *h_io,
-                       const int32_t *order,
+                       const double *f_in, const double *o_prev, double *o_out, double *f_out,
+                       const double *t0, const double *t1, int L_kind, int K,
+                       const double *L_nodes, const drex_params_t *params,
+                       const drex_tolerances_t *tol, double *h_io, const int32_t *order,
                        int32_t *status, int32_t *n_rhs, int32_t *n_accept, int32_t *n_reject,
-                       void *workspace, size_t workspace_bytes, void *stream) {
+                       int64_t *grain_evals, void *workspace, size_t workspace_bytes,
+                       void *stream) {
     if (S < 0 || P < 0 || N < 0) return fail(DREX_E_INVALID, "negative size");
     if (!params || !tol || !sys_phase_host || !sys_fabric_host || !sys_regime_host)
         return fail(DREX_E_INVALID, "drex_integrate_f64: null host argument");
@@ -306,9 +296,10 @@ int drex_integrate_f64(int64_t S, int64_t P, int64_t N, const int32_t *sys_parti
     if (K < 1 || (L_kind != DREX_L_CONSTANT && K < 2) || (L_kind == DREX_L_LINEAR && K != 2))
         return fail(DREX_E_INVALID, "L_kind %d needs a different node count than K = %d", L_kind, K);
     if (!(tol->rtol >= 0.0) || !(tol->atol_abs >= 0.0) || !(tol->atol_rel >= 0.0) ||
-        !(tol->rtol + tol->atol_abs + tol->atol_rel > 0.0))
+        !(tol->atol_abs_F >= 0.0) || !(tol->atol_abs_f >= 0.0) ||
+        !(tol->rtol + tol->atol_rel + fmin(tol->atol_abs, fmin(tol->atol_abs_F, tol->atol_abs_f)) > 0.0))
         return fail(DREX_E_INVALID, "tolerances must be non-negative and not all zero");
-    if ((tol->method & 0xff) != 0 || (tol->method & ~0xfff) != 0) return fail(DREX_E_INVALID, "unknown integration method %d", tol->method);
+    if (tol->method != 0) return fail(DREX_E_INVALID, "unknown integration method %d", tol->method);
     if (S == 0 || N == 0) return DREX_OK;
     if (!sys_particle || !sys_phase || !sys_fabric || !sys_regime || !sys_vol_frac || !F || !o_in ||
         !f_in || !o_out || !f_out || !t0 || !t1 || !L_nodes || !status)
@@ -316,23 +307,18 @@ int drex_integrate_f64(int64_t S, int64_t P, int64_t N, const int32_t *sys_parti
     int device = 0;
     DREX_CUDA_CHECK(cudaGetDevice(&device));
     int slots = integrate_slots(device);
-    if (slots < 1) return fail(DREX_E_CUDA, "could not query occupancy of the integrator kernel");
-    // Kernel choice: one CTA per system (drex_integrate.cuh) unless the two-slot pipelined
-    // kernel (drex_integrate_pipe.cuh) is asked for.  Measured at bench size the two are within
-    // a few per cent of each other, so the simpler one is the default.
-    // method bits: 0x100 one-system kernel with the through-memory fraction stages, 0x200
-    // one-system kernel, 0x400 pipelined kernel.
-    int method = tol->method;
-    if (!(method & 0x700)) {  // testing aid: DREX_INTEGRATOR=pipe|single overrides the automatic choice
-        const char *env = getenv("DREX_INTEGRATOR");
-        if (env && !strcmp(env, "pipe")) method |= 0x400;
-        if (env && !strcmp(env, "single")) method |= 0x200;
-    }
-    const bool pipe = (method & 0x400) != 0;
+    if (slots < 1) return fail(DREX_E_CUDA, "could not query the device of the integrator kernel");
     if ((int64_t)slots > S) slots = (int)S;
-    if ((method & 0x400) && (int64_t)slots * 2 > S) slots = (int)((S + 1) / 2);  // both slots in use
-    const size_t slot_bytes = pipe ? pipe_slot_bytes(N) : integrate_slot_bytes(N);
-    const size_t need = 256 + (size_t)slots * (pipe ? 2 : 1) * slot_bytes;
+    const size_t state_bytes = (size_t)S * 9 * (size_t)N * sizeof(double);
+    const char *in_lo = (const char *)o_in, *out_lo = (const char *)o_out;
+    const bool aliased = o_prev == nullptr && in_lo < out_lo + state_bytes && out_lo < in_lo + state_bytes;
+    if (o_prev != nullptr) {
+        const char *pv = (const char *)o_prev;
+        if (pv < out_lo + state_bytes && out_lo < pv + state_bytes)
+            return fail(DREX_E_INVALID, "drex_integrate_f64: o_prev must not alias o_out");
+    }
+    const size_t scratch_bytes = integrate_scratch_bytes(slots, N);
+    const size_t need = 256 + scratch_bytes + (aliased ? state_bytes : 0);
     if (!workspace || workspace_bytes < need)
         return fail(DREX_E_WORKSPACE, "drex_integrate_f64: workspace too small (%zu < %zu)",
                     workspace_bytes, need);
@@ -342,33 +328,32 @@ int drex_integrate_f64(int64_t S, int64_t P, int64_t N, const int32_t *sys_parti
     A.sys_particle = sys_particle; A.sys_phase = sys_phase; A.sys_fabric = sys_fabric;
     A.sys_regime = sys_regime; A.sys_vol_frac = sys_vol_frac;
     A.F = F; A.o_in = o_in; A.f_in = f_in; A.o_out = o_out; A.f_out = f_out;
+    A.o_prev = o_prev ? o_prev : o_in;
     A.t0 = t0; A.t1 = t1; A.L_kind = L_kind; A.K = K; A.L_nodes = L_nodes;
     A.gbm_mobility = params->gbm_mobility;
     A.gbs_threshold = params->gbs_threshold;
     A.tol.rtol = tol->rtol; A.tol.atol_abs = tol->atol_abs; A.tol.atol_rel = tol->atol_rel;
+    A.tol.atol_abs_F = tol->atol_abs_F; A.tol.atol_abs_f = tol->atol_abs_f;
     A.tol.first_step_frac = tol->first_step_frac; A.tol.max_step_frac = tol->max_step_frac;
     A.tol.max_steps = tol->max_steps > 0 ? tol->max_steps : 100000;
-    A.tol.method = method;
-    A.h_io = h_io; A.order = order; A.status = status; A.n_rhs = n_rhs; A.n_accept = n_accept; A.n_reject = n_reject;
+    A.tol.method = 0;
+    A.h_io = h_io; A.order = order; A.status = status; A.n_rhs = n_rhs; A.n_accept = n_accept;
+    A.n_reject = n_reject; A.grain_evals = grain_evals;
     A.queue = (int *)workspace;
     A.scratch = (double *)((char *)workspace + 256);
-    A.slot_doubles = (int64_t)(slot_bytes / sizeof(double));
+    A.chunk_cap = integrate_chunk_cap(N);
     DREX_CUDA_CHECK(cudaMemsetAsync(workspace, 0, 256, st));
-    const drex::FabricTable T = make_fabric_table(*params);
-    if (pipe) {
-        const size_t dyn_smem = (size_t)drex::PIPE_CW * drex::STAGE_DOUBLES * sizeof(double);
-        A.smem_arrays = 0;
-        DREX_CUDA_CHECK(cudaFuncSetAttribute(drex::integrate_pipe_kernel,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
-        drex::integrate_pipe_kernel<<<(unsigned)slots, drex::PIPE_BLOCK, dyn_smem, st>>>(A, T);
-    } else {
-        int smem_arrays = 0;
-        const size_t dyn_smem = integrate_smem_bytes(device, N, &smem_arrays);
-        A.smem_arrays = smem_arrays;
-        DREX_CUDA_CHECK(cudaFuncSetAttribute(drex::integrate_kernel,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
-        drex::integrate_kernel<<<(unsigned)slots, drex::INT_BLOCK, dyn_smem, st>>>(A, T);
+    if (aliased) {
+        double *copy = (double *)((char *)workspace + 256 + scratch_bytes);
+        DREX_CUDA_CHECK(cudaMemcpyAsync(copy, o_in, state_bytes, cudaMemcpyDeviceToDevice, st));
+        A.o_in = copy;
+        A.o_prev = copy;
     }
+    const drex::FabricTable T = make_fabric_table(*params);
+    const size_t dyn_smem = integrate_smem_bytes();
+    DREX_CUDA_CHECK(cudaFuncSetAttribute(drex::integrate_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    drex::integrate_kernel<<<(unsigned)slots, drex::INT_BLOCK, dyn_smem, st>>>(A, T);
     DREX_CUDA_CHECK(cudaGetLastError());
     return DREX_OK;
 }

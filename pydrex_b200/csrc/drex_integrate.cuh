@@ -1,4 +1,4 @@
-// drex_integrate.cuh -- batched on-device adaptive integrator for grain ensembles.
+// drex_integrate.cuh -- batched on-device adaptive integrator for grain ensembles (sm_100a).
 //
 // Replaces the scipy LSODA loop of Mineral.update_orientations
 // (src/pydrex/minerals.py:388-541): state y = [F(9) | orientations(9N) | fractions(N)],
@@ -6,32 +6,39 @@
 // norm ODEPACK lsoda uses, grain-boundary sliding once at the end of the interval
 // (minerals.py:464-474).
 //
-// Design (B200-first, not a translation of LSODA):
-//  * persistent kernel, one CTA per SM; a CTA owns one system (particle, phase) from t0 to
-//    t1 and walks its own accepted/rejected steps with no host round trip; CTAs pull
-//    systems from an atomic queue, so particles with 9 or 106 right-hand sides per
-//    interval balance themselves (per-particle step control);
-//  * Bogacki-Shampine 3(2) with FSAL: LSODA never leaves its non-stiff Adams branch on
-//    this problem, and at the reference tolerance (1e-4 absolute)
-//    a third-order pair needs the fewest right-hand sides;
-//  * the ODE splits: the rotation rate of a grain depends on that grain only (9
-//    unknowns), and only the volume fractions couple through the mean strain energy.
-//    Phase 1 therefore takes each grain through ALL THREE stages in registers with no
-//    synchronisation (one HBM/L2 round trip of the orientation per STEP, not per stage),
-//    recording the strain energy at each stage; phase 2 runs the cheap coupled fraction
-//    stages out of shared memory with four fixed-order block reductions;
-//  * each warp streams its grains in chunks of 32: the chunk's orientation and FSAL slope
-//    (18 rows x 256 B of the SoA arrays) are fetched by TMA bulk copies
-//    (cp.async.bulk -> mbarrier) into a per-warp shared-memory stage while the warp is
-//    still computing the previous chunk, so HBM latency never reaches the FP64 pipe;
-//  * FP64 throughout; clip/renormalise inside every right-hand side as
-//    utils.extract_vars does (utils.py:183-190).
+// Design (B200-first, not a translation of LSODA; the tests carry a numpy model of it):
+//  * THE ODE DECOUPLES.  The rotation rate and strain energy E_g of a grain depend on that
+//    grain and L(t) only (core.py:687-760).  The volume fractions obey the replicator equation
+//        df_g/dt = s vf M* fhat_g (Ebar - E_g),  fhat = clip(f)/sum clip(f),  Ebar = sum fhat E
+//    (core.py:431-436, minerals.py:450-451), whose exact solution is
+//        fhat_g(t) = fhat_g(t0) e^{v_g(t)} / sum_j fhat_j(t0) e^{v_j(t)},  dv_g/dt = -s vf M* E_g.
+//    So a grain carries TEN unknowns (nine direction cosines and v_g) that see no other grain
+//    until the end of the interval, where one normalisation recovers the fractions.  No
+//    reduction, no barrier and no memory round trip is left inside a step.
+//  * A WARP OWNS A CHUNK OF 32 GRAINS FROM t0 TO t1: the state lives in the warp's shared-memory
+//    rows and registers for the whole interval and every chunk walks its OWN Bogacki-Shampine
+//    3(2) steps (FSAL), controlled by the weighted max norm over its grains.  Per outer interval
+//    a grain costs 80 B of HBM reads and 80 B of writes -- whatever the number of steps.  (The
+//    first version of this kernel stepped all N grains of a system together: four block
+//    reductions and a 144 B/grain round trip per step, 41 % of its time outside the arithmetic.)
+//  * persistent CTAs (one per SM, 16 warps) pull SYSTEMS from an atomic queue (longest first);
+//    the 16 warps pull the system's chunks from a shared-memory ticket.  Up to three systems are
+//    in flight per CTA: one warp prepares the next system (flow tables, the deformation gradient)
+//    while the others still integrate chunks of the current one, and the warp that completes
+//    the last chunk of a system finishes it (normalisation, grain-boundary sliding) while the
+//    others have moved on -- the warps never meet at a barrier.
+//  * the next chunk's orientations and fractions (ten rows of 256 B) are fetched by TMA bulk
+//    copies (cp.async.bulk -> mbarrier) into the warp's prefetch rows while it integrates the
+//    current chunk.
+//  * L(t) over the interval is a polynomial (DREX_L_CHEBYSHEV): the preparing warp converts the
+//    node table to Chebyshev coefficients once, and the three stage matrices of a step cost a
+//    warp one Clenshaw recurrence on 30 lanes.
+//  * FP64 throughout; clip inside every right-hand side as utils.extract_vars does
+//    (utils.py:183-190).
 #pragma once
 #include "drex_common.cuh"
 #include "drex_derivatives.cuh"
 #include "drex_grain.cuh"
-
-#include <type_traits>
 
 namespace drex {
 
@@ -40,16 +47,19 @@ namespace drex {
 #endif
 constexpr int INT_BLOCK = DREX_INT_BLOCK;
 constexpr int INT_WARPS = INT_BLOCK / 32;
-// per-warp shared-memory stage, rows of 32 grains: 0-8 orientation and 9-17 FSAL slope (TMA
-// targets), 18-26 running new state, 27-35 running error combination.  Keeping the two
-// accumulators here instead of in registers is what lets 512 threads (4 warps per
-// scheduler) share the register file: the FP64 pipe needs that many warps to cover its
-// own dependent-issue latency.
-constexpr int STAGE_ROWS = 36;
-constexpr int STAGE_DOUBLES = STAGE_ROWS * 32;
+constexpr int INT_CTAS_PER_SM = 1;
+constexpr int INT_NCTX = 3;   // systems in flight per CTA
+constexpr int INT_KMAX = 33;  // L(t) tables up to this many nodes live in shared memory
+// per-warp shared-memory rows of 32 grains: 0-8 state, 9-17 FSAL slope, 18-26 new state, 27-35
+// error combination (the state and new-state rows swap roles on an accepted step), 36-45 the
+// prefetched next chunk (orientation rows 0-8 of o_in, row 9 of f_in; TMA target).  Keeping the
+// accumulators here instead of in registers is what lets 512 threads share the register file.
+constexpr int ROW_A = 0, ROW_K1 = 9, ROW_Y = 18, ROW_E = 27, ROW_PF = 36;
+constexpr int WARP_ROWS = 46;
+constexpr int WARP_DOUBLES = WARP_ROWS * 32;
 
 struct TolArgs {
-    double rtol, atol_abs, atol_rel, first_step_frac, max_step_frac;
+    double rtol, atol_abs, atol_rel, atol_abs_F, atol_abs_f, first_step_frac, max_step_frac;
     int max_steps, method;
 };
 
@@ -58,32 +68,22 @@ struct IntegrateArgs {
     const int32_t *sys_particle, *sys_phase, *sys_fabric, *sys_regime;
     const double *sys_vol_frac;
     double *F;
-    const double *o_in, *f_in;
+    const double *o_in, *f_in;  // o_in never aliases o_out inside the kernel (drex_capi.cu)
+    const double *o_prev;       // orientations restored by grain-boundary sliding (usually o_in)
     double *o_out, *f_out;
     const double *t0, *t1;
     int L_kind, K;
     const double *L_nodes;
     double gbm_mobility, gbs_threshold;
     TolArgs tol;
-    double *h_io;
-    const int32_t *order;  // optional queue permutation (longest systems first)
+    double *h_io;           // [S][n_chunks] first trial step in / next suggestion out, or null
+    const int32_t *order;   // optional queue permutation (longest systems first)
     int32_t *status, *n_rhs, *n_accept, *n_reject;
-    double *scratch;       // n_slots * slot_doubles
-    int64_t slot_doubles;  // per-CTA scratch size in doubles
-    int *queue;            // atomic work counter, zeroed before launch
-    int smem_arrays;       // how many of the 4 fraction-stage arrays live in shared memory
+    int64_t *grain_evals;   // optional: right-hand sides x live grains per system
+    double *scratch;        // per CTA: INT_NCTX x chunk_cap doubles (per-chunk partial sums)
+    int64_t chunk_cap;
+    int *queue;             // atomic work counter, zeroed before launch
 };
-
-// per-CTA global scratch layout, in units of Npad = 32 * ceil(N / 32) doubles.
-// YK buffers hold the running state in CHUNKED SoA: [chunk][row 0..17][32 grains], rows 0-8
-// the orientation and 9-17 its FSAL slope, so that one chunk is one contiguous 4608 B block
-// = one TMA bulk copy.
-constexpr int SLOT_YKA = 0, SLOT_YKB = 18;
-constexpr int SLOT_FA = 36, SLOT_FB = 37, SLOT_KFA = 38, SLOT_KFB = 39;
-constexpr int SLOT_P2 = 40;  // 4 fraction-stage arrays when they do not fit in shared memory
-constexpr int SLOT_E1 = 44;  // strain energies at the interval start (fused first step)
-constexpr int SLOT_ARRAYS = 45;
-constexpr int CHUNK_DOUBLES = 18 * 32;
 
 // ---- TMA bulk copy + mbarrier (sm_90+/sm_100a PTX) ------------------------------------
 __device__ __forceinline__ uint32_t smem_addr(const void *p) {
@@ -119,133 +119,19 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_global,
         : "memory");
 }
 
-// velocity gradient at time t for particle `ip` (the DREX_L_* providers)
-__device__ inline void eval_L(const IntegrateArgs &A, int64_t ip, double t, double ta, double tb,
-                              double *L) {
-    const double *nodes = A.L_nodes + ip * A.K * 9;
-    if (A.L_kind == 0 || A.K == 1) {
-        for (int c = 0; c < 9; ++c) L[c] = nodes[c];
-        return;
-    }
-    const double span = tb - ta;
-    double x = (span != 0.0) ? (t - ta) / span : 0.0;  // in [0, 1]
-    if (A.L_kind == 1) {
-        for (int c = 0; c < 9; ++c) L[c] = nodes[c] + x * (nodes[9 + c] - nodes[c]);
-        return;
-    }
-    if (A.L_kind == 3) {
-        double pos = fmin(fmax(x, 0.0), 1.0) * (A.K - 1);
-        int j = (int)pos;
-        if (j > A.K - 2) j = A.K - 2;
-        const double w = pos - j;
-        for (int c = 0; c < 9; ++c)
-            L[c] = nodes[j * 9 + c] + w * (nodes[(j + 1) * 9 + c] - nodes[j * 9 + c]);
-        return;
-    }
-    // Chebyshev-Lobatto nodes x_j = (1 - cos(pi j/(K-1)))/2 on [0, 1]; barycentric weights
-    // (-1)^j, halved at both ends.
-    double numer[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, denom = 0.0;
-    const int K = A.K;
-    for (int j = 0; j < K; ++j) {
-        const double xj = 0.5 * (1.0 - cospi((double)j / (double)(K - 1)));
-        const double d = x - xj;
-        if (fabs(d) < 1e-15) {
-            for (int c = 0; c < 9; ++c) L[c] = nodes[j * 9 + c];
-            return;
-        }
-        double w = (j & 1) ? -1.0 : 1.0;
-        if (j == 0 || j == K - 1) w *= 0.5;
-        w /= d;
-        denom += w;
-        for (int c = 0; c < 9; ++c) numer[c] += w * nodes[j * 9 + c];
-    }
-    for (int c = 0; c < 9; ++c) L[c] = numer[c] / denom;
+// A wait between warps of one CTA (a system being prepared or finished by another warp).  The
+// watchdog turns a protocol bug into a launch failure instead of a hung GPU.
+__device__ __forceinline__ void spin_pause(unsigned &n) {
+    __nanosleep(64);
+    if (++n > (1u << 26)) __trap();
 }
-
-// One component c of L(t): lets 27 lanes (3 stage times x 9 components) evaluate the three
-// stage matrices in parallel instead of one lane looping over all of it -- this sits on the
-// serial path of every step while the other 15 warps wait at a barrier.
-__device__ inline double eval_L_component(const IntegrateArgs &A, const double *table, double t,
-                                          double ta, double tb, int c, const double *xnode) {
-    // `table` is the particle's node table [K][9]: the shared-memory copy made once per
-    // system when K <= 33, otherwise the global one
-    const double *nodes = table + c;
-    if (A.L_kind == 0 || A.K == 1) return nodes[0];
-    const double span = tb - ta;
-    const double x = (span != 0.0) ? (t - ta) / span : 0.0;
-    if (A.L_kind == 1) return nodes[0] + x * (nodes[9] - nodes[0]);
-    if (A.L_kind == 3) {
-        const double pos = fmin(fmax(x, 0.0), 1.0) * (A.K - 1);
-        int j = (int)pos;
-        if (j > A.K - 2) j = A.K - 2;
-        return nodes[j * 9] + (pos - j) * (nodes[(j + 1) * 9] - nodes[j * 9]);
-    }
-    // barycentric form without an exit inside the loop, so that the K iterations overlap: a
-    // node hit (|x - x_j| < 1e-15) is remembered and its term replaced by a harmless one
-    double numer = 0.0, denom = 0.0, hit_value = 0.0;
-    bool hit = false;
-    const int K = A.K;
-    for (int j = 0; j < K; ++j) {
-        const double xj = (j < 33) ? xnode[j] : 0.5 * (1.0 - cospi((double)j / (double)(K - 1)));
-        const double v = nodes[j * 9];
-        double d = x - xj;
-        const bool here = fabs(d) < 1e-15;
-        hit_value = (here && !hit) ? v : hit_value;
-        hit = hit || here;
-        d = here ? 1.0 : d;
-        // 1/d by the hardware approximation + two Newton steps (full double accuracy; the
-        // barycentric form uses the same weights above and below the fraction bar)
-        double r;
-        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-        r = fma(r, fma(-d, r, 1.0), r);
-        r = fma(r, fma(-d, r, 1.0), r);
-        double w = (j & 1) ? -r : r;
-        if (j == 0 || j == K - 1) w *= 0.5;
-        denom += w;
-        numer = fma(w, v, numer);
-    }
-    return hit ? hit_value : numer / denom;
-}
-
-// The flow quantities of `n` stage times (n = 1 or 3) evaluated cooperatively by warp 0:
-// 9 n lanes fetch the components of L(t_i), n lanes solve for the strain-rate scale, 9 n lanes
-// normalise.  This is serial work every other warp of the CTA waits for at a barrier, so
-// it is spread over the lanes instead of being looped by one thread.
-struct StageFlow;
-__device__ __noinline__ void warp_stage_flows(const IntegrateArgs &A, const double *table, StageFlow *st,
-                                        int first, int n, double t0s, double t1s, double t2s,
-                                        double ta, double tb, const double *xnode, int lane);
-
-// Per-stage flow quantities shared by the CTA.
-struct StageFlow {
-    double2 DL[9];   // {sym(L)/s, L/s} per component: one 16-byte shared load each
-    double V[9];     // left stretch of L.F_stage (regime matrix_diffusion only)
-    double Lraw[9];  // L
-    double s;        // strain_rate_max
-};
-
-struct StepShared {
-    StageFlow st[4];       // stage times t + h/2, t + 3h/4, t + h; [3]: the interval start t0
-    double F[9], kF[9];    // deformation gradient and its FSAL slope L(t).F
-    double Fnew[9], kFnew[9];
-    double errF;           // weighted error of the F block
-    double t, h, tend;
-    double red[64];
-    uint64_t mbar[INT_WARPS];
-    uint64_t mbar2[INT_WARPS];  // second in-flight chunk of the end-of-interval pass
-    double xnode[33];      // Chebyshev-Lobatto abscissae of the L(t) table (K <= 33)
-    double Ltab[33 * 9];   // this particle's L(t) node table (K <= 33; larger ones stay global)
-    int sys, flag;
-    int const_flow;        // L(t) constant over the interval: stage flows computed once
-};
 
 // Step planning: the rest of the interval is cut into n EQUAL steps, n the smallest count
 // whose step exceeds the controller's proposal by at most DREX_STRETCH.  A proposal that
 // would leave a sliver (remaining = 2.05 h) becomes two steps of 1.025 h instead of three
 // attempts.  The error test of every step is unchanged; the stretch only spends part of the
 // controller's safety margin (DREX_SAFETY^3 = 0.73 of the tolerance; error ~ h^3, and
-// 1.10^3 = 1.33).  Measured at bench size: 6 % fewer right-hand sides on simple shear, 4 % on
-// corner flow; 1.05 gains less, 1.15 and above lose it again to rejected steps.
+// 1.10^3 = 1.33).
 #ifndef DREX_STRETCH
 #define DREX_STRETCH 1.10
 #endif
@@ -270,9 +156,46 @@ __device__ __forceinline__ double plan_step(double h_prop, double remaining) {
 #define BS_E3 (1.0 / 9.0)
 #define BS_E4 (-1.0 / 8.0)
 
-// strain_rate_max (drex_common.cuh) with the divisions and the square root of the serial path
-// replaced by the ~1 ulp fast versions of drex_math.cuh: this runs on one lane per stage time
-// while the rest of the CTA waits.
+// Flow quantities of one stage time, as the right-hand side consumes them.
+struct ChunkFlow {
+    double2 DL[9];  // {sym(L)/s, L/s} per component (minerals.py:421,438-439)
+    double s;       // strain_rate_max (minerals.py:422)
+    double nks;     // -(0.3 if frictional) vf M* s: dv/dt = nks E
+};
+
+// One system in flight (shared memory).  Written by the preparing warp before `ticket` is
+// published and read-only afterwards, except the counters at the end.
+struct SysSlot {
+    double t0, t1, kappa, rscale;
+    double Q[9];                   // regimes 0/1/7: orientation increment common to all grains
+    ChunkFlow cflow;               // the flow when L is constant over the interval
+    double Ltab[INT_KMAX * 9];     // this particle's L(t) node table (K <= INT_KMAX)
+    double coef[10][INT_KMAX];     // Chebyshev coefficients of L (0-8) and of the strain-rate scale (9)
+    double ctab[2 * INT_KMAX];     // cos(pi m / (K - 1))
+    double Lst[4][9];              // stage matrices of the deformation-gradient integration
+    unsigned long long ticket;     // (sequence number << 32) | next chunk: the slot is ready when the
+                                   // upper half equals the sequence number a warp looks for
+    unsigned long long grain_evals;
+    int sys, regime, fab, mode, n_chunks, prep_at, const_flow, s_table, f_active, status0;
+    int done, status, n_rhs, n_acc, n_rej;
+    int busy;                      // from the start of prepare to the end of finalize
+};
+
+struct CtaShared {
+    SysSlot slot[INT_NCTX];
+    uint64_t mbar[INT_WARPS];
+    int hand_seq;  // sequence number of the system currently handing out chunks
+    int end_seq;   // number of systems this CTA processes (INT_MAX until the queue runs dry)
+};
+
+__device__ __forceinline__ int ld_vol(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
+__device__ __forceinline__ void st_vol(int *p, int v) { *reinterpret_cast<volatile int *>(p) = v; }
+__device__ __forceinline__ unsigned long long ld_vol64(const unsigned long long *p) {
+    return *reinterpret_cast<const volatile unsigned long long *>(p);
+}
+
+// strain_rate_max (drex_common.cuh) with the divisions and the square root replaced by the
+// ~1 ulp fast versions of drex_math.cuh.
 __device__ inline double strain_rate_max_fast(const double *L) {
     const double d00 = L[0], d11 = L[4], d22 = L[8];
     const double d01 = 0.5 * (L[1] + L[3]), d02 = 0.5 * (L[2] + L[6]), d12 = 0.5 * (L[5] + L[7]);
@@ -295,71 +218,105 @@ __device__ inline double strain_rate_max_fast(const double *L) {
     return fmax(fabs(e_hi), fabs(e_lo));
 }
 
-__device__ __noinline__ void warp_stage_flows(const IntegrateArgs &A, const double *table, StageFlow *st,
-                                        int first, int n, double t0s, double t1s, double t2s,
-                                        double ta, double tb, const double *xnode, int lane) {
-    const int si = lane / 9, c = lane - 9 * si;
-    const bool active = lane < 9 * n;
-    const double t = (si == 0) ? t0s : ((si == 1) ? t1s : t2s);
-    if (A.L_kind == 2 && A.K > 1 && A.K <= 9) {
-        // Chebyshev table with at most nine nodes: the barycentric weights of the n stage times
-        // are formed by 9 n lanes in parallel (one reciprocal each) and handed round by
-        // shuffles, instead of every lane walking all nodes on its own (3300 -> ~700 cycles of
-        // the serial section).  Same operations in the same order per component as
-        // eval_L_component: bit-identical.
-        const int K = A.K;
-        const double span = tb - ta;
-        const double x = (span != 0.0) ? (t - ta) / span : 0.0;
-        double w = 0.0;
-        bool here = false;
-        if (active && c < K) {
-            double d = x - xnode[c];
-            here = fabs(d) < 1e-15;
-            d = here ? 1.0 : d;
-            double r;
-            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-            r = fma(r, fma(-d, r, 1.0), r);
-            r = fma(r, fma(-d, r, 1.0), r);
-            w = (c & 1) ? -r : r;
-            if (c == 0 || c == K - 1) w *= 0.5;
-        }
-        const unsigned hits = __ballot_sync(0xffffffffu, here);
-        const int base = active ? 9 * si : 0;
-        double numer = 0.0, denom = 0.0;
-        for (int j = 0; j < K; ++j) {
-            const double wj = __shfl_sync(0xffffffffu, w, base + j);
-            denom += wj;
-            if (active) numer = fma(wj, table[j * 9 + c], numer);
-        }
-        if (active) {
-            const unsigned mine = (hits >> (9 * si)) & 0x1ffu;  // nodes this stage time sits on
-            st[first + si].Lraw[c] = mine ? table[(__ffs(mine) - 1) * 9 + c] : numer / denom;
-        }
-    } else if (active) {
-        st[first + si].Lraw[c] = eval_L_component(A, table, t, ta, tb, c, xnode);
+// sum_k a_k T_k(xi) by Clenshaw's recurrence (a_0 and a_{K-1} already carry their halves)
+__device__ __forceinline__ double clenshaw(const double *a, int K, double xi) {
+    double b1 = 0.0, b2 = 0.0;
+    const double x2 = xi + xi;
+    for (int k = K - 1; k >= 1; --k) {
+        const double b0 = fma(x2, b1, a[k] - b2);
+        b2 = b1;
+        b1 = b0;
     }
-    __syncwarp();
-    if (lane < n) st[first + lane].s = strain_rate_max_fast(st[first + lane].Lraw);
-    __syncwarp();
+    return fma(xi, b1, a[0] - b2);
+}
+
+// One component c of L(t) for the providers without a coefficient table: linear, piecewise
+// linear, and Chebyshev tables too large for shared memory (barycentric form).
+__device__ __noinline__ double eval_L_generic(const IntegrateArgs &A, const double *table, double t,
+                                              double ta, double tb, int c) {
+    const double *nodes = table + c;
+    if (A.L_kind == 0 || A.K == 1) return nodes[0];
+    const double span = tb - ta;
+    const double x = (span != 0.0) ? (t - ta) / span : 0.0;
+    if (A.L_kind == 1) return nodes[0] + x * (nodes[9] - nodes[0]);
+    if (A.L_kind == 3) {
+        const double pos = fmin(fmax(x, 0.0), 1.0) * (A.K - 1);
+        int j = (int)pos;
+        if (j > A.K - 2) j = A.K - 2;
+        return nodes[j * 9] + (pos - j) * (nodes[(j + 1) * 9] - nodes[j * 9]);
+    }
+    // Chebyshev-Lobatto nodes x_j = (1 - cos(pi j/(K-1)))/2 on [0, 1]; barycentric weights
+    // (-1)^j, halved at both ends
+    double numer = 0.0, denom = 0.0;
+    const int K = A.K;
+    for (int j = 0; j < K; ++j) {
+        const double xj = 0.5 * (1.0 - cospi((double)j / (double)(K - 1)));
+        const double d = x - xj;
+        if (fabs(d) < 1e-15) return nodes[j * 9];
+        double w = (j & 1) ? -1.0 : 1.0;
+        if (j == 0 || j == K - 1) w *= 0.5;
+        w /= d;
+        denom += w;
+        numer += w * nodes[j * 9];
+    }
+    return numer / denom;
+}
+
+// Component c (0-8) of L(t) for the system in `sl`.
+__device__ __forceinline__ double slot_L(const IntegrateArgs &A, const SysSlot &sl, double t, int c) {
+    if (A.L_kind == 0 || A.K == 1) return sl.Ltab[c];
+    if (A.L_kind == 2 && A.K <= INT_KMAX) {
+        const double span = sl.t1 - sl.t0;
+        const double xi = (span != 0.0) ? fma(2.0, (t - sl.t0) / span, -1.0) : -1.0;
+        return clenshaw(sl.coef[c], A.K, xi);
+    }
+    const double *table = (A.K <= INT_KMAX) ? sl.Ltab : A.L_nodes + (int64_t)A.sys_particle[sl.sys] * A.K * 9;
+    return eval_L_generic(A, table, t, sl.t0, sl.t1, c);
+}
+
+// The flow quantities of n <= 3 times from per-lane values: lane 10 i + c holds component c of
+// L(t_i) (c < 9) and, when have_s, the strain-rate scale in c = 9.  Every lane of the warp calls.
+__device__ __forceinline__ void store_flows(ChunkFlow *dst, int n, double val, bool have_s,
+                                            double kappa, int lane) {
+    const int si = lane / 10, c = lane - 10 * si;
+    const bool active = si < n;
+    const int base = active ? 10 * si : 0;
+    if (!have_s) {  // warp-uniform
+        double Lm[9];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) Lm[j] = __shfl_sync(0xffffffffu, val, base + j);
+        if (active && c == 9) val = strain_rate_max_fast(Lm);
+    }
+    const double sv = __shfl_sync(0xffffffffu, val, base + 9);
+    const int ct = (c < 9) ? 3 * (c % 3) + c / 3 : 0;  // transposed component
+    const double lt = __shfl_sync(0xffffffffu, val, base + ct);
     if (active) {
-        StageFlow &sf = st[first + si];
-        const int ct = 3 * (c % 3) + c / 3;  // transposed component
-        const double l = sf.Lraw[c], lt = sf.Lraw[ct], sc = sf.s;
-        sf.DL[c] = make_double2(div_fast(0.5 * (l + lt), sc),  // minerals.py:421,438
-                                div_fast(l, sc));              // minerals.py:439
+        if (c < 9) {
+            dst[si].DL[c] = make_double2(div_fast(0.5 * (val + lt), sv), div_fast(val, sv));
+        } else {
+            dst[si].s = sv;
+            dst[si].nks = -kappa * sv;
+        }
     }
     __syncwarp();
 }
 
-__device__ inline void fill_stage_flow(StageFlow &sf, const double *L) {
-    const double s = strain_rate_max(L);
-    sf.s = s;
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) {
-            sf.Lraw[3 * i + j] = L[3 * i + j];
-            sf.DL[3 * i + j] = make_double2((0.5 * (L[3 * i + j] + L[3 * j + i])) / s,  // minerals.py:421,438
-                                            L[3 * i + j] / s);                          // minerals.py:439
-        }
+// Stage flows at n <= 3 times for a warp stepping a chunk of the system in `sl`.
+__device__ __forceinline__ void warp_flows(const IntegrateArgs &A, const SysSlot &sl, ChunkFlow *dst,
+                                           int n, double ta, double tb, double tc, int lane) {
+    const int si = lane / 10, c = lane - 10 * si;
+    const double t = (si == 0) ? ta : ((si == 1) ? tb : tc);
+    double val = 0.0;
+    if (A.L_kind == 2 && A.K <= INT_KMAX) {
+        // the hot case: one Clenshaw recurrence per lane, components and scale alike
+        const double span = sl.t1 - sl.t0;
+        const double xi = fma(2.0, (t - sl.t0) / span, -1.0);
+        if (si < n && (c < 9 || sl.s_table)) val = clenshaw(sl.coef[c], A.K, xi);
+        store_flows(dst, n, val, sl.s_table != 0, sl.kappa, lane);
+    } else {
+        if (si < n && c < 9) val = slot_L(A, sl, t, c);
+        store_flows(dst, n, val, false, sl.kappa, lane);
+    }
 }
 
 // Clip to [-1, 1] (utils.py:187) on the integer pipe: the FP64 pipe is the bottleneck and
@@ -384,830 +341,646 @@ __device__ __forceinline__ void clip9(double (&a)[9]) {
     }
 }
 
-// Rotation rate (already multiplied by strain_rate_max, minerals.py:450) and strain
-// energy of one grain at one stage.  MODE is a GRAIN_* constant for the dislocation
-// regimes, or STAGE_OTHER for the regimes without slip (0, 1, 7).
-constexpr int STAGE_OTHER = 4;
-
+// Rotation rate (times strain_rate_max, minerals.py:450; times 0.3 when yielding, core.py:459)
+// and strain energy of one grain at one stage.
 template <int MODE>
-__device__ __forceinline__ void stage_rhs(const double (&a)[9], const StageFlow &sf, int regime,
+__device__ __forceinline__ void chunk_rhs(const double (&a)[9], const ChunkFlow &fl, double rscale,
                                           const FabricConsts &fc, const double *__restrict__ mt,
                                           double (&k)[9], double &energy) {
-    if (MODE != STAGE_OTHER && (MODE != GRAIN_RUNTIME || regime == 4 || regime == 6)) {
-        double D[9], L[9];
+    double D[9], L[9];
 #pragma unroll
-        for (int c = 0; c < 9; ++c) {
-            const double2 dl = sf.DL[c];
-            D[c] = dl.x;
-            L[c] = dl.y;
-        }
-        GrainOut out;
-        const double sc = (regime == 6) ? 0.3 * sf.s : sf.s;  // core.py:459
-        grain_rhs<false, MODE>(a, D, L, fc, mt, out, nullptr, 0.5 * sc);
-#pragma unroll
-        for (int c = 0; c < 9; ++c) k[c] = out.da[c];
-        energy = out.energy;
-    } else if (regime == 1) {  // core.py:392-405: every grain gets the stretch of L.F
-#pragma unroll
-        for (int c = 0; c < 9; ++c) k[c] = sf.s * sf.V[c];
-        energy = 0.0;
-    } else {  // regimes 0, 7: identity (core.py:386-391)
-#pragma unroll
-        for (int c = 0; c < 9; ++c) k[c] = (c % 4 == 0) ? sf.s : 0.0;
-        energy = 0.0;
+    for (int c = 0; c < 9; ++c) {
+        const double2 dl = fl.DL[c];
+        D[c] = dl.x;
+        L[c] = dl.y;
     }
+    GrainOut out;
+    grain_rhs<false, MODE>(a, D, L, fc, mt, out, nullptr, 0.5 * rscale * fl.s);
+#pragma unroll
+    for (int c = 0; c < 9; ++c) k[c] = out.da[c];
+    energy = out.energy;
 }
 
-// Weighted error ratio |err| / (atol + relw |y_new|).  Only its size relative to 1 steers
-// the step, so the reciprocal is the 2^-23-accurate hardware approximation and the running
-// maximum is kept in float32; a float sum of all ratios carries NaN/inf to the accept test.
-__device__ __forceinline__ float err_ratio(double err, double ynew, double atol_abs, double relw) {
+// Weighted error ratio |err| / (atol + relw |y_new|) as float bits.  Only its size relative to
+// 1 steers the step, so the reciprocal is the 2^-23-accurate hardware approximation; the
+// running maximum is taken on the BITS (non-negative floats order like unsigned integers and a
+// NaN sorts above infinity, so a non-finite state reaches the accept test).
+__device__ __forceinline__ uint32_t err_bits(double err, double ynew, double atol_abs, double relw) {
     const double sc = fma(relw, fabs(ynew), atol_abs);
     double rc;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(sc));
-    return (float)(fabs(err) * rc);
+    return __float_as_uint((float)(fabs(err) * rc)) & 0x7fffffffu;
 }
 
-// Chunks of 32 grains a warp can keep in registers during the fraction stages and the
-// end-of-interval pass (fast path: N <= 32 * INT_WARPS * MAXQ = 5120 grains).
-#ifndef DREX_MAXQ
-#define DREX_MAXQ 10
-#endif
-constexpr int MAXQ = DREX_MAXQ;
+struct ChunkResult {
+    double v, h_next;
+    int status, n_rhs, n_acc, n_rej, row;
+};
 
-#ifndef DREX_CTAS_PER_SM
-#define DREX_CTAS_PER_SM 1
-#endif
-constexpr int INT_CTAS_PER_SM = DREX_CTAS_PER_SM;
+// One chunk of 32 grains from t0 to t1: state in rows ROW_A.. of `rows` (already loaded), one
+// grain per lane.  Returns with the final orientation in rows res.row.. and v_g in res.v.
+template <int MODE>
+__device__ __forceinline__ void integrate_chunk(const IntegrateArgs &A, const SysSlot &sl,
+                                                const FabricConsts &fc, const double *__restrict__ mt,
+                                                double *rows, ChunkFlow *wf, int lane, double f0,
+                                                double h, ChunkResult &res) {
+    const double t_begin = sl.t0, t_end = sl.t1, span = t_end - t_begin;
+    const double relw = A.tol.atol_rel + A.tol.rtol, atol_abs = A.tol.atol_abs;
+    const bool f_active = sl.f_active != 0, const_flow = sl.const_flow != 0;
+    const ChunkFlow *fl = const_flow ? &sl.cflow : wf;
+    const int fstride = const_flow ? 0 : 1;
+    const double rscale = sl.rscale;
+    double *sa = rows + ROW_A * 32 + lane, *sy = rows + ROW_Y * 32 + lane;
+    double *const sk = rows + ROW_K1 * 32 + lane, *const se = rows + ROW_E * 32 + lane;
+    double t = t_begin, v = 0.0, kv1 = 0.0, h_carry = h;
+    int n_rhs = 0, n_acc = 0, n_rej = 0, status = 0;
+    bool need_k1 = true, last_rejected = false;
+    while (span != 0.0) {
+        if (n_acc + n_rej >= A.tol.max_steps) {
+            status = 1;  // DREX_STATUS_MAX_STEPS
+            break;
+        }
+        if (!const_flow) {
+            if (need_k1) warp_flows(A, sl, wf + 3, 1, t, t, t, lane);
+            warp_flows(A, sl, wf, 3, fma(BS_A21, h, t), fma(BS_A32, h, t), t + h, lane);
+        }
+        double k[9], st[9], e, kv = 0.0, vy = 0.0, ve = 0.0;
+        if (need_k1) {
+#pragma unroll
+            for (int c = 0; c < 9; ++c) st[c] = sa[c * 32];
+        } else {
+#pragma unroll
+            for (int c = 0; c < 9; ++c) st[c] = fma(h * BS_A21, sk[c * 32], sa[c * 32]);
+        }
+        // The stages run as a ROLLED loop: one copy of the right-hand side in the hot loop keeps
+        // it inside the instruction cache.  The bookkeeping between the stages differs per stage
+        // and sits behind warp-uniform branches: rows sy / se hold the partial new state
+        // y + h (b1 k1 + b2 k2) and the partial error e1 k1 + e2 k2 after stage 2, the full ones
+        // after stage 3.  Stage -1 (first step of the interval only) is the slope at t0.
+#pragma unroll 1
+        for (int stg = need_k1 ? -1 : 0; stg < 3; ++stg) {
+            clip9(st);
+            const ChunkFlow &sf = fl[(stg & 3) * fstride];  // -1 -> [3]: the step's start time
+            chunk_rhs<MODE>(st, sf, rscale, fc, mt, k, e);
+            kv = f_active ? sf.nks * e : 0.0;
+            if (stg < 0) {
+#pragma unroll
+                for (int c = 0; c < 9; ++c) {
+                    sk[c * 32] = k[c];
+                    st[c] = fma(h * BS_A21, k[c], sa[c * 32]);
+                }
+                kv1 = kv;
+            } else if (stg == 0) {
+#pragma unroll
+                for (int c = 0; c < 9; ++c) {
+                    const double ac = sa[c * 32], kc = sk[c * 32];
+                    sy[c * 32] = fma(h * BS_B2, k[c], fma(h * BS_B1, kc, ac));
+                    se[c * 32] = fma(BS_E2, k[c], BS_E1 * kc);
+                    st[c] = fma(h * BS_A32, k[c], ac);  // stage 3 starts from y + 3h/4 k2
+                }
+                vy = fma(h * BS_B2, kv, fma(h * BS_B1, kv1, v));
+                ve = fma(BS_E2, kv, BS_E1 * kv1);
+            } else if (stg == 1) {
+#pragma unroll
+                for (int c = 0; c < 9; ++c) {
+                    const double yn = fma(h * BS_B3, k[c], sy[c * 32]);
+                    sy[c * 32] = yn;
+                    se[c * 32] = fma(BS_E3, k[c], se[c * 32]);
+                    st[c] = yn;  // stage 4 is evaluated at the new state itself
+                }
+                vy = fma(h * BS_B3, kv, vy);
+                ve = fma(BS_E3, kv, ve);
+            }
+        }
+        uint32_t eb = 0;
+#pragma unroll
+        for (int c = 0; c < 9; ++c) {
+            const double err = h * fma(BS_E4, k[c], se[c * 32]);
+            eb = max(eb, err_bits(err, sy[c * 32], atol_abs, relw));
+        }
+        if (f_active) {
+            // the fraction components: f_g ~ f_g(t0) e^{v_g}, err_f = f_g err_v
+            const double fe = f0 * exp_tab(vy, mt);
+            eb = max(eb, err_bits(fe * (h * fma(BS_E4, kv, ve)), fe, A.tol.atol_abs_f, relw));
+        }
+        eb = __reduce_max_sync(0xffffffffu, eb);
+        n_rhs += need_k1 ? 4 : 3;
+        need_k1 = false;
+        const float emax = __uint_as_float(eb);
+        if (!(emax < INFINITY)) {
+            status = 3;  // DREX_STATUS_NOT_FINITE
+            break;
+        }
+        const bool accept = emax <= 1.0f;
+        double fac = (emax > 0.0f) ? DREX_SAFETY * rcbrt((double)emax) : 5.0;  // err^(-1/3)
+        fac = fmin(accept ? (last_rejected ? 1.0 : 5.0) : 1.0, fmax(0.2, fac));
+        double h_next = h * fac;
+        h_carry = h_next;
+        if (accept) {
+            ++n_acc;
+            last_rejected = false;
+            t += h;
+            v = vy;
+            kv1 = kv;
+            double *tmp = sa;
+            sa = sy;
+            sy = tmp;
+#pragma unroll
+            for (int c = 0; c < 9; ++c) sk[c * 32] = k[c];
+            const double remaining = t_end - t;
+            if (fabs(remaining) <= 1e-13 * fmax(fabs(t_end), fabs(span))) break;
+            if (A.tol.max_step_frac > 0.0 && fabs(h_next) > A.tol.max_step_frac * fabs(span))
+                h_next = A.tol.max_step_frac * span;
+            if (fabs(h_next) >= fabs(remaining) * (1.0 - 1e-10)) h_next = remaining;
+            else if (DREX_STRETCH > 1.0) h_next = plan_step(h_next, remaining);
+        } else {
+            ++n_rej;
+            last_rejected = true;
+            if (fabs(h_next) <= 1e-14 * fmax(fabs(t), fabs(span))) {
+                status = 2;  // DREX_STATUS_STEP_UNDERFLOW
+                break;
+            }
+        }
+        h = h_next;
+    }
+    res.v = v;
+    res.h_next = h_carry;
+    res.status = status;
+    res.n_rhs = n_rhs;
+    res.n_acc = n_acc;
+    res.n_rej = n_rej;
+    res.row = (sa == rows + ROW_A * 32 + lane) ? ROW_A : ROW_Y;
+}
+
+// ---- per-system prologue (one warp, once per system and interval) ------------------------
+
+// The deformation gradient dF/dt = L(t) F (minerals.py:426) from t0 to t1 with its own BS3(2)
+// steps; lane 0 does the arithmetic, 27 lanes evaluate the stage matrices.  In the regimes
+// without slip every grain turns at the same rate R(t) -- s V(t), V the left stretch of L F
+// (regime 1: core.py:392-405, minerals.py:427-429), or s I (regimes 0 and 7: core.py:386-391)
+// -- so Q = int R dt is integrated here as nine more unknowns and each grain just adds it.
+__device__ __noinline__ int integrate_gradient(const IntegrateArgs &A, SysSlot &sl, int lane) {
+    const int64_t s = sl.sys;
+    const int regime = sl.regime;
+    const bool with_Q = regime != 4 && regime != 6;
+    const double t_begin = sl.t0, t_end = sl.t1, span = t_end - t_begin;
+    const double relw = A.tol.atol_rel + A.tol.rtol, atol_abs = A.tol.atol_abs_F;
+    const int si = lane / 9, c = lane - 9 * si;
+    double F[9], kF[9], Q[9], R1[9];
+    int status = 0;
+    auto rate = [&](const double *Lm, const double *LF, double *R) {
+        const double sv = strain_rate_max(Lm);
+        if (regime == 1) {
+            left_stretch(LF, R);
+            for (int i = 0; i < 9; ++i) R[i] *= sv;
+        } else {
+            for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? sv : 0.0;
+        }
+    };
+    if (lane < 9) sl.Lst[3][lane] = slot_L(A, sl, t_begin, lane);
+    __syncwarp();
+    if (lane == 0) {
+        for (int i = 0; i < 9; ++i) {
+            F[i] = A.F[s * 9 + i];
+            Q[i] = 0.0;
+        }
+        matmul3(sl.Lst[3], F, kF);
+        if (with_Q) rate(sl.Lst[3], kF, R1);
+    }
+    double t = t_begin, h = span;
+    int steps = 0;
+    while (span != 0.0) {
+        if (steps++ >= A.tol.max_steps) {
+            status = 1;
+            break;
+        }
+        const double ts = (si == 0) ? fma(BS_A21, h, t) : ((si == 1) ? fma(BS_A32, h, t) : t + h);
+        if (lane < 27) sl.Lst[si][c] = slot_L(A, sl, ts, c);
+        __syncwarp();
+        int verdict = 0;  // 1 accept, 2 accept and done, 0 reject, <0 failure
+        double h_next = h;
+        if (lane == 0) {
+            double F2[9], F3[9], Fn[9], k2[9], k3[9], k4[9], R2[9], R3[9], R4[9], Qn[9];
+            for (int i = 0; i < 9; ++i) F2[i] = F[i] + h * BS_A21 * kF[i];
+            matmul3(sl.Lst[0], F2, k2);
+            for (int i = 0; i < 9; ++i) F3[i] = F[i] + h * BS_A32 * k2[i];
+            matmul3(sl.Lst[1], F3, k3);
+            for (int i = 0; i < 9; ++i) Fn[i] = F[i] + h * (BS_B1 * kF[i] + BS_B2 * k2[i] + BS_B3 * k3[i]);
+            matmul3(sl.Lst[2], Fn, k4);
+            double em = 0.0;
+            for (int i = 0; i < 9; ++i) {
+                const double err = h * (BS_E1 * kF[i] + BS_E2 * k2[i] + BS_E3 * k3[i] + BS_E4 * k4[i]);
+                const double r = fabs(err) / (atol_abs + relw * fabs(Fn[i]));
+                em = (r != r) ? INFINITY : fmax(em, r);
+            }
+            if (with_Q) {
+                rate(sl.Lst[0], k2, R2);
+                rate(sl.Lst[1], k3, R3);
+                rate(sl.Lst[2], k4, R4);
+                for (int i = 0; i < 9; ++i) {
+                    Qn[i] = Q[i] + h * (BS_B1 * R1[i] + BS_B2 * R2[i] + BS_B3 * R3[i]);
+                    const double err = h * (BS_E1 * R1[i] + BS_E2 * R2[i] + BS_E3 * R3[i] + BS_E4 * R4[i]);
+                    const double r = fabs(err) / (A.tol.atol_abs + relw * fabs(Qn[i]));
+                    em = (r != r) ? INFINITY : fmax(em, r);
+                }
+            }
+            if (!(em < INFINITY)) {
+                verdict = -3;
+            } else {
+                const bool accept = em <= 1.0;
+                double fac = (em > 0.0) ? DREX_SAFETY * rcbrt(em) : 5.0;
+                fac = fmin(accept ? 5.0 : 1.0, fmax(0.2, fac));
+                h_next = h * fac;
+                if (accept) {
+                    verdict = 1;
+                    for (int i = 0; i < 9; ++i) {
+                        F[i] = Fn[i];
+                        kF[i] = k4[i];
+                        if (with_Q) {
+                            Q[i] = Qn[i];
+                            R1[i] = R4[i];
+                        }
+                    }
+                    const double remaining = t_end - (t + h);
+                    if (fabs(remaining) <= 1e-13 * fmax(fabs(t_end), fabs(span))) verdict = 2;
+                    else if (fabs(h_next) >= fabs(remaining) * (1.0 - 1e-10)) h_next = remaining;
+                    else h_next = plan_step(h_next, remaining);
+                } else if (fabs(h_next) <= 1e-14 * fmax(fabs(t), fabs(span))) {
+                    verdict = -2;
+                }
+            }
+        }
+        verdict = __shfl_sync(0xffffffffu, verdict, 0);
+        h_next = __shfl_sync(0xffffffffu, h_next, 0);
+        if (verdict < 0) {
+            status = -verdict;
+            break;
+        }
+        if (verdict >= 1) t += h;
+        if (verdict == 2) break;
+        h = h_next;
+    }
+    if (lane == 0) {
+        for (int i = 0; i < 9; ++i) {
+            A.F[s * 9 + i] = F[i];
+            sl.Q[i] = Q[i];
+        }
+    }
+    return status;
+}
+
+// Take the next system from the queue and set slot (seq mod INT_NCTX) up for it; publishes the
+// slot by storing its ticket last.  Called by one whole warp.
+__device__ __noinline__ void prepare_system(const IntegrateArgs &A, const FabricTable &T, CtaShared &sh,
+                                            int seq, int lane) {
+    SysSlot &sl = sh.slot[seq % INT_NCTX];
+    unsigned spins = 0;
+    while (ld_vol(&sl.busy)) spin_pause(spins);  // the system that last used this slot is being finished
+    int s = -1;
+    if (lane == 0) {
+        const int ticket = atomicAdd(A.queue, 1);
+        if (ticket < A.S) s = (A.order != nullptr) ? A.order[ticket] : ticket;
+    }
+    s = __shfl_sync(0xffffffffu, s, 0);
+    if (s < 0) {
+        if (lane == 0) st_vol(&sh.end_seq, seq);
+        return;
+    }
+    const int64_t ip = A.sys_particle[s];
+    const int regime = A.sys_regime[s], fab = A.sys_fabric[s];
+    const int K = A.K;
+    const bool slip = regime == 4 || regime == 6;
+    const int phase = T.fab[fab].phase;
+    const double rscale = (regime == 6) ? 0.3 : 1.0;  // core.py:459,464
+    // grain-boundary migration active? (enstatite strain energy is identically zero,
+    // core.py:674-684 loops over systems 0..2 only)
+    const double kappa = (slip && phase == 0) ? rscale * A.sys_vol_frac[s] * A.gbm_mobility : 0.0;
+    const int n_chunks = (int)((A.N + 31) / 32);
+    if (lane == 0) {
+        sl.busy = 1;
+        sl.sys = s;
+        sl.regime = regime;
+        sl.fab = fab;
+        sl.mode = !slip ? 4 : (phase != 0 ? GRAIN_ENSTATITE
+                                          : (T.fab[fab].default_exponents ? GRAIN_OLIVINE_DEFAULT
+                                                                          : GRAIN_OLIVINE_GENERIC));
+        sl.t0 = A.t0[ip];
+        sl.t1 = A.t1[ip];
+        sl.kappa = kappa;
+        sl.rscale = rscale;
+        sl.f_active = kappa != 0.0;
+        sl.n_chunks = n_chunks;
+        sl.prep_at = n_chunks / 2;
+        sl.const_flow = (A.L_kind == 0 || K == 1) ? 1 : 0;
+        sl.s_table = 0;
+        sl.done = 0;
+        sl.status = 0;
+        sl.n_rhs = 0;
+        sl.n_acc = 0;
+        sl.n_rej = 0;
+        sl.grain_evals = 0ull;
+    }
+    if (K <= INT_KMAX)
+        for (int j = lane; j < K * 9; j += 32) sl.Ltab[j] = A.L_nodes[ip * K * 9 + j];
+    __syncwarp();
+    if (A.L_kind == 0 || K == 1) {
+        store_flows(&sl.cflow, 1, (lane < 9) ? sl.Ltab[lane] : 0.0, false, kappa, lane);
+    } else if (A.L_kind == 2 && K <= INT_KMAX) {
+        // Chebyshev coefficients of the interpolant through the K Lobatto nodes
+        // x_j = (1 - cos(pi j / n)) / 2, n = K - 1, i.e. xi_j = 2 x_j - 1 = cos(pi (n - j) / n):
+        //   a_k = (2 / n) sum''_j f_j T_k(xi_j),  T_k(xi_j) = cos(pi k (n - j) / n),
+        // first and last term of the sum halved, a_0 and a_n halved.
+        const int n = K - 1;
+        for (int m = lane; m < 2 * n; m += 32) sl.ctab[m] = cospi((double)m / (double)n);
+        __syncwarp();
+        auto coefficient = [&](const double *f, int stride, int k) {
+            double acc = 0.0;
+            for (int j = 0; j <= n; ++j) {
+                const double w = (j == 0 || j == n) ? 0.5 : 1.0;
+                acc = fma(w * f[j * stride], sl.ctab[(k * (n - j)) % (2 * n)], acc);
+            }
+            return acc * (((k == 0 || k == n) ? 1.0 : 2.0) / (double)n);
+        };
+        for (int idx = lane; idx < 9 * K; idx += 32) {
+            const int c = idx / K, k = idx - c * K;
+            sl.coef[c][k] = coefficient(sl.Ltab + c, 9, k);
+        }
+        // the strain-rate scale s(t) = max |eig sym L(t)| as a tenth series, kept only if it
+        // reproduces s at the midpoints between the nodes (s has kinks where the dominant
+        // eigenvalue changes; then every stage evaluates the closed form instead)
+        double *snode = sl.Lst[0];  // K <= 33 <= 36 doubles of scratch
+        for (int j = lane; j < K; j += 32) snode[j] = strain_rate_max(sl.Ltab + 9 * j);
+        __syncwarp();
+        for (int k = lane; k < K; k += 32) sl.coef[9][k] = coefficient(snode, 1, k);
+        __syncwarp();
+        double worst = 0.0;
+        for (int j = lane; j < n; j += 32) {
+            const double xi = -cospi(((double)j + 0.5) / (double)n);
+            double Lm[9];
+            for (int c = 0; c < 9; ++c) Lm[c] = clenshaw(sl.coef[c], K, xi);
+            const double se = strain_rate_max(Lm), si = clenshaw(sl.coef[9], K, xi);
+            const double rel = fabs(si - se) / se;
+            worst = (rel == rel) ? fmax(worst, rel) : INFINITY;
+        }
+        worst = warp_max(worst);
+        __syncwarp();
+        if (lane == 0) sl.s_table = (worst <= 1e-12) ? 1 : 0;
+        __syncwarp();
+    }
+    const int status0 = integrate_gradient(A, sl, lane);
+    if (lane == 0) sl.status0 = status0;
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0)
+        *reinterpret_cast<volatile unsigned long long *>(&sl.ticket) = (unsigned long long)(unsigned)seq << 32;
+}
+
+// End of the interval for one system, by the warp that completed its last chunk:
+// extract_vars -> apply_gbs against the interval-start orientations -> extract_vars
+// (minerals.py:464-474, 536-538; utils.py:159-190).  f_out holds u_g = max(f_g(t0), 0) e^{v_g}
+// and psum the per-chunk sums of u; every sum is formed in a fixed order.
+__device__ __noinline__ void finalize_system(const IntegrateArgs &A, SysSlot &sl, const double *psum,
+                                             int lane) {
+    const int64_t N = A.N, s = sl.sys;
+    const int nq = sl.n_chunks;
+    double *f_out = A.f_out + s * N;
+    double *o_out = A.o_out + s * 9 * N;
+    const double *o_prev = A.o_prev + s * 9 * N;
+    double acc = 0.0;
+    for (int q = lane; q < nq; q += 32) acc += __ldcg(psum + q);
+    const double S1 = warp_sum(acc);
+    const double floor_v = A.gbs_threshold / (double)N;
+    acc = 0.0;
+#pragma unroll 4
+    for (int q = 0; q < nq; ++q) {
+        const int64_t g = (int64_t)q * 32 + lane;
+        if (g < N) {
+            const double fh = __ldcg(f_out + g) / S1;
+            acc += (fh < floor_v) ? floor_v : fh;
+        }
+    }
+    const double S2 = warp_sum(acc);
+    acc = 0.0;
+#pragma unroll 4
+    for (int q = 0; q < nq; ++q) {
+        const int64_t g = (int64_t)q * 32 + lane;
+        if (g < N) {
+            const double fh = __ldcg(f_out + g) / S1;
+            acc += fmax(((fh < floor_v) ? floor_v : fh) / S2, 0.0);
+        }
+    }
+    const double S3 = warp_sum(acc);
+#pragma unroll 2
+    for (int q = 0; q < nq; ++q) {
+        const int64_t g = (int64_t)q * 32 + lane;
+        if (g < N) {
+            const double fh = __ldcg(f_out + g) / S1;
+            const bool slide = fh < floor_v;
+            f_out[g] = fmax((slide ? floor_v : fh) / S2, 0.0) / S3;
+            if (slide) {  // no rotation: the grain keeps its interval-start orientation
+#pragma unroll
+                for (int c = 0; c < 9; ++c) o_out[c * N + g] = clip1(o_prev[c * N + g]);
+            }
+        }
+    }
+    if (lane == 0) {
+        const int status = max(sl.status, sl.status0);
+        A.status[s] = status;
+        if (A.n_rhs) A.n_rhs[s] = sl.n_rhs;
+        if (A.n_accept) A.n_accept[s] = sl.n_acc;
+        if (A.n_reject) A.n_reject[s] = sl.n_rej;
+        if (A.grain_evals) A.grain_evals[s] = (int64_t)sl.grain_evals;
+    }
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) st_vol(&sl.busy, 0);
+}
+
+// ---- chunk tickets -------------------------------------------------------------------------
+
+struct ChunkRef {
+    int seq, q;  // seq < 0: none (-1: the CTA is done, -2: would have to wait)
+};
+
+// Next chunk of the system currently handing out work.
+__device__ __forceinline__ ChunkRef grab_chunk(CtaShared &sh, bool blocking, int lane) {
+    int seq = -1, q = -1;
+    if (lane == 0) {
+        unsigned spins = 0;
+        for (;;) {
+            const int hs = ld_vol(&sh.hand_seq);
+            if (hs >= ld_vol(&sh.end_seq)) break;
+            SysSlot &sl = sh.slot[hs % INT_NCTX];
+            const unsigned long long cur = ld_vol64(&sl.ticket);
+            if ((int)(cur >> 32) != hs) {  // still being prepared
+                if (!blocking) {
+                    seq = -2;
+                    break;
+                }
+                spin_pause(spins);
+                continue;
+            }
+            const int t = (int)(cur & 0xffffffffull);
+            if (t >= sl.n_chunks) {
+                atomicCAS(&sh.hand_seq, hs, hs + 1);
+                continue;
+            }
+            if (atomicCAS(&sl.ticket, cur, cur + 1ull) == cur) {
+                seq = hs;
+                q = t;
+                break;
+            }
+        }
+    }
+    seq = __shfl_sync(0xffffffffu, seq, 0);
+    q = __shfl_sync(0xffffffffu, q, 0);
+    __threadfence_block();  // the slot's fields were written before its ticket was published
+    return ChunkRef{seq, q};
+}
 
 __global__ void __launch_bounds__(INT_BLOCK, INT_CTAS_PER_SM)
 integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
     extern __shared__ __align__(128) double dyn_smem[];
-    __shared__ StepShared sh;
+    __shared__ CtaShared sh;
     __shared__ __align__(16) double math_tab[MATH_TABLE_DOUBLES];
     load_math_tables(math_tab);
-#ifdef DREX_PHASE_TIMERS
-    // development aid (scripts/phase_timers.py): thread 0's clock at the phase boundaries,
-    // summed per CTA and added to 8 counters behind the work queue
-    __shared__ long long ptimer[8];
-    __shared__ long long pmark;
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < 8; ++i) ptimer[i] = 0;
-        pmark = clock64();
-    }
-#define DREX_MARK(slot)                                  \
-    if (threadIdx.x == 0) {                              \
-        const long long now_ = clock64();                \
-        ptimer[slot] += now_ - pmark;                    \
-        pmark = now_;                                    \
-    }
-#else
-#define DREX_MARK(slot)
-#endif
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
     const int64_t N = A.N;
-    const int64_t n_chunks = (N + 31) / 32;
-    const bool fast = n_chunks <= (int64_t)MAXQ * INT_WARPS && !(A.tol.method & 0x100);
-    double *slot = A.scratch + (int64_t)blockIdx.x * A.slot_doubles;
-    double *stage = dyn_smem + warp * STAGE_DOUBLES;  // [STAGE_ROWS][32] doubles of this warp
-    double *p2_smem = dyn_smem + INT_WARPS * STAGE_DOUBLES;
-    const int64_t Npad = (N + 31) / 32 * 32;
-    // stage energies (and the generic path's clipped fractions): shared memory while they
-    // fit, global scratch otherwise
-    double *E2 = (0 < A.smem_arrays) ? p2_smem : slot + (SLOT_P2 + 0) * Npad;
-    double *E3 = (1 < A.smem_arrays) ? p2_smem + 1 * Npad : slot + (SLOT_P2 + 1) * Npad;
-    double *E4 = (2 < A.smem_arrays) ? p2_smem + 2 * Npad : slot + (SLOT_P2 + 2) * Npad;
-    double *fs = (3 < A.smem_arrays) ? p2_smem + 3 * Npad : slot + (SLOT_P2 + 3) * Npad;
-
+    double *rows = dyn_smem + warp * WARP_DOUBLES;
+    ChunkFlow *wf = reinterpret_cast<ChunkFlow *>(dyn_smem + INT_WARPS * WARP_DOUBLES) + 4 * warp;
+    double *psum_base = A.scratch + (int64_t)blockIdx.x * INT_NCTX * A.chunk_cap;
     uint64_t *mbar = &sh.mbar[warp];
-    uint32_t mbar_parity = 0, mbar2_parity = 0;
-    if (lane == 0) {
-        mbar_init(mbar, 1);
-        mbar_init(&sh.mbar2[warp], 1);
+    uint32_t parity = 0;
+    if (lane == 0) mbar_init(mbar, 1);
+    if (tid == 0) {
+        sh.hand_seq = 0;
+        sh.end_seq = 0x7fffffff;
+        for (int i = 0; i < INT_NCTX; ++i) {
+            sh.slot[i].ticket = ~0ull;
+            sh.slot[i].busy = 0;
+        }
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
+    if (warp == 0) prepare_system(A, T, sh, 0, lane);
 
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) {
-            const int ticket = atomicAdd(A.queue, 1);
-            sh.sys = (ticket < A.S && A.order != nullptr) ? A.order[ticket] : ticket;
+    // TMA needs 16-byte aligned rows: N even and aligned bases; otherwise plain loads
+    const bool rows_aligned = ((N & 1) == 0) && ((reinterpret_cast<uintptr_t>(A.o_in) & 15) == 0) &&
+                              ((reinterpret_cast<uintptr_t>(A.f_in) & 15) == 0);
+    auto prefetch = [&](const ChunkRef &ch) {
+        // ten 256 B rows (nine of o_in, one of f_in) of chunk ch into rows ROW_PF..: one copy per
+        // lane, issued by ten lanes at once
+        if (!rows_aligned) return;
+        const int64_t s = sh.slot[ch.seq % INT_NCTX].sys;
+        const int64_t g0 = (int64_t)ch.q * 32;
+        const uint32_t row_bytes = (uint32_t)(((N - g0 < 32) ? (N - g0) : 32) * sizeof(double));
+        if (lane == 0) mbar_expect_tx(mbar, 10 * row_bytes);
+        __syncwarp();
+        if (lane < 9) bulk_g2s(rows + (ROW_PF + lane) * 32, A.o_in + (s * 9 + lane) * N + g0, row_bytes, mbar);
+        if (lane == 9) bulk_g2s(rows + (ROW_PF + 9) * 32, A.f_in + s * N + g0, row_bytes, mbar);
+    };
+
+    ChunkRef cur = grab_chunk(sh, true, lane);
+    if (cur.seq >= 0) prefetch(cur);
+    while (cur.seq >= 0) {
+        SysSlot &sl = sh.slot[cur.seq % INT_NCTX];
+        const int64_t s = sl.sys;
+        const int64_t g = (int64_t)cur.q * 32 + lane;
+        const bool live = g < N;
+        // The warp that drew chunk `prep_at` of a system prepares the NEXT system before starting
+        // on its chunk, so that the slot is ready long before the current system runs out.  (Not
+        // at the time of the draw: a warp still holding an unfinished chunk must never wait for
+        // another system to be finished.)
+        if (cur.q == sl.prep_at) prepare_system(A, T, sh, cur.seq + 1, lane);
+        // ---- this chunk's state into rows ROW_A.., then the prefetch rows are free again
+        double f0;
+        if (rows_aligned) {
+            mbar_wait(mbar, parity);
+            parity ^= 1u;
+            const double *pf = rows + ROW_PF * 32 + lane;
+#pragma unroll
+            for (int c = 0; c < 9; ++c) rows[(ROW_A + c) * 32 + lane] = live ? pf[c * 32] : 0.0;
+            f0 = live ? pf[9 * 32] : 0.0;
+            // generic-proxy reads of the prefetch rows, then an async-proxy overwrite of them
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        } else {
+#pragma unroll
+            for (int c = 0; c < 9; ++c)
+                rows[(ROW_A + c) * 32 + lane] = live ? A.o_in[(s * 9 + c) * N + g] : 0.0;
+            f0 = live ? A.f_in[s * N + g] : 0.0;
         }
-        __syncthreads();
-        const int64_t s = sh.sys;
-        if (s >= A.S) break;
-        DREX_MARK(0)  // queue + end-of-system bookkeeping
+        __syncwarp();
+        ChunkRef nxt = grab_chunk(sh, false, lane);
+        if (nxt.seq >= 0) prefetch(nxt);
 
-        const int64_t ip = A.sys_particle[s];
-        const int regime = A.sys_regime[s];
-        // broadcast from lane 0: provably warp-uniform, so the fabric constants are addressed
-        // through uniform registers / the constant bank instead of ~30 vector registers
-        const int fab_u = __shfl_sync(0xffffffffu, A.sys_fabric[s], 0);
-        const FabricConsts &fc = T.fab[fab_u];
-        const double t_begin = A.t0[ip], t_end = A.t1[ip];
-        const double span = t_end - t_begin;
-        const double *o_in = A.o_in + s * 9 * N;
-        const double *f_in = A.f_in + s * N;
-        // grain-boundary migration active? (enstatite strain energy is identically zero,
-        // core.py:674-684 loops over systems 0..2 only)
-        const double gbm_scale = ((regime == 6) ? 0.3 : 1.0) * A.sys_vol_frac[s] * A.gbm_mobility;
-        const bool f_active = (regime == 4 || regime == 6) && fc.phase == 0 && gbm_scale != 0.0;
-        const double relw = A.tol.atol_rel + A.tol.rtol, atol_abs = A.tol.atol_abs;
-
-        double *yk_cur = slot + SLOT_YKA * Npad, *yk_nxt = slot + SLOT_YKB * Npad;
-        const double *f_cur = f_in;
-        double *f_nxt = slot + SLOT_FA * Npad;
-        double *kf_cur = slot + SLOT_KFA * Npad, *kf_nxt = slot + SLOT_KFB * Npad;
-
-        // ---- initial slope at t0 (one right-hand side) --------------------------------
-        const double *Ltable = (A.K <= 33) ? sh.Ltab : A.L_nodes + ip * A.K * 9;
-        if (tid < 32) {
-            if (A.L_kind == 2)
-                for (int j = lane; j < A.K && j < 33; j += 32)
-                    sh.xnode[j] = 0.5 * (1.0 - cospi((double)j / (double)(A.K - 1)));
-            if (A.K <= 33)
-                for (int j = lane; j < A.K * 9; j += 32) sh.Ltab[j] = A.L_nodes[ip * A.K * 9 + j];
-            __syncwarp();
-            warp_stage_flows(A, Ltable, sh.st, 3, 1, t_begin, t_begin, t_begin, t_begin, t_end, sh.xnode, lane);
-        }
-        if (tid == 0) {
-            const double *L = sh.st[3].Lraw;
-            sh.const_flow = (A.L_kind == 0 || A.K == 1) ? 1 : 0;
-            if (sh.const_flow) {
-                sh.st[0] = sh.st[3];
-                sh.st[1] = sh.st[3];
-                sh.st[2] = sh.st[3];
-            }
-            for (int c = 0; c < 9; ++c) sh.F[c] = A.F[s * 9 + c];
-            matmul3(L, sh.F, sh.kF);
-            if (regime == 1) left_stretch(sh.kF, sh.st[3].V);
-            sh.t = t_begin;
-            sh.tend = t_end;
-            double h = (A.h_io != nullptr) ? A.h_io[s] : 0.0;
+        f0 = fmax(f0, 0.0);  // utils.py:188
+        ChunkResult res;
+        res.v = 0.0;
+        res.h_next = 0.0;
+        res.status = res.n_rhs = res.n_acc = res.n_rej = 0;
+        res.row = ROW_A;
+        const int mode = sl.mode;
+        if (mode != 4) {
+            // first trial step of this chunk: carried from the previous interval, else the
+            // whole interval (or first_step_frac of it)
+            const double span = sl.t1 - sl.t0;
+            double h = (A.h_io != nullptr) ? A.h_io[s * sl.n_chunks + cur.q] : 0.0;
             if (!(fabs(h) > 0.0)) h = (A.tol.first_step_frac > 0.0 ? A.tol.first_step_frac : 1.0) * span;
             h = copysign(fabs(h), span);
             if (A.tol.max_step_frac > 0.0 && fabs(h) > A.tol.max_step_frac * fabs(span))
                 h = A.tol.max_step_frac * span;
-            // a step carried over from a longer interval must not leave this one
-            if (!(fabs(h) < fabs(span))) h = span;
-            if (DREX_STRETCH > 1.0) h = plan_step(h, span);
-            sh.h = h;
+            if (!(fabs(h) < fabs(span))) h = span;  // a step carried over from a longer interval
+            if (DREX_STRETCH > 1.0 && span != 0.0) h = plan_step(h, span);
+            // broadcast from lane 0: provably warp-uniform, so the fabric constants are addressed
+            // through uniform registers / the constant bank instead of ~30 vector registers
+            const int fab_u = __shfl_sync(0xffffffffu, sl.fab, 0);
+            const FabricConsts &fc = T.fab[fab_u];
+            if (mode == GRAIN_ENSTATITE) integrate_chunk<GRAIN_ENSTATITE>(A, sl, fc, math_tab, rows, wf, lane, f0, h, res);
+            else if (mode == GRAIN_OLIVINE_DEFAULT) integrate_chunk<GRAIN_OLIVINE_DEFAULT>(A, sl, fc, math_tab, rows, wf, lane, f0, h, res);
+            else integrate_chunk<GRAIN_OLIVINE_GENERIC>(A, sl, fc, math_tab, rows, wf, lane, f0, h, res);
         }
-        __syncthreads();
-        double sum_clip = 0.0;  // sum of max(f, 0) of the current state (utils.py:188-189)
-        // FUSED FIRST STEP.  A separate initial-slope pass moves every orientation through the
-        // SM twice more (o_in in, state + slope out to the chunked buffer: ~1.1 MB per system,
-        // as long as a right-hand side takes).  Instead the first step of the interval reads
-        // o_in directly and runs FOUR stages per chunk (slope at t0, then the three stages);
-        // nothing is written back for it: a rejected first step is simply redone, slope
-        // included.  Needs 16-byte aligned o_in rows (TMA) and the register-resident fraction
-        // stages; otherwise, and for a zero-length interval, the separate pass below runs.
-        double *E1 = slot + SLOT_E1 * Npad;
-        const bool fused = fast && span != 0.0 && ((N & 1) == 0) &&
-                           ((reinterpret_cast<uintptr_t>(o_in) & 15) == 0) && !(A.tol.method & 0x800);
-        if (!fused) {
-            // software-pipelined: the next chunk's loads are in flight during this chunk's math
-            double sumc = 0.0, sume = 0.0, an[9], fn = 0.0;
-            {
-                const int64_t g0 = (int64_t)warp * 32 + lane;
-                const bool ok = warp < n_chunks && g0 < N;
+        // ---- results of the chunk: clipped orientations (utils.py:187), u_g = clip(f_g) e^{v_g}
+        {
+            const double *fin = rows + res.row * 32 + lane;
+            double *o_out = A.o_out + s * 9 * N + g;
+            if (live) {
 #pragma unroll
-                for (int c = 0; c < 9; ++c) an[c] = ok ? o_in[c * N + g0] : 0.0;
-                fn = ok ? f_in[g0] : 0.0;
-            }
-            for (int64_t q = warp; q < n_chunks; q += INT_WARPS) {
-                const int64_t g = q * 32 + lane;
-                double a[9], k[9], e;
-#pragma unroll
-                for (int c = 0; c < 9; ++c) a[c] = an[c];
-                const double xc = fmax(fn, 0.0);
-                {
-                    const int64_t gn = (q + INT_WARPS) * 32 + lane;
-                    const bool ok = (q + INT_WARPS) < n_chunks && gn < N;
-#pragma unroll
-                    for (int c = 0; c < 9; ++c) an[c] = ok ? o_in[c * N + gn] : 0.0;
-                    fn = ok ? f_in[gn] : 0.0;
-                }
-                double *blk = yk_cur + q * CHUNK_DOUBLES + lane;
-#pragma unroll
-                for (int c = 0; c < 9; ++c) blk[c * 32] = a[c];  // idle lanes of the tail: zeros
-                clip9(a);
-                stage_rhs<GRAIN_RUNTIME>(a, sh.st[3], regime, fc, math_tab, k, e);
-#pragma unroll
-                for (int c = 0; c < 9; ++c) blk[(9 + c) * 32] = k[c];
-                if (g < N) {
-                    if (f_active) E4[g] = e;
-                    sumc += xc;
-                    sume += xc * e;
-                }
-            }
-            block_sum2<INT_BLOCK>(sumc, sume, sh.red);
-            sum_clip = sumc;
-            if (f_active) {
-                const double mean = sume / sumc;
-                // df = vf M* (f / sum f) (mean - E) s (core.py:431-436): the factor common to all
-                // grains of a stage, s vf M* / sum f, is formed once per thread
-                const double ps = sh.st[3].s * gbm_scale / sumc;
-                if (fast) {
-                    double fr[MAXQ], er[MAXQ];
-#pragma unroll
-                    for (int j = 0; j < MAXQ; ++j) {
-                        const int64_t g = ((int64_t)warp + j * INT_WARPS) * 32 + lane;
-                        const bool ok = g < N;
-                        fr[j] = ok ? f_in[g] : 0.0;
-                        er[j] = ok ? E4[g] : 0.0;
-                    }
-#pragma unroll
-                    for (int j = 0; j < MAXQ; ++j) {
-                        const int64_t g = ((int64_t)warp + j * INT_WARPS) * 32 + lane;
-                        if (g < N) kf_cur[g] = (ps * fmax(fr[j], 0.0)) * (mean - er[j]);
-                    }
-                } else {
-                    for (int64_t q = warp; q < n_chunks; q += INT_WARPS) {
-                        const int64_t g = q * 32 + lane;
-                        if (g < N) kf_cur[g] = (ps * fmax(f_in[g], 0.0)) * (mean - E4[g]);
-                    }
-                }
-            }
-        }
-        int n_rhs = fused ? 0 : 1, n_acc = 0, n_rej = 0, status = 0;
-        bool done = (span == 0.0);
-        bool last_rejected = false;
-        double h_carry = 0.0;
-
-        // ---- adaptive steps -------------------------------------------------------------
-        DREX_MARK(1)  // initial slope
-        while (!done) {
-            __syncthreads();  // the state buffers of the previous step are complete
-            DREX_MARK(5)  // accept / controller of the previous step (or nothing)
-            if (n_acc + n_rej >= A.tol.max_steps) {
-                status = 1;  // DREX_STATUS_MAX_STEPS
-                break;
-            }
-            auto issue_chunk = [&](int64_t q) {
-                // one elected lane fetches chunk q (18 rows x 256 B, contiguous) into rows 0-17
-                if (lane == 0) {
-                    mbar_expect_tx(mbar, (uint32_t)(CHUNK_DOUBLES * sizeof(double)));
-                    bulk_g2s(stage, yk_cur + q * CHUNK_DOUBLES, (uint32_t)(CHUNK_DOUBLES * sizeof(double)), mbar);
-                }
-            };
-            // until a step has been accepted the state is still o_in: fused first step
-            const bool first = fused && n_acc == 0;
-            auto issue_first = [&](int64_t q) {
-                // the nine 256 B rows of o_in for chunk q into rows 0-8: one copy per lane, issued
-                // by nine lanes at once (nine copies in a row from one lane showed up as the
-                // top stall of the kernel)
-                const int64_t g0 = q * 32;
-                const uint32_t row_bytes = (uint32_t)(((N - g0 < 32) ? (N - g0) : 32) * sizeof(double));
-                if (lane == 0) mbar_expect_tx(mbar, 9 * row_bytes);
-                __syncwarp();
-                if (lane < 9) bulk_g2s(stage + lane * 32, o_in + lane * N + g0, row_bytes, mbar);
-            };
-            // prefetch this warp's first chunk while the stage flows are being set up
-            if (warp < n_chunks) {
-                if (first) issue_first(warp);
-                else issue_chunk(warp);
-            }
-
-            // stage flows at t + h/2, t + 3h/4, t + h (three lanes), then F by lane 0
-            if (!sh.const_flow && tid < 32)
-                warp_stage_flows(A, Ltable, sh.st, 0, 3, sh.t + BS_A21 * sh.h, sh.t + BS_A32 * sh.h,
-                                 sh.t + sh.h, t_begin, t_end, sh.xnode, lane);
-            __syncthreads();
-            // The deformation gradient is advanced by one thread of the LAST warp: chunks are
-            // dealt round-robin, so that warp owns the fewest (9 instead of 10 at N = 5000)
-            // and has the slack; on warp 0 these ~6000 serial cycles made it the warp every
-            // other one waits for at the next barrier.
-            if (tid == INT_BLOCK - 32) {
-                // dF/dt = L(t) F (minerals.py:426), same BS3(2) stages
-                const double h = sh.h;
-                double F2[9], F3[9], k2[9], k3[9];
-                for (int c = 0; c < 9; ++c) F2[c] = sh.F[c] + h * BS_A21 * sh.kF[c];
-                matmul3(sh.st[0].Lraw, F2, k2);
-                for (int c = 0; c < 9; ++c) F3[c] = sh.F[c] + h * BS_A32 * k2[c];
-                matmul3(sh.st[1].Lraw, F3, k3);
-                for (int c = 0; c < 9; ++c)
-                    sh.Fnew[c] = sh.F[c] + h * (BS_B1 * sh.kF[c] + BS_B2 * k2[c] + BS_B3 * k3[c]);
-                matmul3(sh.st[2].Lraw, sh.Fnew, sh.kFnew);
-                double em = 0.0;
                 for (int c = 0; c < 9; ++c) {
-                    const double err = h * (BS_E1 * sh.kF[c] + BS_E2 * k2[c] + BS_E3 * k3[c] + BS_E4 * sh.kFnew[c]);
-                    const double sc = atol_abs + relw * fabs(sh.Fnew[c]);
-                    const double r = fabs(err) / sc;
-                    em = (r != r) ? INFINITY : fmax(em, r);
-                }
-                sh.errF = em;
-                if (regime == 1) {  // stretch of (L F) at the stage states (minerals.py:427-429)
-                    left_stretch(k2, sh.st[0].V);
-                    left_stretch(k3, sh.st[1].V);
-                    left_stretch(sh.kFnew, sh.st[2].V);
+                    const double y = (mode != 4) ? fin[c * 32] : fin[c * 32] + sl.Q[c];
+                    o_out[c * N] = clip_int(y);
                 }
             }
-            DREX_MARK(2)  // stage flows + F stages by thread 0
-            // only the diffusion regime reads tid 0's results (V) during phase 1; errF and
-            // Fnew are consumed after the block reductions below
-            if (regime == 1) __syncthreads();
-            const double h = sh.h;
-            float emax_f = 0.0f, racc = 0.0f;  // max and sum of the error ratios
-
-            // ---- phase 1: every grain through all three stages, no synchronisation --------
-            auto phase1 = [&](auto mode_tag) {
-            constexpr int MODE = decltype(mode_tag)::value;
-            for (int64_t q = warp; q < n_chunks; q += INT_WARPS) {
-                const int64_t g = q * 32 + lane;
-                const int64_t qn = q + INT_WARPS;
-                const bool live = g < N;
-                double *sa = stage + lane, *sk = stage + 9 * 32 + lane;
-                double *sy = stage + 18 * 32 + lane, *se = stage + 27 * 32 + lane;
-                double k[9], st[9], e = 0.0;
-                mbar_wait(mbar, mbar_parity);
-                mbar_parity ^= 1u;
-                if (first) {
-                    // rows 0-8 hold o_in; lanes past the end of a ragged last chunk carry zeros
-#pragma unroll
-                    for (int c = 0; c < 9; ++c) {
-                        if (!live) sa[c * 32] = 0.0;
-                        st[c] = live ? sa[c * 32] : 0.0;
-                    }
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 9; ++c) st[c] = fma(h * BS_A21, sk[c * 32], sa[c * 32]);
-                }
-                // The three stages run as a ROLLED loop: one copy of the ~1300-instruction
-                // right-hand side in the hot loop keeps it inside the instruction cache
-                // (three inlined copies are ~80 KB of SASS and every warp streams them
-                // from L2 on every chunk).  The bookkeeping between the stages differs per
-                // stage and sits behind CTA-uniform branches: rows sy / se hold the partial
-                // new state y + h (b1 k1 + b2 k2) and the partial error e1 k1 + e2 k2 after
-                // stage 2, the full ones after stage 3.
-#pragma unroll 1
-                for (int stg = first ? -1 : 0; stg < 3; ++stg) {
-                    clip9(st);
-                    stage_rhs<MODE>(st, sh.st[stg & 3], regime, fc, math_tab, k, e);  // -1 -> [3]: t0
-                    if (f_active && live) {
-                        double *Ep = (stg == 0) ? E2 : ((stg == 1) ? E3 : ((stg == 2) ? E4 : E1));
-                        Ep[g] = e;
-                    }
-                    if (stg < 0) {
-                        // slope at t0 (the FSAL slope of a later step): rows 9-17, then stage 2
-#pragma unroll
-                        for (int c = 0; c < 9; ++c) {
-                            sk[c * 32] = k[c];
-                            st[c] = fma(h * BS_A21, k[c], sa[c * 32]);
-                        }
-                    } else if (stg == 0) {
-#pragma unroll
-                        for (int c = 0; c < 9; ++c) {
-                            const double ac = sa[c * 32], kc = sk[c * 32];
-                            sy[c * 32] = fma(h * BS_B2, k[c], fma(h * BS_B1, kc, ac));
-                            se[c * 32] = fma(BS_E2, k[c], BS_E1 * kc);
-                            st[c] = fma(h * BS_A32, k[c], ac);  // stage 3 starts from y + 3h/4 k2
-                        }
-                        // rows 0-17 are free now: fetch the next chunk behind stages 3 and 4
-                        __syncwarp();
-                        if (qn < n_chunks) {
-                            if (first) issue_first(qn);
-                            else issue_chunk(qn);
-                        }
-                    } else if (stg == 1) {
-#pragma unroll
-                        for (int c = 0; c < 9; ++c) {
-                            const double yn = fma(h * BS_B3, k[c], sy[c * 32]);
-                            sy[c * 32] = yn;
-                            se[c * 32] = fma(BS_E3, k[c], se[c * 32]);
-                            st[c] = yn;  // stage 4 is evaluated at the new state itself
-                        }
-                    }
-                }
-                {
-                    double *blk = yk_nxt + q * CHUNK_DOUBLES + lane;  // idle tail lanes carry zeros
-#pragma unroll
-                    for (int c = 0; c < 9; ++c) {
-                        const double yn = sy[c * 32];
-                        const double err = h * (se[c * 32] + BS_E4 * k[c]);
-                        const float r = err_ratio(err, yn, atol_abs, relw);
-                        emax_f = fmaxf(emax_f, r);
-                        racc += r;  // any non-finite k or y_new makes err, hence r, non-finite
-                        blk[c * 32] = yn;
-                        blk[(9 + c) * 32] = k[c];
-                    }
-                }
-            }
-            };
-            // one instantiation per variant: only that variant's code is in the hot loop
-            if (regime != 4 && regime != 6) phase1(std::integral_constant<int, STAGE_OTHER>{});
-            else if (fc.phase != 0) phase1(std::integral_constant<int, GRAIN_ENSTATITE>{});
-            else if (fc.default_exponents) phase1(std::integral_constant<int, GRAIN_OLIVINE_DEFAULT>{});
-            else phase1(std::integral_constant<int, GRAIN_OLIVINE_GENERIC>{});
-            n_rhs += first ? 4 : 3;
-            DREX_MARK(3)  // phase 1 (warp 0's own chunks)
-            // the new state was written through the generic proxy and is read by TMA (async
-            // proxy) in the next step
-            asm volatile("fence.proxy.async.global;" ::: "memory");
-            double emax = (racc < INFINITY) ? (double)emax_f : INFINITY;
-            double sum_clip_new = sum_clip;
-
-            // ---- phase 2: coupled volume fractions (core.py:431-436) --------------------
-            if (f_active && fast) {
-                // every per-grain value of this thread stays in registers across the four
-                // block reductions; loads are issued together, stores at the end
-                double fr[MAXQ], k1[MAXQ], xr[MAXQ], k2[MAXQ], e4[MAXQ];
-#pragma unroll
-                for (int j = 0; j < MAXQ; ++j) {
-                    const int64_t g = ((int64_t)warp + j * INT_WARPS) * 32 + lane;
-                    const bool ok = g < N;
-                    fr[j] = ok ? f_cur[g] : 0.0;
-                    k1[j] = ok ? (first ? E1[g] : kf_cur[g]) : 0.0;  // first step: energy at t0 for now
-                    e4[j] = ok ? E4[g] : 0.0;
-                }
-                double sc_ = 0.0, se_ = 0.0;
-                if (first) {
-                    // initial slope of the fractions (core.py:431-436 at t0), which the separate
-                    // initial pass computes otherwise
-#pragma unroll
-                    for (int j = 0; j < MAXQ; ++j) {
-                        const double xc = fmax(fr[j], 0.0);
-                        sc_ += xc;
-                        se_ += xc * k1[j];
-                    }
-                    block_sum2<INT_BLOCK>(sc_, se_, sh.red);
-                    sum_clip = sc_;
-                    const double mean0 = se_ / sc_, ps0 = sh.st[3].s * gbm_scale / sc_;
-#pragma unroll
-                    for (int j = 0; j < MAXQ; ++j) k1[j] = (ps0 * fmax(fr[j], 0.0)) * (mean0 - k1[j]);
-                    sc_ = 0.0;
-                    se_ = 0.0;
-                }
-#pragma unroll
-                for (int j = 0; j < MAXQ; ++j) {  // stage 2 state
-                    const int64_t g = ((int64_t)warp + j * INT_WARPS) * 32 + lane;
-                    xr[j] = fmax(fr[j] + (h * BS_A21) * k1[j], 0.0);
-                    sc_ += xr[j];
-                    se_ += xr[j] * ((g < N) ? E2[g] : 0.0);
-                }
-                block_sum2<INT_BLOCK>(sc_, se_, sh.red);
-                double sumc = sc_, mean = se_ / sc_, ps = sh.st[0].s * gbm_scale / sumc;
-                sc_ = 0.0;
-                se_ = 0.0;
-#pragma unroll
-                for (int j = 0; j < MAXQ; ++j) {  // k2, stage 3 state
-                    const int64_t g = ((int64_t)warp + j * INT_WARPS) * 32 + lane;
-                    const bool ok = g < N;
-                    k2[j] = (ps * xr[j]) * (mean - (ok ? E2[g] : 0.0));
-                    xr[j] = fmax(fr[j] + (h * BS_A32) * k2[j], 0.0);
-                    sc_ += xr[j];
-                    se_ += xr[j] * (ok ? E3[g] : 0.0);
-                }
-                block_sum2<INT_BLOCK>(sc_, se_, sh.red);
-                sumc = sc_;
-                mean = se_ / sc_;
-                ps = sh.st[1].s * gbm_scale / sumc;
-                sc_ = 0.0;
-                se_ = 0.0;
-#pragma unroll
-                for (int j = 0; j < MAXQ; ++j) {  // k3, new state
-                    const int64_t g = ((int64_t)warp + j * INT_WARPS) * 32 + lane;
-                    const double k3 = (ps * xr[j]) * (mean - ((g < N) ? E3[g] : 0.0));
-                    const double fn = fr[j] + h * (BS_B1 * k1[j] + BS_B2 * k2[j] + BS_B3 * k3);
-                    k1[j] = BS_E1 * k1[j] + BS_E2 * k2[j] + BS_E3 * k3;  // error combination
-                    k2[j] = fn;                                           // new fraction
-                    xr[j] = fmax(fn, 0.0);
-                    sc_ += xr[j];
-                    se_ += xr[j] * e4[j];
-                }
-                block_sum2<INT_BLOCK>(sc_, se_, sh.red);
-                sumc = sc_;
-                sum_clip_new = sc_;
-                mean = se_ / sc_;
-                ps = sh.st[2].s * gbm_scale / sumc;
-                float ef = 0.0f, rf = 0.0f;
-#pragma unroll
-                for (int j = 0; j < MAXQ; ++j) {  // k4 (FSAL), error
-                    const int64_t g = ((int64_t)warp + j * INT_WARPS) * 32 + lane;
-                    const double k4 = (ps * xr[j]) * (mean - e4[j]);
-                    if (g < N) {
-                        kf_nxt[g] = k4;
-                        f_nxt[g] = k2[j];
-                        const double err = h * (k1[j] + BS_E4 * k4);
-                        const float r = err_ratio(err, k2[j], atol_abs, relw);
-                        ef = fmaxf(ef, r);
-                        rf += r;
-                    }
-                }
-                emax = (rf < INFINITY) ? fmax(emax, (double)ef) : INFINITY;
-            } else if (f_active) {
-                // generic path for ensembles too large for the register path: the same four
-                // sweeps through memory (E2 -> k2 -> error combination, E3 -> new fraction)
-                double *kf2 = E2, *acce = E2, *fnew_s = E3;
-                double sc_ = 0.0, se_ = 0.0;
-                for (int64_t q = warp; q < n_chunks; q += INT_WARPS) {  // stage 2 state
-                    const int64_t g = q * 32 + lane;
-                    if (g < N) {
-                        const double xc = fmax(f_cur[g] + (h * BS_A21) * kf_cur[g], 0.0);
-                        fs[g] = xc;
-                        sc_ += xc;
-                        se_ += xc * E2[g];
-                    }
-                }
-                block_sum2<INT_BLOCK>(sc_, se_, sh.red);
-                double sumc = sc_, mean = se_ / sc_, ps = sh.st[0].s * gbm_scale / sumc;
-                sc_ = 0.0;
-                se_ = 0.0;
-                for (int64_t q = warp; q < n_chunks; q += INT_WARPS) {  // k2, stage 3 state
-                    const int64_t g = q * 32 + lane;
-                    if (g < N) {
-                        const double k2 = (ps * fs[g]) * (mean - E2[g]);
-                        kf2[g] = k2;  // E2[g] is dead from here
-                        const double xc = fmax(f_cur[g] + (h * BS_A32) * k2, 0.0);
-                        fs[g] = xc;
-                        sc_ += xc;
-                        se_ += xc * E3[g];
-                    }
-                }
-                block_sum2<INT_BLOCK>(sc_, se_, sh.red);
-                sumc = sc_;
-                mean = se_ / sc_;
-                ps = sh.st[1].s * gbm_scale / sumc;
-                sc_ = 0.0;
-                se_ = 0.0;
-                for (int64_t q = warp; q < n_chunks; q += INT_WARPS) {  // k3, new state
-                    const int64_t g = q * 32 + lane;
-                    if (g < N) {
-                        const double k1 = kf_cur[g], k2 = kf2[g];
-                        const double k3 = (ps * fs[g]) * (mean - E3[g]);
-                        const double fn = f_cur[g] + h * (BS_B1 * k1 + BS_B2 * k2 + BS_B3 * k3);
-                        f_nxt[g] = fn;
-                        fnew_s[g] = fn;  // E3[g] is dead from here
-                        acce[g] = BS_E1 * k1 + BS_E2 * k2 + BS_E3 * k3;
-                        const double xc = fmax(fn, 0.0);
-                        fs[g] = xc;
-                        sc_ += xc;
-                        se_ += xc * E4[g];
-                    }
-                }
-                block_sum2<INT_BLOCK>(sc_, se_, sh.red);
-                sumc = sc_;
-                sum_clip_new = sc_;
-                mean = se_ / sc_;
-                ps = sh.st[2].s * gbm_scale / sumc;
-                float ef = 0.0f, rf = 0.0f;
-                for (int64_t q = warp; q < n_chunks; q += INT_WARPS) {  // k4 (FSAL), error
-                    const int64_t g = q * 32 + lane;
-                    if (g < N) {
-                        const double k4 = (ps * fs[g]) * (mean - E4[g]);
-                        kf_nxt[g] = k4;
-                        const double err = h * (acce[g] + BS_E4 * k4);
-                        const float r = err_ratio(err, fnew_s[g], atol_abs, relw);
-                        ef = fmaxf(ef, r);
-                        rf += r;
-                    }
-                }
-                emax = (rf < INFINITY) ? fmax(emax, (double)ef) : INFINITY;
-            }
-            emax = block_max<INT_BLOCK>(emax, sh.red);
-            DREX_MARK(4)  // waiting for the slowest warp + phase 2 + reductions
-            emax = fmax(emax, sh.errF);
-
-            // ---- accept / reject (uniform across the CTA: every thread holds emax) -------
-            if (!(emax < INFINITY)) {
-                status = 3;  // DREX_STATUS_NOT_FINITE
-                break;
-            }
-            const bool accept = emax <= 1.0;
-            double fac = (emax > 0.0) ? DREX_SAFETY * rcbrt(emax) : 5.0;  // err^(-1/3), no general pow
-            fac = fmin(accept ? (last_rejected ? 1.0 : 5.0) : 1.0, fmax(0.2, fac));
-            double t_now = sh.t, h_next = h * fac;
-            __syncthreads();  // all reads of sh.t / sh.h / sh.F done
-            if (accept) {
-                ++n_acc;
-                last_rejected = false;
-                t_now = t_now + h;
-                h_carry = h_next;
-                sum_clip = sum_clip_new;
-                // swap ping-pong buffers
-                double *ykt = yk_cur;
-                yk_cur = yk_nxt;
-                yk_nxt = ykt;
-                if (f_active) {
-                    const double *f_old = f_cur;
-                    f_cur = f_nxt;
-                    f_nxt = (f_old == f_in) ? slot + SLOT_FB * Npad : const_cast<double *>(f_old);
-                    double *kft = kf_cur;
-                    kf_cur = kf_nxt;
-                    kf_nxt = kft;
-                }
-                if (tid == 0) {
-                    for (int c = 0; c < 9; ++c) {
-                        sh.F[c] = sh.Fnew[c];
-                        sh.kF[c] = sh.kFnew[c];
-                    }
-                }
-                const double remaining = t_end - t_now;
-                if (fabs(remaining) <= 1e-13 * fmax(fabs(t_end), fabs(span))) {
-                    done = true;
-                } else {
-                    if (A.tol.max_step_frac > 0.0 && fabs(h_next) > A.tol.max_step_frac * fabs(span))
-                        h_next = A.tol.max_step_frac * span;
-                    if (fabs(h_next) >= fabs(remaining) * (1.0 - 1e-10)) h_next = remaining;
-                    else if (DREX_STRETCH > 1.0) h_next = plan_step(h_next, remaining);
-                }
-            } else {
-                ++n_rej;
-                last_rejected = true;
-                h_carry = h_next;
-                if (fabs(h_next) <= 1e-14 * fmax(fabs(t_now), fabs(span))) {
-                    status = 2;  // DREX_STATUS_STEP_UNDERFLOW
-                    break;
-                }
-            }
-            if (tid == 0) {
-                sh.t = t_now;
-                sh.h = done ? h_carry : h_next;  // when done: suggestion for the next interval
+            const double u = sl.f_active ? f0 * exp_tab(res.v, math_tab) : f0;
+            if (live) A.f_out[s * N + g] = u;
+            const double part = warp_sum(live ? u : 0.0);
+            if (lane == 0) {
+                psum_base[(int64_t)(cur.seq % INT_NCTX) * A.chunk_cap + cur.q] = part;
+                if (A.h_io != nullptr && mode != 4) A.h_io[s * sl.n_chunks + cur.q] = res.h_next;
+                const int live_n = (int)((N - (int64_t)cur.q * 32 < 32) ? (N - (int64_t)cur.q * 32) : 32);
+                atomicAdd(&sl.n_rhs, res.n_rhs);
+                atomicAdd(&sl.n_acc, res.n_acc);
+                atomicAdd(&sl.n_rej, res.n_rej);
+                atomicAdd(&sl.grain_evals, (unsigned long long)res.n_rhs * (unsigned long long)live_n);
+                if (res.status) atomicMax(&sl.status, res.status);
             }
         }
-        __syncthreads();
-
-        DREX_MARK(5)
-        // ---- end of interval: extract_vars -> apply_gbs -> extract_vars ------------------
-        // (minerals.py:464-474, 536-538; utils.py:159-190)
-        double *o_out = A.o_out + s * 9 * N;
-        double *f_out = A.f_out + s * N;
-        const double floor_v = A.gbs_threshold / (double)N;
-        double s1 = sum_clip;  // sum of max(f, 0), carried from the last accepted step
-        if (fast) {
-            double fa[MAXQ];
-            uint32_t slide_mask = 0;
-            double s2 = 0.0, dummy = 0.0;
-#pragma unroll
-            for (int j = 0; j < MAXQ; ++j) {
-                const int64_t g = ((int64_t)warp + j * INT_WARPS) * 32 + lane;
-                fa[j] = (g < N) ? f_cur[g] : 0.0;
-            }
-            if (fused && (!f_active || n_acc == 0)) {
-                // no fraction stage has summed the (unchanged) fractions yet
-                double sc_ = 0.0;
-#pragma unroll
-                for (int j = 0; j < MAXQ; ++j) sc_ += fmax(fa[j], 0.0);
-                block_sum2<INT_BLOCK>(sc_, dummy, sh.red);
-                s1 = sc_;
-                dummy = 0.0;
-            }
-#pragma unroll
-            for (int j = 0; j < MAXQ; ++j) {
-                const int64_t g = ((int64_t)warp + j * INT_WARPS) * 32 + lane;
-                double v = fmax(fa[j], 0.0) / s1;
-                const bool slide = (g < N) && (v < floor_v);
-                slide_mask |= slide ? (1u << j) : 0u;
-                v = slide ? floor_v : v;
-                fa[j] = (g < N) ? v : 0.0;
-                s2 += fa[j];
-            }
-            // no accepted step with the fused first step: the state is still o_in for every grain
-            if (fused && n_acc == 0) slide_mask = 0xffffffffu;
-            block_sum2<INT_BLOCK>(s2, dummy, sh.red);
-            double s3 = 0.0;
-            dummy = 0.0;
-#pragma unroll
-            for (int j = 0; j < MAXQ; ++j) {
-                fa[j] = fmax(fa[j] / s2, 0.0);
-                s3 += fa[j];
-            }
-            block_sum2<INT_BLOCK>(s3, dummy, sh.red);
-#pragma unroll
-            for (int j = 0; j < MAXQ; ++j) {
-                const int64_t g = ((int64_t)warp + j * INT_WARPS) * 32 + lane;
-                if (g < N) f_out[g] = fa[j] / s3;
-            }
-            DREX_MARK(7)  // end-of-interval pass, fraction part (development builds only)
-            // orientations: sliding grains get the interval-start orientation back.  This pass is
-            // pure data movement and latency-bound with one chunk of loads in flight per thread,
-            // so when the rows are 16-byte aligned both candidates of a chunk -- the new
-            // orientation (9 rows of the chunked buffer, contiguous) and the interval-start one
-            // (9 rows of o_in) -- come in by TMA bulk copies, two chunks ahead, into the two halves
-            // of the warp's stage; no registers are tied up by loads in flight.
-            const bool rows_aligned = ((N & 1) == 0) && ((reinterpret_cast<uintptr_t>(o_in) & 15) == 0);
-            if (rows_aligned) {
-                // jj: index of the chunk among this warp's chunks (bit of slide_mask).  The o_in rows
-                // are fetched only for chunks in which some grain slides: enstatite never does
-                // (its fractions stay 1/N), olivine not before the texture has evolved.
-                auto issue_end = [&](int64_t q, int half, int jj) {
-                    const int64_t g0 = q * 32;
-                    const uint32_t row_bytes = (uint32_t)(((N - g0 < 32) ? (N - g0) : 32) * sizeof(double));
-                    uint64_t *bar = half ? &sh.mbar2[warp] : mbar;
-                    double *dst = stage + half * 18 * 32;
-                    const bool need = __any_sync(0xffffffffu, ((slide_mask >> jj) & 1u) != 0);
-                    if (lane == 0)
-                        mbar_expect_tx(bar, (uint32_t)(9 * 32 * sizeof(double)) + (need ? 9 * row_bytes : 0u));
-                    __syncwarp();
-                    if (need && lane < 9) bulk_g2s(dst + (9 + lane) * 32, o_in + lane * N + g0, row_bytes, bar);
-                    if (lane == 9) bulk_g2s(dst, yk_cur + q * CHUNK_DOUBLES, (uint32_t)(9 * 32 * sizeof(double)), bar);
-                };
-                if (warp < n_chunks) issue_end(warp, 0, 0);
-                if (warp + INT_WARPS < n_chunks) issue_end(warp + INT_WARPS, 1, 1);
-                int j = 0;
-                for (int64_t q = warp; q < n_chunks; q += INT_WARPS, ++j) {
-                    const int64_t g = q * 32 + lane;
-                    const int half = j & 1;
-                    if (half) {
-                        mbar_wait(&sh.mbar2[warp], mbar2_parity);
-                        mbar2_parity ^= 1u;
-                    } else {
-                        mbar_wait(mbar, mbar_parity);
-                        mbar_parity ^= 1u;
-                    }
-                    const double *base = stage + half * 18 * 32 + lane;
-                    const bool sl = ((slide_mask >> j) & 1u) != 0;
-                    double a[9];
-#pragma unroll
-                    for (int c = 0; c < 9; ++c) a[c] = sl ? base[(9 + c) * 32] : base[c * 32];
-                    clip9(a);
-                    // generic-proxy loads, then an async-proxy overwrite of the same rows: the
-                    // proxy fence orders them
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    __syncwarp();
-                    if (q + 2 * INT_WARPS < n_chunks) issue_end(q + 2 * INT_WARPS, half, j + 2);
-                    if (g < N) {
-#pragma unroll
-                        for (int c = 0; c < 9; ++c) o_out[c * N + g] = a[c];
-                    }
-                }
-            } else {
-            // pipelined so the next chunk's loads overlap this chunk's stores
-            double an[9];
-            {
-                const int64_t g0 = (int64_t)warp * 32 + lane;
-                const bool ok = warp < n_chunks && g0 < N;
-                const bool sl = (slide_mask & 1u) != 0;
-                const double *blk = yk_cur + (int64_t)warp * CHUNK_DOUBLES + lane;
-#pragma unroll
-                for (int c = 0; c < 9; ++c) an[c] = ok ? (sl ? o_in[c * N + g0] : blk[c * 32]) : 0.0;
-            }
-            int j = 0;
-            for (int64_t q = warp; q < n_chunks; q += INT_WARPS, ++j) {
-                const int64_t g = q * 32 + lane;
-                double a[9];
-#pragma unroll
-                for (int c = 0; c < 9; ++c) a[c] = an[c];
-                {
-                    const int64_t gn = (q + INT_WARPS) * 32 + lane;
-                    const bool ok = (q + INT_WARPS) < n_chunks && gn < N;
-                    const bool sl = ((slide_mask >> (j + 1)) & 1u) != 0;
-                    const double *blk = yk_cur + (q + INT_WARPS) * CHUNK_DOUBLES + lane;
-#pragma unroll
-                    for (int c = 0; c < 9; ++c) an[c] = ok ? (sl ? o_in[c * N + gn] : blk[c * 32]) : 0.0;
-                }
-                clip9(a);
-                if (g < N) {
-#pragma unroll
-                    for (int c = 0; c < 9; ++c) o_out[c * N + g] = a[c];
-                }
-            }
-            }
-        } else {
-            double s2 = 0.0, dummy = 0.0;
-            for (int64_t g = tid; g < N; g += INT_BLOCK) {
-                double fa = fmax(f_cur[g], 0.0) / s1;
-                const bool slide = fa < floor_v;
-                double a[9];
-#pragma unroll
-                for (int c = 0; c < 9; ++c)
-                    a[c] = slide ? o_in[c * N + g] : yk_cur[(g >> 5) * CHUNK_DOUBLES + c * 32 + (g & 31)];
-#pragma unroll
-                for (int c = 0; c < 9; ++c) o_out[c * N + g] = clip1(a[c]);
-                fa = slide ? floor_v : fa;
-                fs[g] = fa;
-                s2 += fa;
-            }
-            block_sum2<INT_BLOCK>(s2, dummy, sh.red);
-            double s3 = 0.0;
-            dummy = 0.0;
-            for (int64_t g = tid; g < N; g += INT_BLOCK) {
-                const double fb = fmax(fs[g] / s2, 0.0);
-                fs[g] = fb;
-                s3 += fb;
-            }
-            block_sum2<INT_BLOCK>(s3, dummy, sh.red);
-            for (int64_t g = tid; g < N; g += INT_BLOCK) f_out[g] = fs[g] / s3;
+        // the stores above, then the completion count: the warp that sees the last one finishes
+        __threadfence_block();
+        __syncwarp();
+        int d = 0;
+        if (lane == 0) d = atomicAdd(&sl.done, 1);
+        d = __shfl_sync(0xffffffffu, d, 0);
+        if (d == sl.n_chunks - 1) {
+            __threadfence_block();
+            finalize_system(A, sl, psum_base + (int64_t)(cur.seq % INT_NCTX) * A.chunk_cap, lane);
         }
-        if (tid == 0) {
-            for (int c = 0; c < 9; ++c) A.F[s * 9 + c] = sh.F[c];
-            if (A.h_io) A.h_io[s] = sh.h;
-            A.status[s] = status;
-            if (A.n_rhs) A.n_rhs[s] = n_rhs;
-            if (A.n_accept) A.n_accept[s] = n_acc;
-            if (A.n_reject) A.n_reject[s] = n_rej;
+        if (nxt.seq == -2) {
+            nxt = grab_chunk(sh, true, lane);
+            if (nxt.seq >= 0) prefetch(nxt);
         }
-        DREX_MARK(6)  // end-of-interval pass
+        cur = nxt;
     }
-#ifdef DREX_PHASE_TIMERS
-    if (threadIdx.x == 0) {
-        ptimer[7] += clock64() - pmark;  // waiting for the launch to end is not seen; tail only
-        unsigned long long *out = reinterpret_cast<unsigned long long *>(A.queue) + 8;
-        for (int i = 0; i < 8; ++i) atomicAdd(out + i, (unsigned long long)ptimer[i]);
-    }
-#endif
 }
 
 }  // namespace drex

@@ -69,6 +69,20 @@ def random_orientations(n_systems, n_grains, seed, device):
     return R.reshape(n_systems, n_grains, 3, 3)
 
 
+def _on_own_device(method):
+    """Run a ParticleEnsemble method with the ensemble's GPU as the current CUDA device: the
+    library sizes its launches from cudaGetDevice() and the binding passes torch's current
+    stream, both of which belong to the CURRENT device, not to the tensors' device."""
+    import functools
+
+    @functools.wraps(method)
+    def wrapper(self, *args, **kwargs):
+        with self._torch.cuda.device(self.device):
+            return method(self, *args, **kwargs)
+
+    return wrapper
+
+
 class ParticleEnsemble:
     """P particles x len(phases) mineral phases x N grains, resident on one GPU.
 
@@ -122,18 +136,26 @@ class ParticleEnsemble:
         self._weight = torch.tensor([4.0 if ph == 0 else 1.0 for ph in self.phases],
                                     dtype=torch.float32, device=dev).repeat(P)
         self.order = torch.argsort(self._weight, descending=True, stable=True).to(i32)
-        self.h = torch.zeros(S, dtype=f64, device=dev)
-        self.stats = torch.zeros((4, S), dtype=i32, device=dev)  # status, n_rhs, n_accept, n_reject
+        # the integrator steps chunks of 32 grains independently: one carried step per chunk
+        self.n_chunks = (N + 31) // 32
+        self.h = torch.zeros((S, self.n_chunks), dtype=f64, device=dev)
+        # status, n_rhs, n_accept, n_reject per system, the counters summed over its chunks
+        self.stats = torch.zeros((4, S), dtype=i32, device=dev)
+        self.grain_evals = torch.zeros(S, dtype=torch.int64, device=dev)  # per-grain right-hand sides
+        self._o_alt = None  # second orientation buffer: a launch reads one and writes the other
         self._ws = None
-        self.total_rhs = 0
-        self.total_steps = 0
+        self._host_dirty = True  # update_host: the host copy of the state has not been uploaded
+        self.total_rhs = 0    # right-hand sides x grains, accumulated by update(check=True)
+        self.total_steps = 0  # accepted steps summed over chunks
 
     # -- layout --------------------------------------------------------------------------
+    @_on_own_device
     def _pack(self, aos, soa):
         lib, torch = _lib.load(), self._torch
         S, N = soa.shape[0], soa.shape[2]
         _lib.check(lib.drex_pack_soa_f64(_lib.ptr(aos), _lib.ptr(soa), S, N, _lib.stream_ptr(torch)))
 
+    @_on_own_device
     def orientations(self):
         """Current orientations as [P, n_phases, N, 3, 3] (device tensor, AoS like the reference)."""
         lib, torch = _lib.load(), self._torch
@@ -151,13 +173,19 @@ class ParticleEnsemble:
 
     # -- integration -----------------------------------------------------------------------
     def tolerances(self, rtol=1e-6, atol_abs=1e-4, atol_rel=1e-6, first_step_frac=0.0,
-                   max_step_frac=0.0, max_steps=100000):
+                   max_step_frac=0.0, max_steps=100000, atol_abs_F=None, atol_abs_f=None):
+        """Error weights atol_abs + (atol_rel + rtol) |y| (defaults: minerals.py:523-524);
+        `atol_abs` applies to the orientations and, unless given separately, to the
+        deformation gradient (`atol_abs_F`) and the volume fractions (`atol_abs_f`)."""
         tol = _lib.DrexTolerances()
         tol.rtol, tol.atol_abs, tol.atol_rel = rtol, atol_abs, atol_rel
+        tol.atol_abs_F = atol_abs if atol_abs_F is None else atol_abs_F
+        tol.atol_abs_f = atol_abs if atol_abs_f is None else atol_abs_f
         tol.first_step_frac, tol.max_step_frac = first_step_frac, max_step_frac
         tol.max_steps, tol.method = max_steps, 0
         return tol
 
+    @_on_own_device
     def update(self, t0, t1, L_nodes, kind=_lib.L_CONSTANT, tol=None, check=True):
         """Advance every particle from t0[p] to t1[p] (device tensors [P] or floats).
 
@@ -184,18 +212,17 @@ class ParticleEnsemble:
         prm = _lib.DrexParams(float(p["stress_exponent"]), float(p["deformation_exponent"]),
                               float(p["nucleation_efficiency"]), float(p["gbm_mobility"]),
                               float(p["gbs_threshold"]))
-        if self._ws is None:
-            nbytes = lib.drex_integrate_workspace_bytes(self.S, self.N, dev.index or 0)
-            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self._workspace()
         Pp = _lib.ptr
         m, mh = self.meta, self.meta_host
         _lib.check(lib.drex_integrate_f64(
             self.S, self.P, self.N, Pp(m[0]), Pp(m[1]), Pp(m[2]), Pp(m[3]), Pp(self.vol_frac),
-            Pp(mh[1]), Pp(mh[2]), Pp(mh[3]), Pp(self.F), Pp(self.o), Pp(self.f), Pp(self.o),
-            Pp(self.f), Pp(t0), Pp(t1), int(kind), K, Pp(L_nodes), ctypes.byref(prm),
-            ctypes.byref(tol), Pp(self.h), Pp(self.order), Pp(self.stats[0]), Pp(self.stats[1]),
-            Pp(self.stats[2]), Pp(self.stats[3]), Pp(self._ws), self._ws.numel(),
-            _lib.stream_ptr(torch)))
+            Pp(mh[1]), Pp(mh[2]), Pp(mh[3]), Pp(self.F), Pp(self.o), Pp(self.f), None,
+            Pp(self._o_alt), Pp(self.f), Pp(t0), Pp(t1), int(kind), K, Pp(L_nodes),
+            ctypes.byref(prm), ctypes.byref(tol), Pp(self.h), Pp(self.order), Pp(self.stats[0]),
+            Pp(self.stats[1]), Pp(self.stats[2]), Pp(self.stats[3]), Pp(self.grain_evals),
+            Pp(self._ws), self._ws.numel(), _lib.stream_ptr(torch)))
+        self.o, self._o_alt = self._o_alt, self.o
         # next launch: systems that needed the most right-hand sides go first
         cost = self.stats[1].to(torch.float32) * self._weight
         self.order = torch.argsort(cost, descending=True, stable=True).to(torch.int32)
@@ -207,12 +234,29 @@ class ParticleEnsemble:
                 raise _err.IterationError(
                     f"{bad.size} system(s) failed; first: particle {s // self.n_phases}, phase slot "
                     f"{s % self.n_phases}: {_lib.STATUS_MESSAGES.get(int(stats[0, s]))}")
-            self.total_rhs += int(stats[1].sum())
+            self.total_rhs += int(self.grain_evals.sum().item())
             self.total_steps += int(stats[2].sum())
         return self.stats[0]
 
+    def _workspace(self):
+        """Workspace and second orientation buffer of the integrator, allocated on first use."""
+        lib, torch = _lib.load(), self._torch
+        if self._ws is None:
+            nbytes = lib.drex_integrate_workspace_bytes(self.S, self.N, self.device.index or 0, 0)
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        if self._o_alt is None:
+            self._o_alt = torch.empty_like(self.o)
+
+    def mark_host_dirty(self):
+        """Tell `update_host` that the caller changed the host copy of the state (orientations,
+        fractions or deformation gradients) since the last call: it is uploaded again before
+        the next integration.  Without this the device copy, which `update_host` keeps current,
+        is used and only the velocity-gradient tables cross the bus on the way in."""
+        self._host_dirty = True
+
+    @_on_own_device
     def update_host(self, h_o, h_f, h_F, t0, t1, L_nodes, kind=_lib.L_CONSTANT, tol=None,
-                    h_stats=None, n_chunks=8):
+                    h_stats=None, n_chunks=8, upload=None):
         """Advance particles whose state lives in (pinned) HOST memory in the reference's
         layout and write the new state back: the call a geodynamics code makes once per
         model time step (cf. the Fluidity coupling, examples/fluidity/corner2d).
@@ -224,6 +268,11 @@ class ParticleEnsemble:
         three streams so the host->device copy of group i+1, the integration of group i and
         the device->host copy of group i-1 overlap (PCIe is full duplex).  Synchronises
         before returning.
+
+        The device keeps the state it has just written back, so a host copy nobody touched is
+        NOT uploaded again: `upload=None` (default) uploads on the first call, after
+        `mark_host_dirty()`, and when different host buffers are passed; `upload=True/False`
+        forces the choice.  The new state is always copied back to the host.
         """
         lib, torch = _lib.load(), self._torch
         dev, f64 = self.device, torch.float64
@@ -257,9 +306,11 @@ class ParticleEnsemble:
         prm = _lib.DrexParams(float(p["stress_exponent"]), float(p["deformation_exponent"]),
                               float(p["nucleation_efficiency"]), float(p["gbm_mobility"]),
                               float(p["gbs_threshold"]))
-        if self._ws is None:
-            nbytes = lib.drex_integrate_workspace_bytes(S, N, dev.index or 0)
-            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self._workspace()
+        host_id = (h_o.data_ptr(), h_f.data_ptr(), h_F.data_ptr())
+        if upload is None:
+            upload = self._host_dirty or getattr(self, "_host_id", None) != host_id
+        self._host_id = host_id
         h_o3 = h_o.reshape(S, N, 9)
         h_F2 = h_F.reshape(S, 9)
         Pp = _lib.ptr
@@ -274,31 +325,34 @@ class ParticleEnsemble:
             n = s1 - s0
             aos = self._pipe["aos_in"][c % 2][:n]
             aos_out = self._pipe["aos_out"][c % 2][:n]
-            with torch.cuda.stream(s_in):
-                if packed[c % 2] is not None:
-                    s_in.wait_event(packed[c % 2])  # arrival buffer consumed by the pack kernel
-                aos.copy_(h_o3[s0:s1], non_blocking=True)
-                self.f[s0:s1].copy_(h_f[s0:s1], non_blocking=True)
-                self.F[s0:s1].copy_(h_F2[s0:s1], non_blocking=True)
-                ev_in = torch.cuda.Event()
-                ev_in.record(s_in)
+            if upload:
+                with torch.cuda.stream(s_in):
+                    if packed[c % 2] is not None:
+                        s_in.wait_event(packed[c % 2])  # arrival buffer consumed by the pack kernel
+                    aos.copy_(h_o3[s0:s1], non_blocking=True)
+                    self.f[s0:s1].copy_(h_f[s0:s1], non_blocking=True)
+                    self.F[s0:s1].copy_(h_F2[s0:s1], non_blocking=True)
+                    ev_in = torch.cuda.Event()
+                    ev_in.record(s_in)
             with torch.cuda.stream(s_run):
-                s_run.wait_event(ev_in)
                 sp = _lib.stream_ptr(torch)
-                _lib.check(lib.drex_pack_soa_f64(Pp(aos), Pp(self.o[s0:s1]), n, N, sp))
-                packed[c % 2] = torch.cuda.Event()
-                packed[c % 2].record(s_run)
+                if upload:
+                    s_run.wait_event(ev_in)
+                    _lib.check(lib.drex_pack_soa_f64(Pp(aos), Pp(self.o[s0:s1]), n, N, sp))
+                    packed[c % 2] = torch.cuda.Event()
+                    packed[c % 2].record(s_run)
                 _lib.check(lib.drex_integrate_f64(
                     n, self.P, N, Pp(m[0][s0:s1]), Pp(m[1][s0:s1]), Pp(m[2][s0:s1]),
                     Pp(m[3][s0:s1]), Pp(self.vol_frac[s0:s1]), Pp(mh[1][s0:s1]), Pp(mh[2][s0:s1]),
-                    Pp(mh[3][s0:s1]), Pp(self.F[s0:s1]), Pp(self.o[s0:s1]), Pp(self.f[s0:s1]),
-                    Pp(self.o[s0:s1]), Pp(self.f[s0:s1]), Pp(t0), Pp(t1), int(kind), K,
+                    Pp(mh[3][s0:s1]), Pp(self.F[s0:s1]), Pp(self.o[s0:s1]), Pp(self.f[s0:s1]), None,
+                    Pp(self._o_alt[s0:s1]), Pp(self.f[s0:s1]), Pp(t0), Pp(t1), int(kind), K,
                     Pp(L_nodes), ctypes.byref(prm), ctypes.byref(tol), Pp(self.h[s0:s1]), None,
                     Pp(self.stats[0][s0:s1]), Pp(self.stats[1][s0:s1]), Pp(self.stats[2][s0:s1]),
-                    Pp(self.stats[3][s0:s1]), Pp(self._ws), self._ws.numel(), sp))
+                    Pp(self.stats[3][s0:s1]), Pp(self.grain_evals[s0:s1]), Pp(self._ws),
+                    self._ws.numel(), sp))
                 if out_done[c % 2] is not None:
                     s_run.wait_event(out_done[c % 2])  # departure buffer copied out
-                _lib.check(lib.drex_unpack_soa_f64(Pp(self.o[s0:s1]), Pp(aos_out), n, N, sp))
+                _lib.check(lib.drex_unpack_soa_f64(Pp(self._o_alt[s0:s1]), Pp(aos_out), n, N, sp))
                 ev_run = torch.cuda.Event()
                 ev_run.record(s_run)
             with torch.cuda.stream(s_out):
@@ -313,8 +367,11 @@ class ParticleEnsemble:
                 h_stats.copy_(self.stats, non_blocking=True)
         s_out.synchronize()
         main.wait_stream(s_run)
+        self.o, self._o_alt = self._o_alt, self.o  # the device copy stays current
+        self._host_dirty = False
 
     # -- diagnostics -----------------------------------------------------------------------
+    @_on_own_device
     def voigt_averages(self, elastic_tensors=None):
         """Voigt-averaged stiffness per particle, [P, 6, 6] (minerals.voigt_averages for the
         current snapshot of every particle)."""
@@ -331,6 +388,7 @@ class ParticleEnsemble:
                                               _lib.ptr(Cbar), 0, _lib.stream_ptr(torch)))
         return Cbar.reshape(self.P, self.n_phases, 6, 6).sum(dim=1)
 
+    @_on_own_device
     def resample(self, n_samples=None, seeds=None, phase_slot=0, lo=0, hi=None):
         """Volume-weighted resample of the current texture of particles [lo, hi) for one phase
         slot (stats.resample_orientations, stats.py:14-64, called once per particle with
@@ -359,6 +417,7 @@ class ParticleEnsemble:
             _lib.ptr(out_o), _lib.ptr(out_f), _lib.ptr(ws), nbytes, st))
         return out_o, out_f
 
+    @_on_own_device
     def misorientation_indices(self, system, phase_slot=0, batch=256, n_samples=None, seeds=None):
         """M-index of every particle's texture for one phase slot, [P] (device tensor): of
         the full texture, or -- with `n_samples` -- of the volume-weighted resample drawn

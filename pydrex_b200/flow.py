@@ -29,7 +29,8 @@ def chebyshev_lobatto(K):
 def barycentric_interpolate(values, x):
     """Evaluate the Chebyshev-Lobatto interpolant of `values[K, ...]` at x in [0, 1].
 
-    Host mirror of `eval_L` in csrc/drex_integrate.cuh, used to decide K.
+    The interpolant the kernel evaluates (csrc/drex_integrate.cuh, there through its
+    Chebyshev coefficients); used here to decide K.
     """
     values = np.asarray(values, dtype=np.float64)
     K = values.shape[0]
@@ -68,11 +69,18 @@ def tabulate_velocity_gradient(get_velocity_gradient, get_position, t0, t1, rtol
     if not np.isfinite(scale):
         raise ValueError("velocity gradient is not finite on the requested interval")
     tol = rtol * scale
+    # constant / linear are declared from the five nodes AND the four points halfway between
+    # them, so that a feature narrower than the node spacing is not dropped silently
+    xm = 0.5 * (xs[:-1] + xs[1:])
     if np.abs(samples - samples[0]).max() <= tol:
-        return _lib.L_CONSTANT, samples[:1].copy()
-    lin = samples[0][None] + xs[:, None, None] * (samples[-1] - samples[0])[None]
-    if np.abs(samples - lin).max() <= tol:
-        return _lib.L_LINEAR, np.stack([samples[0], samples[-1]])
+        if max(np.abs(L_at(x) - samples[0]).max() for x in xm) <= tol:
+            return _lib.L_CONSTANT, samples[:1].copy()
+    else:
+        lin = samples[0][None] + xs[:, None, None] * (samples[-1] - samples[0])[None]
+        if np.abs(samples - lin).max() <= tol and max(
+                np.abs(L_at(x) - (samples[0] + x * (samples[-1] - samples[0]))).max()
+                for x in xm) <= tol:
+            return _lib.L_LINEAR, np.stack([samples[0], samples[-1]])
     while True:
         K2 = 2 * (K - 1) + 1
         xs2 = chebyshev_lobatto(K2)

@@ -73,18 +73,35 @@ class StiffnessTensors:
         yield self.enstatite
 
 
-def _tolerances(kwargs, span):
+def _tolerances(kwargs, span, n_grains):
     """Map the LSODA keyword arguments of the reference (minerals.py:523-529) onto the
-    device integrator's error weights."""
+    device integrator's error weights.
+
+    `atol` may be a scalar or, like LSODA's, an array over y = [F(9) | orientations(9N) |
+    fractions(N)]; the device integrator keeps one absolute tolerance per BLOCK of y, so an
+    array must be uniform within each block (anything else raises instead of being
+    silently replaced by its minimum)."""
     kw = dict(kwargs)
     rtol = float(kw.pop("rtol", 1e-6))
     if "atol" in kw:
         atol = np.asarray(kw.pop("atol"), dtype=np.float64)
-        if atol.ndim != 0 and atol.size != 1:
-            atol = atol.min()  # per-component tolerances collapse to the tightest
-        atol_abs, atol_rel = float(atol), 0.0
+        if atol.ndim == 0 or atol.size == 1:
+            atol_F = atol_o = atol_f = float(atol.reshape(-1)[0])
+        elif atol.size == 9 + 10 * n_grains:
+            atol = atol.reshape(-1)
+            blocks = (atol[:9], atol[9:9 + 9 * n_grains], atol[9 + 9 * n_grains:])
+            if any(b.min() != b.max() for b in blocks):
+                raise ValueError(
+                    "per-component `atol` must be uniform within the deformation-gradient (9), "
+                    "orientation (9 n_grains) and fraction (n_grains) blocks of the state vector")
+            atol_F, atol_o, atol_f = (float(b[0]) for b in blocks)
+        else:
+            raise ValueError(f"`atol` must be a scalar or have 9 + 10 n_grains = "
+                             f"{9 + 10 * n_grains} entries, not {atol.size}")
+        atol_rel = 0.0
     else:
-        atol_abs, atol_rel = 1e-4, 1e-6  # |y0| * 1e-6 + 1e-4
+        atol_F = atol_o = atol_f = 1e-4  # |y0| * 1e-6 + 1e-4
+        atol_rel = 1e-6
     first_step = kw.pop("first_step", None)
     max_step = kw.pop("max_step", None)
     kw.pop("min_step", None)
@@ -94,7 +111,8 @@ def _tolerances(kwargs, span):
     if kw:
         raise TypeError(f"unsupported integrator options: {sorted(kw)}")
     tol = _lib.DrexTolerances()
-    tol.rtol, tol.atol_abs, tol.atol_rel = rtol, atol_abs, atol_rel
+    tol.rtol, tol.atol_abs, tol.atol_rel = rtol, atol_o, atol_rel
+    tol.atol_abs_F, tol.atol_abs_f = atol_F, atol_f
     tol.first_step_frac = 0.0
     if first_step is not None and span != 0:
         tol.first_step_frac = min(1.0, abs(float(first_step) / span))
@@ -106,9 +124,45 @@ def _tolerances(kwargs, span):
     return tol, first_step is not None
 
 
+def _regime_segments(get_regime, get_position, t0, t1, n_probe=16):
+    """Cut [t0, t1] where `get_regime(t, x(t))` changes.
+
+    The reference evaluates get_regime inside every right-hand side (minerals.py:409-410);
+    the device integrator holds the regime fixed over one launch, so an interval that crosses
+    a regime boundary becomes several launches (boundary located by bisection to 1e-12 of the
+    interval).  Returns [(ta, tb, regime), ...] in time order."""
+    span = t1 - t0
+
+    def regime_at(t):
+        return int(get_regime(t, get_position(t)))
+
+    if span == 0:
+        return [(t0, t1, regime_at(t0))]
+    ts = t0 + span * np.linspace(0.0, 1.0, n_probe + 1)
+    ts[-1] = t0 + span * (1.0 - 1e-12)  # like L(t): the right end is sampled just inside
+    regs = [regime_at(t) for t in ts]
+    cuts = []
+    for i in range(n_probe):
+        if regs[i] == regs[i + 1]:
+            continue
+        lo, hi = ts[i], ts[i + 1]
+        while abs(hi - lo) > 1e-12 * abs(span):
+            mid = 0.5 * (lo + hi)
+            if mid == lo or mid == hi:
+                break
+            if regime_at(mid) == regs[i]:
+                lo = mid
+            else:
+                hi = mid
+        cuts.append(hi)
+    edges = [t0, *cuts, t1]
+    return [(a, b, regime_at(0.5 * (a + b))) for a, b in zip(edges[:-1], edges[1:])]
+
+
 def _integrate_minerals(minerals, params, deformation_gradients, get_velocity_gradient, pathline,
                         get_regime, kwargs):
-    """Advance several phases of ONE particle over one interval in a single launch."""
+    """Advance several phases of ONE particle over one interval (one launch, or one per
+    deformation-regime segment of the interval)."""
     torch = _lib.require_cuda()
     lib = _lib.load()
     time_start, time_end, get_position = pathline
@@ -129,8 +183,6 @@ def _integrate_minerals(minerals, params, deformation_gradients, get_velocity_gr
         if m.phase not in params["phase_assemblage"]:
             _log.warning("skipping %s mineral, phase omitted from configuration", m.phase)
             continue
-        if get_regime is not None:
-            m.regime = get_regime(time_start, get_position(time_start))
         try:
             vol_fracs.append(
                 params["phase_fractions"][list(params["phase_assemblage"]).index(m.phase)])
@@ -148,12 +200,15 @@ def _integrate_minerals(minerals, params, deformation_gradients, get_velocity_gr
                                            get_regime, kwargs))
         return out
 
-    span = float(time_end) - float(time_start)
-    tol, explicit_first = _tolerances(kwargs, span)
-    kind, nodes = _flow.tabulate_velocity_gradient(get_velocity_gradient, get_position,
-                                                   float(time_start), float(time_end))
+    t_a, t_b = float(time_start), float(time_end)
+    if get_regime is not None:
+        segments = _regime_segments(get_regime, get_position, t_a, t_b)
+    else:
+        segments = [(t_a, t_b, None)]
+    tol, explicit_first = _tolerances(kwargs, t_b - t_a, N)
     dev = torch.device("cuda", torch.cuda.current_device())
     S = len(active)
+    n_chunks = (N + 31) // 32
     f64 = torch.float64
     o_aos = torch.as_tensor(np.stack([np.asarray(m.orientations[-1], dtype=np.float64)
                                       for m in active]).reshape(S, N, 9)).to(dev)
@@ -162,38 +217,66 @@ def _integrate_minerals(minerals, params, deformation_gradients, get_velocity_gr
     F_by_mineral = {id(m): F for m, F in zip(minerals, deformation_gradients)}
     F = torch.as_tensor(np.stack([np.asarray(F_by_mineral[id(m)], dtype=np.float64).reshape(9)
                                   for m in active])).to(dev)
-    meta_host = np.array([[0] * S, [int(m.phase) for m in active],
-                          [int(m.fabric) for m in active], [int(m.regime) for m in active]],
-                         dtype=np.int32)
-    meta = torch.as_tensor(meta_host).to(dev)
     vf = torch.tensor([float(v) for v in vol_fracs], dtype=f64, device=dev)
-    t0 = torch.tensor([float(time_start)], dtype=f64, device=dev)
-    t1 = torch.tensor([float(time_end)], dtype=f64, device=dev)
-    Ln = torch.as_tensor(np.ascontiguousarray(nodes, dtype=np.float64).reshape(1, -1, 9)).to(dev)
-    h0 = [0.0 if explicit_first else float(getattr(m, "_h_next", 0.0) or 0.0) for m in active]
-    h_io = torch.tensor(h0, dtype=f64, device=dev)
-    o_soa = torch.empty((S, 9, N), dtype=f64, device=dev)
+    # per-chunk step suggestions carried from the previous call (same interval length assumed;
+    # a step that does not fit the new interval is clamped by the kernel)
+    h_io = torch.zeros((S, n_chunks), dtype=f64, device=dev)
+    if not explicit_first and len(segments) == 1:
+        for k, m in enumerate(active):
+            h_prev = getattr(m, "_h_next", None)
+            if h_prev is not None and np.shape(h_prev) == (n_chunks,):
+                h_io[k] = torch.as_tensor(h_prev)
+    o_start = torch.empty((S, 9, N), dtype=f64, device=dev)  # interval-start orientations, SoA
+    o_cur = o_start
+    o_new = torch.empty_like(o_start)
     stats = torch.zeros((4, S), dtype=torch.int32, device=dev)
-    p = _lib.DrexParams(float(params["stress_exponent"]), float(params["deformation_exponent"]),
-                        float(params["nucleation_efficiency"]), float(params["gbm_mobility"]),
-                        float(params["gbs_threshold"]))
-    ws_bytes = lib.drex_integrate_workspace_bytes(S, N, dev.index or 0)
+    evals = torch.zeros(S, dtype=torch.int64, device=dev)
+    ws_bytes = lib.drex_integrate_workspace_bytes(S, N, dev.index or 0, 0)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     st = _lib.stream_ptr(torch)
     P = _lib.ptr
-    _lib.check(lib.drex_pack_soa_f64(P(o_aos), P(o_soa), S, N, st))
-    _lib.check(lib.drex_integrate_f64(
-        S, 1, N, P(meta[0]), P(meta[1]), P(meta[2]), P(meta[3]), P(vf),
-        P(meta_host[1]), P(meta_host[2]), P(meta_host[3]),
-        P(F), P(o_soa), P(f), P(o_soa), P(f), P(t0), P(t1), int(kind), int(nodes.shape[0]), P(Ln),
-        ctypes.byref(p), ctypes.byref(tol), P(h_io), None,
-        P(stats[0]), P(stats[1]), P(stats[2]), P(stats[3]), P(ws), ws_bytes, st))
-    _lib.check(lib.drex_unpack_soa_f64(P(o_soa), P(o_aos), S, N, st))
-    stats_h = stats.cpu().numpy()
-    for k, m in enumerate(active):
-        if stats_h[0, k] != 0:
-            raise _err.IterationError(
-                f"integration of {m.phase!r} failed: {_lib.STATUS_MESSAGES.get(int(stats_h[0, k]))}")
+    _lib.check(lib.drex_pack_soa_f64(P(o_aos), P(o_start), S, N, st))
+    totals = np.zeros((3, S), dtype=np.int64)
+    total_evals = np.zeros(S, dtype=np.int64)
+    for i_seg, (ta, tb, regime) in enumerate(segments):
+        last = i_seg == len(segments) - 1
+        if regime is not None:
+            for m in active:
+                m.regime = regime
+        kind, nodes = _flow.tabulate_velocity_gradient(get_velocity_gradient, get_position, ta, tb)
+        meta_host = np.array([[0] * S, [int(m.phase) for m in active],
+                              [int(m.fabric) for m in active], [int(m.regime) for m in active]],
+                             dtype=np.int32)
+        meta = torch.as_tensor(meta_host).to(dev)
+        t0 = torch.tensor([ta], dtype=f64, device=dev)
+        t1 = torch.tensor([tb], dtype=f64, device=dev)
+        Ln = torch.as_tensor(np.ascontiguousarray(nodes, dtype=np.float64).reshape(1, -1, 9)).to(dev)
+        # grain-boundary sliding acts once, at the end of the whole interval, against the
+        # orientations at its start (minerals.py:464-474): inner segments run without it
+        p = _lib.DrexParams(float(params["stress_exponent"]), float(params["deformation_exponent"]),
+                            float(params["nucleation_efficiency"]), float(params["gbm_mobility"]),
+                            float(params["gbs_threshold"]) if last else 0.0)
+        if o_new is o_start:  # never write over the interval-start orientations
+            o_new = torch.empty_like(o_start)
+        o_prev = o_start if (last and o_cur is not o_start) else None
+        _lib.check(lib.drex_integrate_f64(
+            S, 1, N, P(meta[0]), P(meta[1]), P(meta[2]), P(meta[3]), P(vf),
+            P(meta_host[1]), P(meta_host[2]), P(meta_host[3]),
+            P(F), P(o_cur), P(f), P(o_prev), P(o_new), P(f), P(t0), P(t1), int(kind),
+            int(nodes.shape[0]), P(Ln), ctypes.byref(p), ctypes.byref(tol), P(h_io), None,
+            P(stats[0]), P(stats[1]), P(stats[2]), P(stats[3]), P(evals), P(ws), ws_bytes, st))
+        stats_h = stats.cpu().numpy()
+        for k, m in enumerate(active):
+            if stats_h[0, k] != 0:
+                raise _err.IterationError(
+                    f"integration of {m.phase!r} failed: "
+                    f"{_lib.STATUS_MESSAGES.get(int(stats_h[0, k]))}")
+        totals += stats_h[1:4]
+        total_evals += evals.cpu().numpy()
+        o_cur, o_new = o_new, o_cur
+        if not last:
+            h_io.zero_()
+    _lib.check(lib.drex_unpack_soa_f64(P(o_cur), P(o_aos), S, N, st))
     o_h = o_aos.cpu().numpy().reshape(S, N, 3, 3)
     f_h = f.cpu().numpy()
     F_h = F.cpu().numpy().reshape(S, 3, 3)
@@ -202,10 +285,12 @@ def _integrate_minerals(minerals, params, deformation_gradients, get_velocity_gr
     for k, m in enumerate(active):
         m.orientations.append(o_h[k].copy())
         m.fractions.append(f_h[k].copy())
-        m._h_next = float(h_h[k])
-        m.n_rhs = getattr(m, "n_rhs", 0) + int(stats_h[1, k])
-        m.n_steps = getattr(m, "n_steps", 0) + int(stats_h[2, k])
-        m.n_rejected = getattr(m, "n_rejected", 0) + int(stats_h[3, k])
+        m._h_next = h_h[k].copy() if len(segments) == 1 else None
+        # counters per grain: right-hand sides and accepted / rejected steps averaged over
+        # the chunks of 32 grains, which step independently
+        m.n_rhs = getattr(m, "n_rhs", 0) + int(round(total_evals[k] / N))
+        m.n_steps = getattr(m, "n_steps", 0) + int(round(totals[1, k] / n_chunks))
+        m.n_rejected = getattr(m, "n_rejected", 0) + int(round(totals[2, k] / n_chunks))
         if get_regime is not None:
             m.regime = get_regime(time_end, get_position(time_end))
         results[id(m)] = F_h[k].copy()
@@ -284,9 +369,10 @@ class Mineral:
         - `deformation_gradient` — 3x3 deformation gradient tensor
         - `get_velocity_gradient` — callable f(t, x) returning a 3x3 matrix
         - `pathline` — (t_start, t_end, get_position) with get_position a callable f(t)
-        - `get_regime` — optional callable f(t, x) returning a `DeformationRegime`; it is
-          sampled at the start of the interval (the device integrator holds the regime
-          fixed over one call) and again at its end to update `self.regime`
+        - `get_regime` — optional callable f(t, x) returning a `DeformationRegime`; the
+          interval is probed for regime changes and cut there (one launch per segment, the
+          device integrator holds the regime fixed over a launch), and it is evaluated once
+          more at the end to update `self.regime`
 
         Keyword arguments understood: `rtol`, `atol`, `first_step`, `max_step` (the LSODA
         options of the reference, minerals.py:523-529) and `max_steps`.

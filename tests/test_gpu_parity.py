@@ -534,28 +534,54 @@ def test_update_host_matches_resident_update(drex):
         nt.assert_array_equal(h_f.numpy(), a.f.cpu().numpy())
         nt.assert_array_equal(h_F.numpy().reshape(a.S, 9), a.F.cpu().numpy())
         nt.assert_array_equal(h_stats[1].numpy(), a.stats[1].cpu().numpy())
+    # The device copy stays current, so an untouched host mirror is not uploaded again: garbage
+    # written to the host buffers WITHOUT mark_host_dirty() is ignored (and overwritten) ...
+    h_f.fill_(123.0)
+    t0 = torch.full((P,), 0.15, dtype=torch.float64)
+    t1 = torch.full((P,), 0.2, dtype=torch.float64)
+    a.update(t0.cuda(), t1.cuda(), Ls)
+    b.update_host(h_o, h_f, h_F, t0, t1, Ls, n_chunks=3)
+    nt.assert_array_equal(h_f.numpy(), a.f.cpu().numpy())
+    nt.assert_array_equal(h_o.numpy(), a.orientations().reshape(a.S, N, 3, 3).cpu().numpy())
+    # ... and after mark_host_dirty() the host state is what gets integrated
+    c = drex.ParticleEnsemble(P, N, TWO_PHASE, seed=4)
+    h_o.copy_(c.orientations().reshape(c.S, N, 3, 3).cpu())
+    h_f.copy_(c.f.cpu())
+    h_F.copy_(c.F.reshape(c.S, 3, 3).cpu())
+    b.mark_host_dirty()
+    b.h.zero_()
+    c.update(t0.cuda(), t1.cuda(), Ls)
+    b.update_host(h_o, h_f, h_F, t0, t1, Ls, n_chunks=3)
+    nt.assert_array_equal(h_o.numpy(), c.orientations().reshape(c.S, N, 3, 3).cpu().numpy())
+    nt.assert_array_equal(h_f.numpy(), c.f.cpu().numpy())
 
 
-def test_generic_memory_path_is_bit_identical(drex):
-    """Ensembles above 5120 grains use through-memory fraction stages instead of the
-    register-resident ones; forcing that path on a small ensemble must not change a bit.
-    Also covers N not a multiple of 32, odd N, and N > 5120 end to end."""
+def test_odd_and_large_ensembles(drex, oracle):
+    """N not a multiple of 32 and odd N (rows not 16-byte aligned: plain loads instead of the
+    TMA prefetch), N below one chunk, N above the old register-path limit: agreement with the
+    oracle's converged LSODA run (mode A) and invariants."""
     import torch
+    from scipy.spatial.transform import Rotation
 
-    for N in (333, 1000):
-        a = drex.ParticleEnsemble(3, N, TWO_PHASE, seed=5)
-        b = drex.ParticleEnsemble(3, N, TWO_PHASE, seed=5)
-        L = torch.zeros((3, 3, 3), dtype=torch.float64)
-        L[:, 1, 0] = torch.tensor([2.0, 1.0, 3.0])
-        tol_a, tol_b = a.tolerances(), b.tolerances()
-        tol_b.method = 0x100
-        for k in range(3):
-            a.update(0.05 * k, 0.05 * (k + 1), L, tol=tol_a)
-            b.update(0.05 * k, 0.05 * (k + 1), L, tol=tol_b)
-        nt.assert_array_equal(a.o.cpu().numpy(), b.o.cpu().numpy())
-        nt.assert_array_equal(a.f.cpu().numpy(), b.f.cpu().numpy())
-        nt.assert_array_equal(a.stats.cpu().numpy(), b.stats.cpu().numpy())
-    # N = 6001 > 5120: the generic path for real; invariants + agreement with the oracle RHS
+    for N in (31, 333, 1000):
+        o0 = np.stack([[Rotation.random(N, random_state=7 * p + k).as_matrix() for k in range(2)]
+                       for p in range(3)])
+        ens = drex.ParticleEnsemble(3, N, TWO_PHASE, orientations=o0)
+        L = np.zeros((3, 3, 3))
+        L[:, 1, 0] = [2.0, 1.0, 3.0]
+        tol = ens.tolerances(rtol=1e-11, atol_abs=1e-13, atol_rel=0.0)
+        for k in range(2):
+            ens.update(0.05 * k, 0.05 * (k + 1), torch.as_tensor(L), tol=tol)
+        o_dev = ens.orientations().cpu().numpy()
+        f_dev = ens.fractions().cpu().numpy()
+        p = 2
+        Fo, oo, fo = np.eye(3), o0[p, 0], np.full(N, 1 / N)
+        for k in range(2):
+            Fo, oo, fo = oracle.update_orientations(
+                oo, fo, 4, 0, 0, TWO_PHASE, Fo, _const(L[p]),
+                (0.05 * k, 0.05 * (k + 1), lambda t: np.zeros(3)), rtol=1e-10, atol=1e-12)
+        nt.assert_allclose(o_dev[p, 0], oo, rtol=0, atol=2e-8)
+        nt.assert_allclose(f_dev[p, 0], fo, rtol=1e-7, atol=1e-12)
     N = 6001
     c = drex.ParticleEnsemble(2, N, TWO_PHASE, seed=9)
     L = torch.zeros((2, 3, 3), dtype=torch.float64)
@@ -567,21 +593,49 @@ def test_generic_memory_path_is_bit_identical(drex):
     assert np.abs(np.einsum("pkgij,pkglj->pkgil", o, o) - np.eye(3)).max() < 5e-3
 
 
-def test_pipelined_integrator_matches_one_system_kernel(drex):
-    """The two-slot warp-specialised kernel (drex_integrate_pipe.cuh, method bit 0x400) against
-    the one-system-per-CTA kernel (0x200): same per-grain arithmetic, so orientations and F are
-    bit-identical; the fraction sums are added in a different (fixed) order, so fractions agree
-    to rounding.  Covers odd N, N below one chunk, both phases, carried step sizes, a
-    time-dependent (Chebyshev) L table, slot reuse (more systems than CTA slots), the
-    diffusion regime and run-to-run determinism."""
+def test_chunk_integrator_matches_its_numpy_model(drex, oracle):
+    """The kernel against the numpy restatement of ITS algorithm (oracle/device_model.py:
+    decoupled replicator form, one adaptive step sequence per chunk of 32 grains) at the
+    reference's default tolerances: same step decisions, so the states agree far inside the
+    tolerance and the right-hand-side counts match.  Also: more systems than CTAs (slot reuse),
+    Chebyshev L(t), run-to-run determinism (every sum is formed in a fixed order)."""
     import torch
+    from scipy.spatial.transform import Rotation
 
+    from oracle import device_model
     from pydrex_b200 import _lib
 
-    def run(method, P, N, n_updates, kind=_lib.L_CONSTANT, regime=4):
+    P, N = 3, 333
+    o0 = np.stack([[Rotation.random(N, random_state=3 * p + k).as_matrix() for k in range(2)]
+                   for p in range(P)])
+    ens = drex.ParticleEnsemble(P, N, TWO_PHASE, orientations=o0)
+    L = np.zeros((P, 3, 3))
+    L[:, 1, 0] = [1.0, 2.0, 3.0]
+    L[:, 0, 2] = 0.5
+    evals = 0
+    for k in range(3):
+        ens.update(0.05 * k, 0.05 * (k + 1), torch.as_tensor(L))
+        evals += int(ens.grain_evals[2 * 1].item())
+    o_dev = ens.orientations().cpu().numpy()[1, 0]
+    f_dev = ens.fractions().cpu().numpy()[1, 0]
+    F, o, f, h, n_model = np.eye(3), o0[1, 0], np.full(N, 1 / N), None, 0
+    for k in range(3):
+        st = {}
+        F, o, f = device_model.update_orientations(
+            o, f, 4, 0, 0, TWO_PHASE, F, _const(L[1]), (0.05 * k, 0.05 * (k + 1), lambda t: np.zeros(3)),
+            stats=st, h_carry=h)
+        h = st["h"]
+        live = np.minimum(32, N - 32 * np.arange(len(h)))
+        n_model += int((st["n_rhs"] * live).sum())
+    agree = np.isclose(f_dev, f, rtol=0.2)  # same GBS decision
+    assert agree.mean() > 0.995
+    assert np.abs(o_dev - o)[agree].max() <= 1e-6
+    nt.assert_allclose(f_dev[agree], f[agree], rtol=1e-5)
+    assert abs(evals - n_model) <= 0.05 * n_model, (evals, n_model)
+    nt.assert_allclose(ens.deformation_gradients().cpu().numpy()[1], F, atol=1e-12)
+
+    def run(P, N, n_updates, kind=_lib.L_CONSTANT, regime=4):
         e = drex.ParticleEnsemble(P, N, TWO_PHASE, seed=5, regimes=(regime, regime))
-        tol = e.tolerances()
-        tol.method = method
         for k in range(n_updates):
             if kind == _lib.L_CONSTANT:
                 L = torch.zeros((P, 3, 3), dtype=torch.float64)
@@ -591,69 +645,107 @@ def test_pipelined_integrator_matches_one_system_kernel(drex):
                 L = torch.zeros((P, 5, 3, 3), dtype=torch.float64)
                 L[:, :, 1, 0] = torch.linspace(1.0, 3.0, P)[:, None] * (1.0 + 0.5 * (k + x))[None, :]
                 L[:, :, 0, 2] = 0.3 * x[None, :]
-            e.update(0.05 * k, 0.05 * (k + 1), L, kind=kind, tol=tol)
+            e.update(0.05 * k, 0.05 * (k + 1), L, kind=kind)
         return e
 
-    cases = [(3, 333, 4, _lib.L_CONSTANT, 4), (2, 31, 3, _lib.L_CONSTANT, 4),
-             (5, 1000, 3, _lib.L_CHEBYSHEV, 4), (200, 96, 3, _lib.L_CONSTANT, 4),
-             (3, 200, 2, _lib.L_CONSTANT, 1)]
-    for P, N, n, kind, regime in cases:
-        a, b, c = (run(m, P, N, n, kind, regime) for m in (0x200, 0x400, 0x400))
+    for P, N, n, kind, regime in [(3, 333, 4, _lib.L_CONSTANT, 4), (2, 31, 3, _lib.L_CONSTANT, 4),
+                                  (5, 1000, 3, _lib.L_CHEBYSHEV, 4), (400, 96, 3, _lib.L_CONSTANT, 4),
+                                  (3, 200, 2, _lib.L_CONSTANT, 1)]:
+        a, b = run(P, N, n, kind, regime), run(P, N, n, kind, regime)
         nt.assert_array_equal(a.o.cpu().numpy(), b.o.cpu().numpy())
+        nt.assert_array_equal(a.f.cpu().numpy(), b.f.cpu().numpy())
         nt.assert_array_equal(a.F.cpu().numpy(), b.F.cpu().numpy())
-        nt.assert_allclose(b.f.cpu().numpy(), a.f.cpu().numpy(), rtol=1e-12, atol=0)
-        # same accepted / rejected steps and status; right-hand sides are counted differently (the
-        # one-system kernel fuses the initial slope into the first step and repeats it when
-        # that step is rejected)
-        sa, sb = a.stats.cpu().numpy(), b.stats.cpu().numpy()
-        nt.assert_array_equal(sa[[0, 2, 3]], sb[[0, 2, 3]])
-        assert (sa[1] >= sb[1]).all() and (sa[1] - sb[1] <= sa[3]).all()
-        assert int(a.stats[1].sum()) > 4 * P  # steps were taken
-        # fixed summation order: a second run reproduces every bit
-        nt.assert_array_equal(b.o.cpu().numpy(), c.o.cpu().numpy())
-        nt.assert_array_equal(b.f.cpu().numpy(), c.f.cpu().numpy())
-    # failure status travels through the pipelined kernel too
+        nt.assert_array_equal(a.stats.cpu().numpy(), b.stats.cpu().numpy())
+        assert int(a.stats[0].abs().sum()) == 0
+        nt.assert_allclose(a.f.sum(dim=-1).cpu().numpy(), 1.0, atol=1e-13)
+    # failure status: L = 0 gives a zero strain-rate scale, hence a non-finite right-hand side
     e = drex.ParticleEnsemble(2, 64, TWO_PHASE, seed=1)
-    tol = e.tolerances()
-    tol.method = 0x400
     with pytest.raises(drex.IterationError, match="non-finite"):
-        e.update(0.0, 0.1, torch.zeros((2, 3, 3), dtype=torch.float64), tol=tol)
-
-
-def test_fused_first_step_matches_separate_initial_pass(drex):
-    """The one-system kernel folds the initial slope of an interval into its first step (four
-    stages per chunk straight from o_in) when the rows are 16-byte aligned; method bit 0x800
-    keeps the separate pass.  Same arithmetic per grain: orientations and F identical, fractions
-    to rounding (the fraction sums at t0 are grouped differently).  Odd N takes the separate
-    pass on both sides and must not change at all."""
-    import torch
-
-    for P, N in ((3, 334), (2, 5000), (3, 333)):
-        ens = [drex.ParticleEnsemble(P, N, TWO_PHASE, seed=11) for _ in range(2)]
-        tols = [e.tolerances() for e in ens]
-        tols[0].method, tols[1].method = 0x200, 0x200 | 0x800
-        L = torch.zeros((P, 3, 3), dtype=torch.float64)
-        L[:, 1, 0] = torch.linspace(1.0, 3.0, P)
-        L[:, 0, 2] = 0.5
-        for k in range(4):
-            for e, tol in zip(ens, tols):
-                e.update(0.05 * k, 0.05 * (k + 1), L, tol=tol)
-        a, b = ens
-        nt.assert_allclose(a.o.cpu().numpy(), b.o.cpu().numpy(), rtol=0, atol=1e-13)
-        nt.assert_allclose(a.F.cpu().numpy(), b.F.cpu().numpy(), rtol=0, atol=1e-15)
-        nt.assert_allclose(a.f.cpu().numpy(), b.f.cpu().numpy(), rtol=1e-12, atol=0)
-        sa, sb = a.stats.cpu().numpy(), b.stats.cpu().numpy()
-        nt.assert_array_equal(sa[[0, 2, 3]], sb[[0, 2, 3]])
-        if N % 2:
-            nt.assert_array_equal(a.f.cpu().numpy(), b.f.cpu().numpy())
-            nt.assert_array_equal(sa, sb)
-    # a zero-length interval and a failing first step leave the state as extract_vars /
-    # apply_gbs of the input
+        e.update(0.0, 0.1, torch.zeros((2, 3, 3), dtype=torch.float64))
+    # a zero-length interval leaves the state as extract_vars / apply_gbs of the input
     e = drex.ParticleEnsemble(2, 64, TWO_PHASE, seed=1)
     o0 = e.o.clone()
-    e.update(0.3, 0.3, L[:2])
+    L = torch.zeros((2, 3, 3), dtype=torch.float64)
+    L[:, 1, 0] = 2.0
+    e.update(0.3, 0.3, L)
     nt.assert_array_equal(e.o.cpu().numpy(), o0.cpu().numpy())
     nt.assert_allclose(e.f.sum(dim=-1).cpu().numpy(), 1.0, atol=1e-14)
+
+
+def test_in_place_call_and_regime_change_inside_an_interval(drex, oracle):
+    """(1) o_out == o_in through the C ABI (workspace sized with in_place = 1) gives the same
+    bits as separate buffers.  (2) get_regime changing inside an interval: the interval is cut
+    at the change (minerals.py:409-410 evaluates it in every right-hand side) and grain-boundary
+    sliding still acts once, against the orientations at the start of the whole interval --
+    checked against the oracle driven with the same callable."""
+    import ctypes
+
+    import torch
+
+    from pydrex_b200 import _lib
+
+    lib = _lib.load()
+    P, N = 2, 200
+    ens = drex.ParticleEnsemble(P, N, TWO_PHASE, seed=21)
+    o_in, f_in, F_in = ens.o.clone(), ens.f.clone(), ens.F.clone()
+    L = torch.zeros((P, 1, 9), dtype=torch.float64, device="cuda")
+    L[:, 0, 3] = 2.0
+    ens.update(0.0, 0.1, L.reshape(P, 3, 3))
+    tol = ens.tolerances()
+    prm = _lib.DrexParams(1.5, 3.5, 5.0, 125.0, 0.3)
+    nbytes = lib.drex_integrate_workspace_bytes(ens.S, N, 0, 1)
+    assert nbytes > ens.S * 9 * N * 8
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    t0 = torch.zeros(P, dtype=torch.float64, device="cuda")
+    t1 = torch.full((P,), 0.1, dtype=torch.float64, device="cuda")
+    status = torch.zeros(ens.S, dtype=torch.int32, device="cuda")
+    Pp, m, mh = _lib.ptr, ens.meta, ens.meta_host
+    _lib.check(lib.drex_integrate_f64(
+        ens.S, P, N, Pp(m[0]), Pp(m[1]), Pp(m[2]), Pp(m[3]), Pp(ens.vol_frac), Pp(mh[1]), Pp(mh[2]),
+        Pp(mh[3]), Pp(F_in), Pp(o_in), Pp(f_in), None, Pp(o_in), Pp(f_in), Pp(t0), Pp(t1), 0, 1, Pp(L),
+        ctypes.byref(prm), ctypes.byref(tol), None, None, Pp(status), None, None, None, None, Pp(ws),
+        nbytes, _lib.stream_ptr(torch)))
+    torch.cuda.synchronize()
+    assert int(status.abs().sum()) == 0
+    nt.assert_array_equal(o_in.cpu().numpy(), ens.o.cpu().numpy())
+    nt.assert_array_equal(f_in.cpu().numpy(), ens.f.cpu().numpy())
+    nt.assert_array_equal(F_in.cpu().numpy(), ens.F.cpu().numpy())
+    # a too-small workspace for an in-place call is refused, not silently wrong
+    small = lib.drex_integrate_workspace_bytes(ens.S, N, 0, 0)
+    rc = lib.drex_integrate_f64(
+        ens.S, P, N, Pp(m[0]), Pp(m[1]), Pp(m[2]), Pp(m[3]), Pp(ens.vol_frac), Pp(mh[1]), Pp(mh[2]),
+        Pp(mh[3]), Pp(F_in), Pp(o_in), Pp(f_in), None, Pp(o_in), Pp(f_in), Pp(t0), Pp(t1), 0, 1, Pp(L),
+        ctypes.byref(prm), ctypes.byref(tol), None, None, Pp(status), None, None, None, None, Pp(ws),
+        small, _lib.stream_ptr(torch))
+    assert rc == _lib.DREX_E_WORKSPACE
+
+    # (2) dislocation creep until t = 0.13, diffusion creep afterwards
+    Lm = np.array([[0.0, 0, 0], [2, 0, 0], [0, 0, 0]])
+    get_regime = lambda t, x: 4 if t < 0.13 else 1  # noqa: E731
+    mnr = drex.Mineral(0, 0, 4, n_grains=N, seed=5)
+    o0, f0 = mnr.orientations[0].copy(), mnr.fractions[0].copy()
+    F = mnr.update_orientations(OL_PARAMS, np.eye(3), _const(Lm), (0.0, 0.2, lambda t: np.zeros(3)),
+                                get_regime=get_regime, **TIGHT)
+    assert mnr.regime == 1
+    # oracle: the same two pieces without sliding in between, then sliding against o0
+    nogbs = dict(OL_PARAMS, gbs_threshold=0.0)
+    Fo, oo, fo = oracle.update_orientations(o0, f0, 4, 0, 0, nogbs, np.eye(3), _const(Lm),
+                                            (0.0, 0.13, lambda t: np.zeros(3)), rtol=1e-10, atol=1e-12)
+    Fo, oo, fo = oracle.update_orientations(oo, fo, 1, 0, 0, nogbs, Fo, _const(Lm),
+                                            (0.13, 0.2, lambda t: np.zeros(3)), rtol=1e-10, atol=1e-12)
+    oo, fo = oracle.apply_gbs(oo, fo, 0.3, o0, N)
+    nt.assert_allclose(mnr.orientations[-1], np.clip(oo, -1, 1), rtol=0, atol=5e-8)
+    nt.assert_allclose(mnr.fractions[-1], fo / fo.sum(), rtol=1e-7, atol=1e-12)
+    nt.assert_allclose(F, Fo, rtol=1e-9, atol=1e-12)
+    # per-component atol: block-uniform arrays are honoured, anything else raises
+    atol = np.concatenate([np.full(9, 1e-12), np.full(9 * N, 1e-13), np.full(N, 1e-13)])
+    m2 = drex.Mineral(0, 0, 4, n_grains=N, seed=5)
+    m2.update_orientations(OL_PARAMS, np.eye(3), _const(Lm), (0.0, 0.05, lambda t: np.zeros(3)),
+                           rtol=1e-11, atol=atol)
+    atol[20] = 1e-9
+    with pytest.raises(ValueError, match="uniform within"):
+        m2.update_orientations(OL_PARAMS, np.eye(3), _const(Lm), (0.05, 0.1, lambda t: np.zeros(3)),
+                               rtol=1e-11, atol=atol)
 
 
 def test_backward_interval_and_status_codes(drex):
@@ -773,7 +865,7 @@ def test_carried_step_longer_than_next_interval(drex, oracle):
     ens.update(0.2, 0.21, Lt)  # much shorter than the carried steps
     assert np.all(np.abs(h_after_long) > 0.01)
     assert int(ens.stats[3].sum()) == 0  # nothing to reject on a 0.01 interval
-    assert int(ens.stats[2].max()) == 1  # one accepted step each
+    assert int(ens.stats[2].max()) == ens.n_chunks  # one accepted step per chunk
     assert np.all(ens.h.cpu().numpy() > 0)
     o_dev = ens.orientations().cpu().numpy()
     Fo, oo, fo = np.eye(3), o0[0, 0], np.full(N, 1 / N)

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
     assert sorted(_lib.EXPORTS) == declared
     major, minor = ctypes.c_int(), ctypes.c_int()
     assert lib.drex_version(ctypes.byref(major), ctypes.byref(minor)) == 0
-    assert (major.value, minor.value) == (0, 1)
+    assert (major.value, minor.value) == (0, 2)
 
 
 def test_host_side_argument_validation_without_gpu():
