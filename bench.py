@@ -441,7 +441,7 @@ def run_gpu(args):
             "algorithmic_flop_per_eval": F_ALG, "evals_per_launch": evals_per_launch,
             "launch_ms": kernel_ms,
             "hbm": {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": hbm_gbs / hbm_peak, "bytes_per_grain_attempt": bytes_per_attempt,
+                    "frac": hbm_gbs / hbm_peak, "bytes_per_grain_interval": 160.0,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)"
                     if peaks else "fallback 6650 GB/s"},
             "traffic": traffic,

@@ -196,8 +196,10 @@ size_t drex_integrate_workspace_bytes(int64_t S, int64_t N, int device, int in_p
  *                   calls run with gbs_threshold = 0, the last one with o_prev = the
  *                   orientations at the start of the whole interval.  Must not alias o_out.
  * L_kind, K, L_nodes [P][K][9]  velocity-gradient provider (DREX_L_*)
- * h_io [S][ceil(N/32)]  per chunk, in: first trial step (<= 0: use first_step_frac); out: next
- *                   suggested step; may be NULL
+ * h_io [S][ceil(N/32)]  per chunk, in: first trial step (0: use first_step_frac); out: next
+ *                   suggested step; may be NULL.  Steps are carried as STRAIN increments (time
+ *                   step x max |eig sym L| at the interval end), so that a suggestion made at
+ *                   one strain rate is still right when the next interval is faster or slower
  * order [S]         optional (may be NULL) permutation of 0..S-1: the order in which the
  *                   persistent CTAs pull systems from the work queue.  Results do not
  *                   depend on it; putting expensive systems first (longest-processing-

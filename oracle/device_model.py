@@ -29,8 +29,6 @@ The algorithm
   interval-start orientations, extract_vars.
 """
 
-import ctypes
-
 import numpy as np
 
 from . import oracle
@@ -129,8 +127,14 @@ def update_orientations(orientations, fractions, regime, phase, fabric, params,
     span = t1 - t0
     t = np.full(n_chunks, float(t0))
     h = np.full(n_chunks, float(span))
+    def scale_at(tt):
+        sv = oracle.lib().oracle_strain_rate_max(np.ascontiguousarray(get_L(tt)).ctypes.data_as(oracle._dp))
+        return sv if (sv > 0 and np.isfinite(sv)) else 1.0
+
     if h_carry is not None and len(h_carry) == n_chunks:
-        # a chunk's last proposal of the previous interval (the kernel's per-chunk h_io)
+        # a chunk's last proposal of the previous interval (the kernel's per-chunk h_io),
+        # carried as a STRAIN increment: time step x strain-rate scale
+        h_carry = np.asarray(h_carry) / scale_at(t0)
         ok = np.abs(h_carry) > 0
         hc = np.where(np.abs(h_carry) < abs(span), np.copysign(np.abs(h_carry), span), span)
         h = np.where(ok, plan_step(hc, np.full(n_chunks, float(span))), h)
@@ -183,7 +187,7 @@ def update_orientations(orientations, fractions, regime, phase, fabric, params,
     else:
         raise RuntimeError("max_steps")
     if stats is not None:
-        stats.update(n_rhs=n_rhs, n_acc=n_acc, n_rej=n_rej, h=h_out)
+        stats.update(n_rhs=n_rhs, n_acc=n_acc, n_rej=n_rej, h=h_out * scale_at(t1))
 
     # end of the interval: minerals.py:464-474, 536-538 (utils.py:159-190)
     u = f0 * np.exp(v)

@@ -113,6 +113,11 @@ inline size_t integrate_smem_bytes() {
 
 // Per-CTA scratch: the per-chunk partial sums of the systems in flight.
 inline int64_t integrate_chunk_cap(int64_t N) { return ((N + 31) / 32 + 31) / 32 * 32; }
+// One lane mask per chunk of every system: which grains slide (written by integrate_kernel, read
+// by gbs_restore_kernel).
+inline size_t integrate_mask_bytes(int64_t S, int64_t N) {
+    return align_up((size_t)S * (size_t)((N + 31) / 32) * sizeof(uint32_t), 256);
+}
 inline size_t integrate_scratch_bytes(int slots, int64_t N) {
     return align_up((size_t)slots * drex::INT_NCTX * (size_t)integrate_chunk_cap(N) * sizeof(double), 256);
 }
@@ -149,8 +154,8 @@ int drex_device_info(int device, int *sm_count, int *cc_major, int *cc_minor) {
 int drex_pack_soa_f64(const double *aos, double *soa, int64_t S, int64_t N, void *stream) {
     if (S <= 0 || N <= 0) return DREX_OK;
     if (!aos || !soa) return fail(DREX_E_INVALID, "drex_pack_soa_f64: null pointer");
-    dim3 grid((unsigned)((N + 255) / 256), (unsigned)S);
-    drex::pack_soa_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(aos, soa, S, N);
+    dim3 grid((unsigned)S, (unsigned)((N + drex::LAYOUT_TILE - 1) / drex::LAYOUT_TILE));
+    drex::pack_soa_kernel<<<grid, drex::LAYOUT_TILE, 0, (cudaStream_t)stream>>>(aos, soa, S, N);
     DREX_CUDA_CHECK(cudaGetLastError());
     return DREX_OK;
 }
@@ -158,8 +163,8 @@ int drex_pack_soa_f64(const double *aos, double *soa, int64_t S, int64_t N, void
 int drex_unpack_soa_f64(const double *soa, double *aos, int64_t S, int64_t N, void *stream) {
     if (S <= 0 || N <= 0) return DREX_OK;
     if (!aos || !soa) return fail(DREX_E_INVALID, "drex_unpack_soa_f64: null pointer");
-    dim3 grid((unsigned)((N + 255) / 256), (unsigned)S);
-    drex::unpack_soa_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(soa, aos, S, N);
+    dim3 grid((unsigned)S, (unsigned)((N + drex::LAYOUT_TILE - 1) / drex::LAYOUT_TILE));
+    drex::unpack_soa_kernel<<<grid, drex::LAYOUT_TILE, 0, (cudaStream_t)stream>>>(soa, aos, S, N);
     DREX_CUDA_CHECK(cudaGetLastError());
     return DREX_OK;
 }
@@ -170,7 +175,7 @@ int drex_fluidity_unpack_f64(const double *cpo, int64_t P, int64_t N, double *o_
     if (P == 0) return DREX_OK;
     if (!cpo || !o_soa || !f || !F || !L_prev || !strain)
         return fail(DREX_E_INVALID, "drex_fluidity_unpack_f64: null pointer");
-    dim3 grid((unsigned)((N + 255) / 256 > 0 ? (N + 255) / 256 : 1), (unsigned)P);
+    dim3 grid((unsigned)P, (unsigned)((N + 255) / 256 > 0 ? (N + 255) / 256 : 1));
     drex::fluidity_unpack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(cpo, N, o_soa, f, F, L_prev, strain);
     DREX_CUDA_CHECK(cudaGetLastError());
     return DREX_OK;
@@ -183,7 +188,7 @@ int drex_fluidity_pack_f64(const double *o_soa, const double *f, const double *F
     if (P == 0) return DREX_OK;
     if (!cpo || !o_soa || !f || !F || !strain || !position || !L_new)
         return fail(DREX_E_INVALID, "drex_fluidity_pack_f64: null pointer");
-    dim3 grid((unsigned)((N + 255) / 256 > 0 ? (N + 255) / 256 : 1), (unsigned)P);
+    dim3 grid((unsigned)P, (unsigned)((N + 255) / 256 > 0 ? (N + 255) / 256 : 1));
     drex::fluidity_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(o_soa, f, F, strain, position,
                                                                        L_new, dt, N, cpo);
     DREX_CUDA_CHECK(cudaGetLastError());
@@ -220,7 +225,7 @@ int drex_derivatives_f64(const double *o_soa, const double *f, const double *D, 
     A.S = S; A.N = N;
     const drex::FabricTable T = make_fabric_table(*params);
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid((unsigned)((N + drex::DERIV_BLOCK - 1) / drex::DERIV_BLOCK), (unsigned)S);
+    dim3 grid((unsigned)S, (unsigned)((N + drex::DERIV_BLOCK - 1) / drex::DERIV_BLOCK));
     drex::derivatives_grain_kernel<<<grid, drex::DERIV_BLOCK, 0, st>>>(A, T);
     DREX_CUDA_CHECK(cudaGetLastError());
     drex::derivatives_gbm_kernel<<<(unsigned)S, drex::GBM_BLOCK, 0, st>>>(A);
@@ -268,7 +273,7 @@ size_t drex_integrate_workspace_bytes(int64_t S, int64_t N, int device, int in_p
     int slots = integrate_slots(device);
     if (slots < 1) slots = 1;
     if ((int64_t)slots > S) slots = (int)S;
-    size_t need = 256 + integrate_scratch_bytes(slots, N);
+    size_t need = 256 + integrate_scratch_bytes(slots, N) + integrate_mask_bytes(S, N);
     // o_out == o_in: grain-boundary sliding restores interval-start orientations that the
     // integration has already overwritten, so the call keeps a copy of them here
     if (in_place) need += (size_t)S * 9 * (size_t)N * sizeof(double);
@@ -318,7 +323,8 @@ int drex_integrate_f64(int64_t S, int64_t P, int64_t N, const int32_t *sys_parti
             return fail(DREX_E_INVALID, "drex_integrate_f64: o_prev must not alias o_out");
     }
     const size_t scratch_bytes = integrate_scratch_bytes(slots, N);
-    const size_t need = 256 + scratch_bytes + (aliased ? state_bytes : 0);
+    const size_t mask_bytes = integrate_mask_bytes(S, N);
+    const size_t need = 256 + scratch_bytes + mask_bytes + (aliased ? state_bytes : 0);
     if (!workspace || workspace_bytes < need)
         return fail(DREX_E_WORKSPACE, "drex_integrate_f64: workspace too small (%zu < %zu)",
                     workspace_bytes, need);
@@ -342,19 +348,32 @@ int drex_integrate_f64(int64_t S, int64_t P, int64_t N, const int32_t *sys_parti
     A.queue = (int *)workspace;
     A.scratch = (double *)((char *)workspace + 256);
     A.chunk_cap = integrate_chunk_cap(N);
+    A.slide_mask = (uint32_t *)((char *)workspace + 256 + scratch_bytes);
     DREX_CUDA_CHECK(cudaMemsetAsync(workspace, 0, 256, st));
     if (aliased) {
-        double *copy = (double *)((char *)workspace + 256 + scratch_bytes);
+        double *copy = (double *)((char *)workspace + 256 + scratch_bytes + mask_bytes);
         DREX_CUDA_CHECK(cudaMemcpyAsync(copy, o_in, state_bytes, cudaMemcpyDeviceToDevice, st));
         A.o_in = copy;
         A.o_prev = copy;
     }
     const drex::FabricTable T = make_fabric_table(*params);
+    if (const char *dbg = getenv("DREX_DEBUG_HOSTPTR")) {  // development aid, see watchdog_fire
+        unsigned long long *ptr = (unsigned long long *)strtoull(dbg, nullptr, 0);
+        DREX_CUDA_CHECK(cudaMemcpyToSymbolAsync(drex::g_drex_debug, &ptr, sizeof(ptr), 0,
+                                                cudaMemcpyHostToDevice, st));
+    }
     const size_t dyn_smem = integrate_smem_bytes();
     DREX_CUDA_CHECK(cudaFuncSetAttribute(drex::integrate_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
     drex::integrate_kernel<<<(unsigned)slots, drex::INT_BLOCK, dyn_smem, st>>>(A, T);
     DREX_CUDA_CHECK(cudaGetLastError());
+    if (params->gbs_threshold > 0.0) {  // nothing slides below a threshold of zero
+        int sms = 0;
+        DREX_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        drex::gbs_restore_kernel<<<(unsigned)(8 * sms), drex::RESTORE_BLOCK, 0, st>>>(
+            A.slide_mask, A.o_prev, o_out, S, N);
+        DREX_CUDA_CHECK(cudaGetLastError());
+    }
     return DREX_OK;
 }
 
@@ -771,11 +790,11 @@ int drex_mindex_f32(const double *o_soa, int64_t S, int64_t N, int system_a, int
     DREX_CUDA_CHECK(cudaMemcpyAsync(theory, theory_host, tmax * sizeof(double), cudaMemcpyHostToDevice, st));
     DREX_CUDA_CHECK(cudaMemcpyAsync(thr, thr_host, (tmax + 2) * sizeof(float), cudaMemcpyHostToDevice, st));
     if (N > 0) {
-        dim3 gq((unsigned)((N + 127) / 128), (unsigned)S);
+        dim3 gq((unsigned)S, (unsigned)((N + 127) / 128));
         drex::mindex_quats_kernel<<<gq, 128, 0, st>>>(o_soa, N, quats, n_store, ops);
         DREX_CUDA_CHECK(cudaGetLastError());
         const int n_tiles = (int)((N + drex::MINDEX_TILE - 1) / drex::MINDEX_TILE);
-        dim3 gp((unsigned)((int64_t)n_tiles * (n_tiles + 1) / 2), (unsigned)S);
+        dim3 gp((unsigned)S, (unsigned)((int64_t)n_tiles * (n_tiles + 1) / 2));
         if (refl) {
             drex::mindex_pairs_reflect_kernel<<<gp, drex::MINDEX_TILE, 0, st>>>(quats, N, n_tiles, tmax, thr, cnt);
         } else

@@ -24,28 +24,42 @@ struct FabricTable {
 
 constexpr int DERIV_BLOCK = 128;
 
-__global__ void __launch_bounds__(256) pack_soa_kernel(const double *__restrict__ aos,
-                                                       double *__restrict__ soa, int64_t S,
-                                                       int64_t N) {
-    const int64_t s = blockIdx.y;
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= N || s >= S) return;
-    const double *src = aos + (s * N + g) * 9;
-    double *dst = soa + s * 9 * N + g;
+// AoS [S][N][9] <-> SoA [S][9][N].  A block moves 256 grains through shared memory so that BOTH
+// sides are coalesced: the AoS side as one contiguous run of 256 x 72 B, the SoA side as nine
+// rows of 2 KB (a thread-per-grain copy reads or writes the AoS side at a 72 B stride).  The
+// system index rides in grid.x (no 65535 limit), the 256-grain tile in grid.y.
+constexpr int LAYOUT_TILE = 256;
+
+__global__ void __launch_bounds__(LAYOUT_TILE) pack_soa_kernel(const double *__restrict__ aos,
+                                                               double *__restrict__ soa, int64_t S,
+                                                               int64_t N) {
+    __shared__ double tile[LAYOUT_TILE * 9];
+    const int64_t s = blockIdx.x, g0 = (int64_t)blockIdx.y * LAYOUT_TILE;
+    const int n = (int)((N - g0 < LAYOUT_TILE) ? (N - g0) : LAYOUT_TILE);
+    const double *src = aos + (s * N + g0) * 9;
+    for (int i = threadIdx.x; i < n * 9; i += LAYOUT_TILE) tile[i] = src[i];
+    __syncthreads();
+    if ((int)threadIdx.x < n) {
+        double *dst = soa + s * 9 * N + g0 + threadIdx.x;
 #pragma unroll
-    for (int c = 0; c < 9; ++c) dst[c * N] = src[c];
+        for (int c = 0; c < 9; ++c) dst[c * N] = tile[threadIdx.x * 9 + c];
+    }
 }
 
-__global__ void __launch_bounds__(256) unpack_soa_kernel(const double *__restrict__ soa,
-                                                         double *__restrict__ aos, int64_t S,
-                                                         int64_t N) {
-    const int64_t s = blockIdx.y;
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= N || s >= S) return;
-    const double *src = soa + s * 9 * N + g;
-    double *dst = aos + (s * N + g) * 9;
+__global__ void __launch_bounds__(LAYOUT_TILE) unpack_soa_kernel(const double *__restrict__ soa,
+                                                                 double *__restrict__ aos, int64_t S,
+                                                                 int64_t N) {
+    __shared__ double tile[LAYOUT_TILE * 9];
+    const int64_t s = blockIdx.x, g0 = (int64_t)blockIdx.y * LAYOUT_TILE;
+    const int n = (int)((N - g0 < LAYOUT_TILE) ? (N - g0) : LAYOUT_TILE);
+    if ((int)threadIdx.x < n) {
+        const double *src = soa + s * 9 * N + g0 + threadIdx.x;
 #pragma unroll
-    for (int c = 0; c < 9; ++c) dst[c] = src[c * N];
+        for (int c = 0; c < 9; ++c) tile[threadIdx.x * 9 + c] = src[c * N];
+    }
+    __syncthreads();
+    double *dst = aos + (s * N + g0) * 9;
+    for (int i = threadIdx.x; i < n * 9; i += LAYOUT_TILE) dst[i] = tile[i];
 }
 
 struct DerivArgs {
@@ -61,8 +75,8 @@ derivatives_grain_kernel(const DerivArgs A, const __grid_constant__ FabricTable 
     __shared__ __align__(16) double mt[MATH_TABLE_DOUBLES];
     load_math_tables(mt);
     __syncthreads();
-    const int64_t s = blockIdx.y;
-    const int64_t g = (int64_t)blockIdx.x * DERIV_BLOCK + threadIdx.x;
+    const int64_t s = blockIdx.x;  // systems in grid.x: no 65535 limit
+    const int64_t g = (int64_t)blockIdx.y * DERIV_BLOCK + threadIdx.x;
     if (g >= A.N) return;
     const int regime = A.regime[s];
     const double *o = A.o + s * 9 * A.N + g;
@@ -248,15 +262,15 @@ __global__ void __launch_bounds__(256)
 fluidity_unpack_kernel(const double *__restrict__ cpo, int64_t N, double *__restrict__ o_soa,
                        double *__restrict__ f, double *__restrict__ F, double *__restrict__ L_prev,
                        double *__restrict__ strain) {
-    const int64_t p = blockIdx.y, row = 10 * N + 22;
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t p = blockIdx.x, row = 10 * N + 22;  // particles in grid.x: no 65535 limit
+    const int64_t g = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
     const double *src = cpo + p * row;
     if (g < N) {
 #pragma unroll
         for (int c = 0; c < 9; ++c) o_soa[p * 9 * N + c * N + g] = src[9 * g + c];
         f[p * N + g] = src[9 * N + g];
     }
-    if (blockIdx.x == 0 && threadIdx.x < 9) {
+    if (blockIdx.y == 0 && threadIdx.x < 9) {
         L_prev[p * 9 + threadIdx.x] = src[10 * N + 4 + threadIdx.x];
         F[p * 9 + threadIdx.x] = src[10 * N + 13 + threadIdx.x];
         if (threadIdx.x == 0) strain[p] = src[10 * N];
@@ -268,15 +282,15 @@ fluidity_pack_kernel(const double *__restrict__ o_soa, const double *__restrict_
                      const double *__restrict__ F, const double *__restrict__ strain,
                      const double *__restrict__ position, const double *__restrict__ L_new, double dt,
                      int64_t N, double *__restrict__ cpo) {
-    const int64_t p = blockIdx.y, row = 10 * N + 22;
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t p = blockIdx.x, row = 10 * N + 22;  // particles in grid.x: no 65535 limit
+    const int64_t g = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
     double *dst = cpo + p * row;
     if (g < N) {
 #pragma unroll
         for (int c = 0; c < 9; ++c) dst[9 * g + c] = o_soa[p * 9 * N + c * N + g];
         dst[9 * N + g] = f[p * N + g];
     }
-    if (blockIdx.x == 0 && threadIdx.x < 9) {
+    if (blockIdx.y == 0 && threadIdx.x < 9) {
         dst[10 * N + 4 + threadIdx.x] = L_new[p * 9 + threadIdx.x];
         dst[10 * N + 13 + threadIdx.x] = F[p * 9 + threadIdx.x];
         if (threadIdx.x < 3) dst[10 * N + 1 + threadIdx.x] = position[p * 3 + threadIdx.x];

@@ -392,8 +392,8 @@ __device__ inline void matrix_to_quat(const double *M_in, double *q) {
 __global__ void __launch_bounds__(128)
 mindex_quats_kernel(const double *__restrict__ o_soa, int64_t N, float4 *__restrict__ quats,
                     int n_store, const __grid_constant__ SymOps ops) {
-    const int64_t s = blockIdx.y;
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t s = blockIdx.x;  // textures in grid.x: no 65535 limit
+    const int64_t g = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
     if (g >= N) return;
     double a[9], q[4];
     for (int c = 0; c < 9; ++c) a[c] = o_soa[s * 9 * N + c * N + g];
@@ -469,9 +469,9 @@ mindex_pairs_kernel(const float4 *__restrict__ quats, int64_t N, int n_tiles, in
     __shared__ float4 qj[MINDEX_TILE * NOPS];
     __shared__ unsigned int hist[MAX_THETA];
     __shared__ float thr[MAX_THETA + 2];
-    const int64_t s = blockIdx.y;
+    const int64_t s = blockIdx.x;  // textures in grid.x, tile pairs in grid.y
     int ti, tj;
-    mindex_tile(blockIdx.x, n_tiles, ti, tj);
+    mindex_tile(blockIdx.y, n_tiles, ti, tj);
     const int tid = threadIdx.x;
     for (int b = tid; b < theta_max; b += MINDEX_TILE) hist[b] = 0u;
     for (int b = tid; b < theta_max + 2; b += MINDEX_TILE) thr[b] = thresholds[b];
@@ -515,9 +515,9 @@ mindex_pairs_reflect_kernel(const float4 *__restrict__ quats, int64_t N, int n_t
     __shared__ float4 qj[MINDEX_TILE * 4];
     __shared__ unsigned int hist[MAX_THETA];
     __shared__ float thr[MAX_THETA + 2];
-    const int64_t s = blockIdx.y;
+    const int64_t s = blockIdx.x;  // textures in grid.x, tile pairs in grid.y
     int ti, tj;
-    mindex_tile(blockIdx.x, n_tiles, ti, tj);
+    mindex_tile(blockIdx.y, n_tiles, ti, tj);
     const int tid = threadIdx.x;
     for (int b = tid; b < theta_max; b += MINDEX_TILE) hist[b] = 0u;
     for (int b = tid; b < theta_max + 2; b += MINDEX_TILE) thr[b] = thresholds[b];

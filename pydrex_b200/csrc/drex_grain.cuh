@@ -54,8 +54,8 @@ struct GrainProbe {  // optional intermediates for drex_grain_probe_f64
 // mt: the exp/log tables in shared memory (drex_math.cuh: load_math_tables).
 // MODE selects what is decided at compile time (the integrator's hot loop is instantiated
 // once per variant so that only that variant's code sits in the instruction cache):
-//   0 runtime dispatch on fc, 1 olivine with the default exponents, 2 olivine with generic
-//   exponents, 3 enstatite.
+//   0 runtime dispatch on fc, 1 olivine with the default exponents and the fourth slip system
+//   inactive (A, B, D, E type), 2 any other olivine (generic exponents or C type), 3 enstatite.
 constexpr int GRAIN_RUNTIME = 0, GRAIN_OLIVINE_DEFAULT = 1, GRAIN_OLIVINE_GENERIC = 2,
               GRAIN_ENSTATITE = 3;
 
@@ -65,7 +65,9 @@ __device__ __forceinline__ void grain_rhs(const double (&a)[9], const double (&D
                                           const double *__restrict__ mt, GrainOut &out,
                                           GrainProbe *probe, double half_scale = 0.5) {
     const bool olivine = (MODE == GRAIN_RUNTIME) ? (fc.phase == 0) : (MODE != GRAIN_ENSTATITE);
-    const bool inf3 = fc.inf_index == 3;  // CTA-uniform
+    // GRAIN_OLIVINE_DEFAULT also fixes the infinite-CRSS system to the fourth one (every fabric
+    // but C-type), which keeps the second copy of the selection code out of that hot loop
+    const bool inf3 = (MODE == GRAIN_OLIVINE_DEFAULT) ? true : (fc.inf_index == 3);  // warp-uniform
     // D.a_r for the crystal axes (rows of a)
     double Da1[3], Da2[3];
 #pragma unroll
@@ -202,7 +204,7 @@ __device__ __forceinline__ void grain_rhs(const double (&a)[9], const double (&D
         const double rho0 = fc.rho_pref[0] * (w0 * gp);
         const double rho1 = fc.rho_pref[1] * (w1 * gp);
         energy = rho0 * exp_tab(-fc.lambda * rho0 * rho0, mt) + rho1 * exp_tab(-fc.lambda * rho1 * rho1, mt);
-        if (fc.inf_index == 3) {  // otherwise rho_2 = (1/inf)^(n-p) * ... = 0 contributes 0
+        if (inf3) {  // otherwise rho_2 = (1/inf)^(n-p) * ... = 0 contributes 0
             const double rho2 = fc.rho_pref[2] * (w2 * gp);
             energy += rho2 * exp_tab(-fc.lambda * rho2 * rho2, mt);
         }

@@ -76,12 +76,13 @@ struct IntegrateArgs {
     const double *L_nodes;
     double gbm_mobility, gbs_threshold;
     TolArgs tol;
-    double *h_io;           // [S][n_chunks] first trial step in / next suggestion out, or null
+    double *h_io;           // [S][n_chunks] first trial step in / next suggestion out (as strain), or null
     const int32_t *order;   // optional queue permutation (longest systems first)
     int32_t *status, *n_rhs, *n_accept, *n_reject;
     int64_t *grain_evals;   // optional: right-hand sides x live grains per system
-    double *scratch;        // per CTA: INT_NCTX x chunk_cap doubles (per-chunk partial sums)
+    double *scratch;        // per CTA and slot: chunk_cap doubles (per-chunk partial sums)
     int64_t chunk_cap;
+    uint32_t *slide_mask;   // [S][n_chunks]: lanes of each chunk whose grain slides (gbs_restore_kernel)
     int *queue;             // atomic work counter, zeroed before launch
 };
 
@@ -97,9 +98,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
                  "r"(bytes)
                  : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+__device__ __noinline__ void watchdog_fire(int where, long long a, long long b, long long c);
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int where = 100) {
     uint32_t done = 0;
     const uint32_t addr = smem_addr(bar);
+    unsigned tries = 0;
     while (!done) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -108,6 +111,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             : "=r"(done)
             : "r"(addr), "r"(parity)
             : "memory");
+        if (!done && ++tries > (1u << 22)) watchdog_fire(where, parity, 0, 0);
     }
 }
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_global, uint32_t bytes,
@@ -120,10 +124,33 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_global,
 }
 
 // A wait between warps of one CTA (a system being prepared or finished by another warp).  The
-// watchdog turns a protocol bug into a launch failure instead of a hung GPU.
-__device__ __forceinline__ void spin_pause(unsigned &n) {
+// watchdog turns a protocol bug into a launch failure instead of a hung GPU; when a debug buffer
+// in mapped host memory is attached (DREX_DEBUG_HOSTPTR, development only) the waiting warp first
+// records where it was stuck: the context is lost after the trap, host memory is not.
+__device__ unsigned long long *g_drex_debug = nullptr;
+__device__ __noinline__ void watchdog_fire(int where, long long a, long long b, long long c) {
+    unsigned long long *d = g_drex_debug;
+    if (d != nullptr && (threadIdx.x & 31) == 0) {
+        const unsigned long long idx = (unsigned long long)blockIdx.x * 16 + (threadIdx.x >> 5);
+        if (idx < 4096) {  // one record per warp, plain stores (no atomics across PCIe)
+            volatile unsigned long long *r = d + 8 + 8 * idx;
+            r[0] = (unsigned long long)where;
+            r[1] = blockIdx.x;
+            r[2] = threadIdx.x >> 5;
+            r[3] = (unsigned long long)a;
+            r[4] = (unsigned long long)b;
+            r[5] = (unsigned long long)c;
+        }
+        __threadfence_system();
+    }
+    __syncwarp();
+    __nanosleep(2000000);
+    __trap();
+}
+__device__ __forceinline__ void spin_pause(unsigned &n, int where = 0, long long a = 0, long long b = 0,
+                                           long long c = 0) {
     __nanosleep(64);
-    if (++n > (1u << 26)) __trap();
+    if (++n > (1u << 24)) watchdog_fire(where, a, b, c);
 }
 
 // Step planning: the rest of the interval is cut into n EQUAL steps, n the smallest count
@@ -139,10 +166,12 @@ __device__ __forceinline__ void spin_pause(unsigned &n) {
 #define DREX_SAFETY 0.9
 #endif
 __device__ __forceinline__ double plan_step(double h_prop, double remaining) {
-    const double ratio = fabs(remaining) / (fabs(h_prop) * DREX_STRETCH);
+    // (~1 ulp divisions: the step only has to be close to remaining / n; the last step of an
+    // interval is set to what remains, exactly)
+    const double ratio = div_fast(fabs(remaining), fabs(h_prop) * DREX_STRETCH);
     if (!(ratio > 1.0)) return remaining;  // one step reaches the end
     if (!(ratio < 1e9)) return h_prop;     // degenerate proposal: leave it to the step-underflow test
-    return remaining / ceil(ratio);
+    return div_fast(remaining, ceil(ratio));
 }
 
 // Bogacki-Shampine 3(2)
@@ -167,6 +196,8 @@ struct ChunkFlow {
 // published and read-only afterwards, except the counters at the end.
 struct SysSlot {
     double t0, t1, kappa, rscale;
+    double s_begin, s_end;         // strain-rate scale at t0 and t1 (step sizes are carried as strain)
+    double inv_span2;              // 2 / (t1 - t0), 0 for an empty interval
     double Q[9];                   // regimes 0/1/7: orientation increment common to all grains
     ChunkFlow cflow;               // the flow when L is constant over the interval
     double Ltab[INT_KMAX * 9];     // this particle's L(t) node table (K <= INT_KMAX)
@@ -175,15 +206,17 @@ struct SysSlot {
     double Lst[4][9];              // stage matrices of the deformation-gradient integration
     unsigned long long ticket;     // (sequence number << 32) | next chunk: the slot is ready when the
                                    // upper half equals the sequence number a warp looks for
-    unsigned long long grain_evals;
-    int sys, regime, fab, mode, n_chunks, prep_at, const_flow, s_table, f_active, status0;
-    int done, status, n_rhs, n_acc, n_rej;
+    unsigned long long count_a;    // right-hand sides (low half) and rejected steps, summed over chunks
+    unsigned long long count_b;    // accepted steps (low half) and chunks completed
+    int sys, regime, fab, mode, n_chunks, prep_at, const_flow, s_table, f_active, status0, K;
+    int status, rhs_last;          // worst chunk status; right-hand sides of the (ragged) last chunk
+    int seq;                       // sequence number of the system in this CTA
     int busy;                      // from the start of prepare to the end of finalize
 };
 
 struct CtaShared {
     SysSlot slot[INT_NCTX];
-    uint64_t mbar[INT_WARPS];
+    uint64_t mbar[INT_WARPS];   // next-chunk prefetch
     int hand_seq;  // sequence number of the system currently handing out chunks
     int end_seq;   // number of systems this CTA processes (INT_MAX until the queue runs dry)
 };
@@ -266,9 +299,7 @@ __device__ __noinline__ double eval_L_generic(const IntegrateArgs &A, const doub
 __device__ __forceinline__ double slot_L(const IntegrateArgs &A, const SysSlot &sl, double t, int c) {
     if (A.L_kind == 0 || A.K == 1) return sl.Ltab[c];
     if (A.L_kind == 2 && A.K <= INT_KMAX) {
-        const double span = sl.t1 - sl.t0;
-        const double xi = (span != 0.0) ? fma(2.0, (t - sl.t0) / span, -1.0) : -1.0;
-        return clenshaw(sl.coef[c], A.K, xi);
+        return clenshaw(sl.coef[c], A.K, fma(t - sl.t0, sl.inv_span2, -1.0));
     }
     const double *table = (A.K <= INT_KMAX) ? sl.Ltab : A.L_nodes + (int64_t)A.sys_particle[sl.sys] * A.K * 9;
     return eval_L_generic(A, table, t, sl.t0, sl.t1, c);
@@ -301,22 +332,49 @@ __device__ __forceinline__ void store_flows(ChunkFlow *dst, int n, double val, b
     __syncwarp();
 }
 
-// Stage flows at n <= 3 times for a warp stepping a chunk of the system in `sl`.
-__device__ __forceinline__ void warp_flows(const IntegrateArgs &A, const SysSlot &sl, ChunkFlow *dst,
-                                           int n, double ta, double tb, double tc, int lane) {
+// Stage flows at n <= 3 times for a warp stepping a chunk of the system in `sl`: the hot case, a
+// Chebyshev table with a validated scale series (sl.s_table).  One Clenshaw recurrence per lane,
+// components and scale alike, one shared reciprocal; touches shared memory only and is not
+// inlined, so that the step loops stay small.
+__device__ __noinline__ void warp_flows_cheb(const SysSlot &sl, ChunkFlow *dst, int n, double ta,
+                                             double tb, double tc, int lane) {
+    const int si = lane / 10, c = lane - 10 * si;
+    const bool active = si < n;
+    const double t = (si == 0) ? ta : ((si == 1) ? tb : tc);
+    const double xi = fma(t - sl.t0, sl.inv_span2, -1.0);
+    const double val = active ? clenshaw(sl.coef[c], sl.K, xi) : 0.0;
+    const int base = active ? 10 * si : 0;
+    const double sv = __shfl_sync(0xffffffffu, val, base + 9);
+    const int ct = (c < 9) ? 3 * (c % 3) + c / 3 : 0;  // transposed component
+    const double lt = __shfl_sync(0xffffffffu, val, base + ct);
+    double r;  // 1 / s to ~1 ulp
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(sv));
+    r = fma(r, fma(-sv, r, 1.0), r);
+    r = fma(r, fma(-sv, r, 1.0), r);
+    if (active) {
+        if (c < 9) {
+            const double sym = 0.5 * (val + lt);
+            double q1 = sym * r, q2 = val * r;
+            q1 = fma(fma(-sv, q1, sym), r, q1);
+            q2 = fma(fma(-sv, q2, val), r, q2);
+            dst[si].DL[c] = make_double2(q1, q2);
+        } else {
+            dst[si].s = sv;
+            dst[si].nks = -sl.kappa * sv;
+        }
+    }
+    __syncwarp();
+}
+
+// The same for every other provider (linear, piecewise linear, large tables, a scale with
+// kinks): components one by one, closed-form scale per stage time.
+__device__ __noinline__ void warp_flows(const IntegrateArgs &A, const SysSlot &sl, ChunkFlow *dst,
+                                        int n, double ta, double tb, double tc, int lane) {
     const int si = lane / 10, c = lane - 10 * si;
     const double t = (si == 0) ? ta : ((si == 1) ? tb : tc);
     double val = 0.0;
-    if (A.L_kind == 2 && A.K <= INT_KMAX) {
-        // the hot case: one Clenshaw recurrence per lane, components and scale alike
-        const double span = sl.t1 - sl.t0;
-        const double xi = fma(2.0, (t - sl.t0) / span, -1.0);
-        if (si < n && (c < 9 || sl.s_table)) val = clenshaw(sl.coef[c], A.K, xi);
-        store_flows(dst, n, val, sl.s_table != 0, sl.kappa, lane);
-    } else {
-        if (si < n && c < 9) val = slot_L(A, sl, t, c);
-        store_flows(dst, n, val, false, sl.kappa, lane);
-    }
+    if (si < n && c < 9) val = slot_L(A, sl, t, c);
+    store_flows(dst, n, val, false, sl.kappa, lane);
 }
 
 // Clip to [-1, 1] (utils.py:187) on the integer pipe: the FP64 pipe is the bottleneck and
@@ -372,6 +430,24 @@ __device__ __forceinline__ uint32_t err_bits(double err, double ynew, double ato
     return __float_as_uint((float)(fabs(err) * rc)) & 0x7fffffffu;
 }
 
+// Development aid (scripts/phase_timers.py, build with -DDREX_PHASE_TIMERS): every warp's clock
+// at the boundaries of its activities, summed over the launch into 8 counters behind the work
+// queue: 0 chunk tickets (incl. waiting for a system to be prepared), 1 preparing systems,
+// 2 waiting for the prefetched rows, 3 integrating chunks (stages), 4 chunk results, 5 finishing
+// systems and restoring sliding grains, 6 stage flows, 7 error norm + step controller.
+#ifdef DREX_PHASE_TIMERS
+#define DREX_MARK(slot)                          \
+    {                                            \
+        const long long now_ = clock64();        \
+        ptimer[slot] += now_ - pmark;            \
+        pmark = now_;                            \
+    }
+#define DREX_TIMER_ARGS , ptimer, pmark
+#else
+#define DREX_MARK(slot)
+#define DREX_TIMER_ARGS
+#endif
+
 struct ChunkResult {
     double v, h_next;
     int status, n_rhs, n_acc, n_rej, row;
@@ -383,10 +459,14 @@ template <int MODE>
 __device__ __forceinline__ void integrate_chunk(const IntegrateArgs &A, const SysSlot &sl,
                                                 const FabricConsts &fc, const double *__restrict__ mt,
                                                 double *rows, ChunkFlow *wf, int lane, double f0,
-                                                double h, ChunkResult &res) {
+                                                double h, ChunkResult &res
+#ifdef DREX_PHASE_TIMERS
+                                                , long long (&ptimer)[8], long long &pmark
+#endif
+                                                ) {
     const double t_begin = sl.t0, t_end = sl.t1, span = t_end - t_begin;
     const double relw = A.tol.atol_rel + A.tol.rtol, atol_abs = A.tol.atol_abs;
-    const bool f_active = sl.f_active != 0, const_flow = sl.const_flow != 0;
+    const bool f_active = sl.f_active != 0, const_flow = sl.const_flow != 0, cheb_flow = sl.s_table != 0;
     const ChunkFlow *fl = const_flow ? &sl.cflow : wf;
     const int fstride = const_flow ? 0 : 1;
     const double rscale = sl.rscale;
@@ -400,10 +480,14 @@ __device__ __forceinline__ void integrate_chunk(const IntegrateArgs &A, const Sy
             status = 1;  // DREX_STATUS_MAX_STEPS
             break;
         }
-        if (!const_flow) {
+        if (cheb_flow) {
+            if (need_k1) warp_flows_cheb(sl, wf + 3, 1, t, t, t, lane);
+            warp_flows_cheb(sl, wf, 3, fma(BS_A21, h, t), fma(BS_A32, h, t), t + h, lane);
+        } else if (!const_flow) {
             if (need_k1) warp_flows(A, sl, wf + 3, 1, t, t, t, lane);
             warp_flows(A, sl, wf, 3, fma(BS_A21, h, t), fma(BS_A32, h, t), t + h, lane);
         }
+        DREX_MARK(6)
         double k[9], st[9], e, kv = 0.0, vy = 0.0, ve = 0.0;
         if (need_k1) {
 #pragma unroll
@@ -452,6 +536,7 @@ __device__ __forceinline__ void integrate_chunk(const IntegrateArgs &A, const Sy
                 ve = fma(BS_E3, kv, ve);
             }
         }
+        DREX_MARK(3)
         uint32_t eb = 0;
 #pragma unroll
         for (int c = 0; c < 9; ++c) {
@@ -472,9 +557,10 @@ __device__ __forceinline__ void integrate_chunk(const IntegrateArgs &A, const Sy
             break;
         }
         const bool accept = emax <= 1.0f;
-        double fac = (emax > 0.0f) ? DREX_SAFETY * rcbrt((double)emax) : 5.0;  // err^(-1/3)
-        fac = fmin(accept ? (last_rejected ? 1.0 : 5.0) : 1.0, fmax(0.2, fac));
-        double h_next = h * fac;
+        // safety * err^(-1/3) in float32: only the size of the step depends on it
+        float facf = (emax > 0.0f) ? (float)DREX_SAFETY * exp2f(-0.33333334f * __log2f(emax)) : 5.0f;
+        facf = fminf(accept ? (last_rejected ? 1.0f : 5.0f) : 1.0f, fmaxf(0.2f, facf));
+        double h_next = h * (double)facf;
         h_carry = h_next;
         if (accept) {
             ++n_acc;
@@ -502,7 +588,9 @@ __device__ __forceinline__ void integrate_chunk(const IntegrateArgs &A, const Sy
             }
         }
         h = h_next;
+        DREX_MARK(7)
     }
+    DREX_MARK(7)
     res.v = v;
     res.h_next = h_carry;
     res.status = status;
@@ -635,7 +723,8 @@ __device__ __noinline__ void prepare_system(const IntegrateArgs &A, const Fabric
                                             int seq, int lane) {
     SysSlot &sl = sh.slot[seq % INT_NCTX];
     unsigned spins = 0;
-    while (ld_vol(&sl.busy)) spin_pause(spins);  // the system that last used this slot is being finished
+    while (ld_vol(&sl.busy))  // the system that last used this slot is being finished
+        spin_pause(spins, 1, seq, sl.seq, sl.sys);
     int s = -1;
     if (lane == 0) {
         const int ticket = atomicAdd(A.queue, 1);
@@ -662,23 +751,25 @@ __device__ __noinline__ void prepare_system(const IntegrateArgs &A, const Fabric
         sl.regime = regime;
         sl.fab = fab;
         sl.mode = !slip ? 4 : (phase != 0 ? GRAIN_ENSTATITE
-                                          : (T.fab[fab].default_exponents ? GRAIN_OLIVINE_DEFAULT
-                                                                          : GRAIN_OLIVINE_GENERIC));
+                                          : ((T.fab[fab].default_exponents && T.fab[fab].inf_index == 3)
+                                                 ? GRAIN_OLIVINE_DEFAULT
+                                                 : GRAIN_OLIVINE_GENERIC));
         sl.t0 = A.t0[ip];
         sl.t1 = A.t1[ip];
         sl.kappa = kappa;
         sl.rscale = rscale;
+        sl.inv_span2 = (sl.t1 != sl.t0) ? 2.0 / (sl.t1 - sl.t0) : 0.0;
         sl.f_active = kappa != 0.0;
         sl.n_chunks = n_chunks;
         sl.prep_at = n_chunks / 2;
         sl.const_flow = (A.L_kind == 0 || K == 1) ? 1 : 0;
+        sl.K = K;
         sl.s_table = 0;
-        sl.done = 0;
         sl.status = 0;
-        sl.n_rhs = 0;
-        sl.n_acc = 0;
-        sl.n_rej = 0;
-        sl.grain_evals = 0ull;
+        sl.rhs_last = 0;
+        sl.count_a = 0ull;
+        sl.count_b = 0ull;
+        sl.seq = seq;
     }
     if (K <= INT_KMAX)
         for (int j = lane; j < K * 9; j += 32) sl.Ltab[j] = A.L_nodes[ip * K * 9 + j];
@@ -724,7 +815,24 @@ __device__ __noinline__ void prepare_system(const IntegrateArgs &A, const Fabric
         }
         worst = warp_max(worst);
         __syncwarp();
-        if (lane == 0) sl.s_table = (worst <= 1e-12) ? 1 : 0;
+        // 1e-9: s only enters through the strain energy (the rotation rate is homogeneous of
+        // degree one in (D, L), so D / s and L / s times s do not depend on s)
+        if (lane == 0) sl.s_table = (worst <= 1e-9) ? 1 : 0;
+        __syncwarp();
+    }
+    {
+        // carried step sizes are kept in units of STRAIN (time x strain-rate scale): along a
+        // pathline the strain rate changes from one interval to the next and a step carried as
+        // time would be rejected whenever the flow speeds up
+        double Lm[9], sb = 1.0, se = 1.0;
+        if (lane < 2) {
+            for (int c = 0; c < 9; ++c) Lm[c] = slot_L(A, sl, lane == 0 ? sl.t0 : sl.t1, c);
+            const double sv = strain_rate_max(Lm);
+            if (lane == 0) sb = (sv > 0.0 && sv < INFINITY) ? sv : 1.0;
+            else se = (sv > 0.0 && sv < INFINITY) ? sv : 1.0;
+        }
+        if (lane == 0) sl.s_begin = sb;
+        if (lane == 1) sl.s_end = se;
         __syncwarp();
     }
     const int status0 = integrate_gradient(A, sl, lane);
@@ -735,61 +843,87 @@ __device__ __noinline__ void prepare_system(const IntegrateArgs &A, const Fabric
         *reinterpret_cast<volatile unsigned long long *>(&sl.ticket) = (unsigned long long)(unsigned)seq << 32;
 }
 
+// Per-slot scratch in global memory (L2-resident): per-chunk sums.
+struct SlotScratch {
+    double *psum;
+};
+__device__ __forceinline__ SlotScratch slot_scratch(const IntegrateArgs &A, int slot_index) {
+    SlotScratch sc;
+    sc.psum = A.scratch + ((int64_t)blockIdx.x * INT_NCTX + slot_index) * A.chunk_cap;
+    return sc;
+}
+
 // End of the interval for one system, by the warp that completed its last chunk:
 // extract_vars -> apply_gbs against the interval-start orientations -> extract_vars
 // (minerals.py:464-474, 536-538; utils.py:159-190).  f_out holds u_g = max(f_g(t0), 0) e^{v_g}
-// and psum the per-chunk sums of u; every sum is formed in a fixed order.
-__device__ __noinline__ void finalize_system(const IntegrateArgs &A, SysSlot &sl, const double *psum,
+// and psum the per-chunk sums of u; every sum is formed in a fixed order.  One warp walks
+// 40 KB of fractions twice, so the loads of FIN_BATCH chunks are issued together: the pass is
+// a chain of L2 round trips, not arithmetic.  The ORIENTATIONS of sliding grains are not
+// restored here -- that is a copy of up to 360 KB per system, latency-bound for a single warp --
+// but by gbs_restore_kernel, which streams them at memory bandwidth after this kernel; this
+// pass leaves it one lane mask per chunk.
+constexpr int FIN_BATCH = 8;
+__device__ __noinline__ void finalize_system(const IntegrateArgs &A, SysSlot &sl, const SlotScratch sc,
                                              int lane) {
     const int64_t N = A.N, s = sl.sys;
     const int nq = sl.n_chunks;
     double *f_out = A.f_out + s * N;
-    double *o_out = A.o_out + s * 9 * N;
-    const double *o_prev = A.o_prev + s * 9 * N;
+    uint32_t *mask_out = A.slide_mask + s * nq;
     double acc = 0.0;
-    for (int q = lane; q < nq; q += 32) acc += __ldcg(psum + q);
+    for (int q = lane; q < nq; q += 32) acc += __ldcg(sc.psum + q);
     const double S1 = warp_sum(acc);
     const double floor_v = A.gbs_threshold / (double)N;
+    // first sweep: S2 = sum of the fractions after sliding grains were set to chi / N
     acc = 0.0;
-#pragma unroll 4
-    for (int q = 0; q < nq; ++q) {
-        const int64_t g = (int64_t)q * 32 + lane;
-        if (g < N) {
-            const double fh = __ldcg(f_out + g) / S1;
-            acc += (fh < floor_v) ? floor_v : fh;
+    for (int q0 = 0; q0 < nq; q0 += FIN_BATCH) {
+        double u[FIN_BATCH];
+#pragma unroll
+        for (int j = 0; j < FIN_BATCH; ++j) {
+            const int64_t g = (int64_t)(q0 + j) * 32 + lane;
+            u[j] = (q0 + j < nq && g < N) ? __ldcg(f_out + g) : -1.0;
+        }
+#pragma unroll
+        for (int j = 0; j < FIN_BATCH; ++j) {
+            const double fh = u[j] / S1;
+            acc += (u[j] < 0.0) ? 0.0 : ((fh < floor_v) ? floor_v : fh);  // NaN passes through
         }
     }
     const double S2 = warp_sum(acc);
-    acc = 0.0;
-#pragma unroll 4
-    for (int q = 0; q < nq; ++q) {
-        const int64_t g = (int64_t)q * 32 + lane;
-        if (g < N) {
-            const double fh = __ldcg(f_out + g) / S1;
-            acc += fmax(((fh < floor_v) ? floor_v : fh) / S2, 0.0);
-        }
-    }
-    const double S3 = warp_sum(acc);
-#pragma unroll 2
-    for (int q = 0; q < nq; ++q) {
-        const int64_t g = (int64_t)q * 32 + lane;
-        if (g < N) {
-            const double fh = __ldcg(f_out + g) / S1;
-            const bool slide = fh < floor_v;
-            f_out[g] = fmax((slide ? floor_v : fh) / S2, 0.0) / S3;
-            if (slide) {  // no rotation: the grain keeps its interval-start orientation
+    // The last renormalisation of the reference divides by sum_g (f_g / S2), which is 1 up to
+    // a few ulp whatever the order of summation; it is taken as exactly 1 here.
+    // second sweep: the new fractions, and which grains slide
+    for (int q0 = 0; q0 < nq; q0 += FIN_BATCH) {
+        double u[FIN_BATCH];
 #pragma unroll
-                for (int c = 0; c < 9; ++c) o_out[c * N + g] = clip1(o_prev[c * N + g]);
-            }
+        for (int j = 0; j < FIN_BATCH; ++j) {
+            const int64_t g = (int64_t)(q0 + j) * 32 + lane;
+            u[j] = (q0 + j < nq && g < N) ? __ldcg(f_out + g) : -1.0;
         }
+        uint32_t mine = 0;  // lane j keeps the mask of chunk q0 + j: one coalesced store per batch
+#pragma unroll
+        for (int j = 0; j < FIN_BATCH; ++j) {
+            const int64_t g = (int64_t)(q0 + j) * 32 + lane;
+            bool slide = false;
+            if (!(u[j] < 0.0)) {  // live grain (or NaN, which is written through)
+                const double fh = u[j] / S1;
+                slide = fh < floor_v;
+                f_out[g] = fmax((slide ? floor_v : fh) / S2, 0.0);
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, slide);
+            if (lane == j) mine = m;
+        }
+        if (lane < FIN_BATCH && q0 + lane < nq) mask_out[q0 + lane] = mine;
     }
     if (lane == 0) {
         const int status = max(sl.status, sl.status0);
+        const unsigned long long ca = sl.count_a, cb = sl.count_b;
+        const long long n_rhs = (long long)(ca & 0xffffffffull);
+        const int64_t live_last = N - (int64_t)(nq - 1) * 32;
         A.status[s] = status;
-        if (A.n_rhs) A.n_rhs[s] = sl.n_rhs;
-        if (A.n_accept) A.n_accept[s] = sl.n_acc;
-        if (A.n_reject) A.n_reject[s] = sl.n_rej;
-        if (A.grain_evals) A.grain_evals[s] = (int64_t)sl.grain_evals;
+        if (A.n_rhs) A.n_rhs[s] = (int32_t)n_rhs;
+        if (A.n_accept) A.n_accept[s] = (int32_t)(cb & 0xffffffffull);
+        if (A.n_reject) A.n_reject[s] = (int32_t)(ca >> 32);
+        if (A.grain_evals) A.grain_evals[s] = 32 * n_rhs - (32 - live_last) * (int64_t)sl.rhs_last;
     }
     __threadfence_block();
     __syncwarp();
@@ -817,7 +951,7 @@ __device__ __forceinline__ ChunkRef grab_chunk(CtaShared &sh, bool blocking, int
                     seq = -2;
                     break;
                 }
-                spin_pause(spins);
+                spin_pause(spins, 2, hs, (long long)cur, ld_vol(&sh.end_seq));
                 continue;
             }
             const int t = (int)(cur & 0xffffffffull);
@@ -838,8 +972,9 @@ __device__ __forceinline__ ChunkRef grab_chunk(CtaShared &sh, bool blocking, int
     return ChunkRef{seq, q};
 }
 
+
 __global__ void __launch_bounds__(INT_BLOCK, INT_CTAS_PER_SM)
-integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
+integrate_kernel(const __grid_constant__ IntegrateArgs A, const __grid_constant__ FabricTable T) {
     extern __shared__ __align__(128) double dyn_smem[];
     __shared__ CtaShared sh;
     __shared__ __align__(16) double math_tab[MATH_TABLE_DOUBLES];
@@ -849,21 +984,26 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
     const int64_t N = A.N;
     double *rows = dyn_smem + warp * WARP_DOUBLES;
     ChunkFlow *wf = reinterpret_cast<ChunkFlow *>(dyn_smem + INT_WARPS * WARP_DOUBLES) + 4 * warp;
-    double *psum_base = A.scratch + (int64_t)blockIdx.x * INT_NCTX * A.chunk_cap;
     uint64_t *mbar = &sh.mbar[warp];
     uint32_t parity = 0;
     if (lane == 0) mbar_init(mbar, 1);
     if (tid == 0) {
         sh.hand_seq = 0;
         sh.end_seq = 0x7fffffff;
-        for (int i = 0; i < INT_NCTX; ++i) {
+        for (int i = 0; i < INT_NCTX; ++i) {  // shared memory comes with whatever the last kernel left
             sh.slot[i].ticket = ~0ull;
             sh.slot[i].busy = 0;
+            sh.slot[i].seq = -1;
         }
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
+#ifdef DREX_PHASE_TIMERS
+    long long ptimer[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long pmark = clock64();
+#endif
     if (warp == 0) prepare_system(A, T, sh, 0, lane);
+    DREX_MARK(1)
 
     // TMA needs 16-byte aligned rows: N even and aligned bases; otherwise plain loads
     const bool rows_aligned = ((N & 1) == 0) && ((reinterpret_cast<uintptr_t>(A.o_in) & 15) == 0) &&
@@ -881,8 +1021,27 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
         if (lane == 9) bulk_g2s(rows + (ROW_PF + 9) * 32, A.f_in + s * N + g0, row_bytes, mbar);
     };
 
+    // deferred completion count of the last chunk this warp finished (see below)
+    int pend_slot = -1, pend_acc = 0;
+    auto flush_pending = [&]() -> int {
+        // returns the slot of a system this warp has to finish (it reported the last chunk), or -1
+        if (pend_slot < 0) return -1;
+        SysSlot &ps = sh.slot[pend_slot];
+        __threadfence();  // the chunk's sums and fractions are read back from L2 (ld.cg) by the finisher
+        __syncwarp();
+        unsigned long long cb = 0ull;
+        if (lane == 0) cb = atomicAdd(&ps.count_b, (unsigned long long)pend_acc | (1ull << 32));
+        const int d = __shfl_sync(0xffffffffu, (int)(cb >> 32), 0);
+        const int slot = pend_slot;
+        pend_slot = -1;
+        if (d != ps.n_chunks - 1) return -1;
+        __threadfence_block();
+        return slot;
+    };
+
     ChunkRef cur = grab_chunk(sh, true, lane);
     if (cur.seq >= 0) prefetch(cur);
+    DREX_MARK(0)
     while (cur.seq >= 0) {
         SysSlot &sl = sh.slot[cur.seq % INT_NCTX];
         const int64_t s = sl.sys;
@@ -892,7 +1051,14 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
         // on its chunk, so that the slot is ready long before the current system runs out.  (Not
         // at the time of the draw: a warp still holding an unfinished chunk must never wait for
         // another system to be finished.)
-        if (cur.q == sl.prep_at) prepare_system(A, T, sh, cur.seq + 1, lane);
+        if (cur.q == sl.prep_at) {
+            // (first everything this warp still owes to older systems: preparing waits for a free
+            // slot, i.e. for an older system to be finished completely)
+            const int fs = flush_pending();
+            if (fs >= 0) finalize_system(A, sh.slot[fs], slot_scratch(A, fs), lane);
+            prepare_system(A, T, sh, cur.seq + 1, lane);
+        }
+        DREX_MARK(1)
         // ---- this chunk's state into rows ROW_A.., then the prefetch rows are free again
         double f0;
         if (rows_aligned) {
@@ -911,8 +1077,10 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
             f0 = live ? A.f_in[s * N + g] : 0.0;
         }
         __syncwarp();
+        DREX_MARK(2)
         ChunkRef nxt = grab_chunk(sh, false, lane);
         if (nxt.seq >= 0) prefetch(nxt);
+        DREX_MARK(0)
 
         f0 = fmax(f0, 0.0);  // utils.py:188
         ChunkResult res;
@@ -925,7 +1093,7 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
             // first trial step of this chunk: carried from the previous interval, else the
             // whole interval (or first_step_frac of it)
             const double span = sl.t1 - sl.t0;
-            double h = (A.h_io != nullptr) ? A.h_io[s * sl.n_chunks + cur.q] : 0.0;
+            double h = (A.h_io != nullptr) ? A.h_io[s * sl.n_chunks + cur.q] / sl.s_begin : 0.0;
             if (!(fabs(h) > 0.0)) h = (A.tol.first_step_frac > 0.0 ? A.tol.first_step_frac : 1.0) * span;
             h = copysign(fabs(h), span);
             if (A.tol.max_step_frac > 0.0 && fabs(h) > A.tol.max_step_frac * fabs(span))
@@ -936,10 +1104,12 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
             // through uniform registers / the constant bank instead of ~30 vector registers
             const int fab_u = __shfl_sync(0xffffffffu, sl.fab, 0);
             const FabricConsts &fc = T.fab[fab_u];
-            if (mode == GRAIN_ENSTATITE) integrate_chunk<GRAIN_ENSTATITE>(A, sl, fc, math_tab, rows, wf, lane, f0, h, res);
-            else if (mode == GRAIN_OLIVINE_DEFAULT) integrate_chunk<GRAIN_OLIVINE_DEFAULT>(A, sl, fc, math_tab, rows, wf, lane, f0, h, res);
-            else integrate_chunk<GRAIN_OLIVINE_GENERIC>(A, sl, fc, math_tab, rows, wf, lane, f0, h, res);
+            if (mode == GRAIN_ENSTATITE) integrate_chunk<GRAIN_ENSTATITE>(A, sl, fc, math_tab, rows, wf, lane, f0, h, res DREX_TIMER_ARGS);
+            else if (mode == GRAIN_OLIVINE_DEFAULT) integrate_chunk<GRAIN_OLIVINE_DEFAULT>(A, sl, fc, math_tab, rows, wf, lane, f0, h, res DREX_TIMER_ARGS);
+            else integrate_chunk<GRAIN_OLIVINE_GENERIC>(A, sl, fc, math_tab, rows, wf, lane, f0, h, res DREX_TIMER_ARGS);
         }
+        DREX_MARK(7)
+        const int fin_slot = flush_pending();  // the previous chunk's completion (fast by now)
         // ---- results of the chunk: clipped orientations (utils.py:187), u_g = clip(f_g) e^{v_g}
         {
             const double *fin = rows + res.row * 32 + lane;
@@ -955,31 +1125,75 @@ integrate_kernel(const IntegrateArgs A, const __grid_constant__ FabricTable T) {
             if (live) A.f_out[s * N + g] = u;
             const double part = warp_sum(live ? u : 0.0);
             if (lane == 0) {
-                psum_base[(int64_t)(cur.seq % INT_NCTX) * A.chunk_cap + cur.q] = part;
-                if (A.h_io != nullptr && mode != 4) A.h_io[s * sl.n_chunks + cur.q] = res.h_next;
-                const int live_n = (int)((N - (int64_t)cur.q * 32 < 32) ? (N - (int64_t)cur.q * 32) : 32);
-                atomicAdd(&sl.n_rhs, res.n_rhs);
-                atomicAdd(&sl.n_acc, res.n_acc);
-                atomicAdd(&sl.n_rej, res.n_rej);
-                atomicAdd(&sl.grain_evals, (unsigned long long)res.n_rhs * (unsigned long long)live_n);
+                slot_scratch(A, cur.seq % INT_NCTX).psum[cur.q] = part;
+                if (A.h_io != nullptr && mode != 4) A.h_io[s * sl.n_chunks + cur.q] = res.h_next * sl.s_end;
+                if (cur.q == sl.n_chunks - 1) sl.rhs_last = res.n_rhs;
                 if (res.status) atomicMax(&sl.status, res.status);
+                atomicAdd(&sl.count_a, (unsigned long long)res.n_rhs | ((unsigned long long)res.n_rej << 32));
             }
         }
-        // the stores above, then the completion count: the warp that sees the last one finishes
-        __threadfence_block();
-        __syncwarp();
-        int d = 0;
-        if (lane == 0) d = atomicAdd(&sl.done, 1);
-        d = __shfl_sync(0xffffffffu, d, 0);
-        if (d == sl.n_chunks - 1) {
-            __threadfence_block();
-            finalize_system(A, sl, psum_base + (int64_t)(cur.seq % INT_NCTX) * A.chunk_cap, lane);
-        }
+        // This chunk's completion is reported when the warp finishes its NEXT chunk (or runs out
+        // of work): the count must follow the stores above, and a fence right here waits a full
+        // round trip to L2 for them; one chunk later they have long landed.
+        pend_slot = cur.seq % INT_NCTX;
+        pend_acc = res.n_acc;
+        DREX_MARK(4)
+        if (fin_slot >= 0) finalize_system(A, sh.slot[fin_slot], slot_scratch(A, fin_slot), lane);
+        DREX_MARK(5)
         if (nxt.seq == -2) {
+            // the next system is still being prepared: report first, then wait for it
+            const int fs = flush_pending();
+            if (fs >= 0) finalize_system(A, sh.slot[fs], slot_scratch(A, fs), lane);
             nxt = grab_chunk(sh, true, lane);
             if (nxt.seq >= 0) prefetch(nxt);
         }
+        DREX_MARK(0)
         cur = nxt;
+    }
+    {
+        const int fs = flush_pending();
+        if (fs >= 0) finalize_system(A, sh.slot[fs], slot_scratch(A, fs), lane);
+    }
+    DREX_MARK(5)
+#ifdef DREX_PHASE_TIMERS
+    if (lane == 0) {
+        unsigned long long *out = reinterpret_cast<unsigned long long *>(A.queue) + 8;
+        for (int i = 0; i < 8; ++i) atomicAdd(out + i, (unsigned long long)ptimer[i]);
+    }
+#endif
+}
+
+// Grain-boundary sliding, orientations: a sliding grain keeps its interval-start orientation
+// (utils.py:170), i.e. o_prev is copied over what the integration wrote for it.  Runs after
+// integrate_kernel on the same stream: one warp per chunk whose mask is not empty, nine
+// coalesced loads and masked stores; pure streaming at memory bandwidth (up to 144 B per
+// sliding grain), nothing when no grain slides.
+constexpr int RESTORE_BLOCK = 256;
+__global__ void __launch_bounds__(RESTORE_BLOCK)
+gbs_restore_kernel(const uint32_t *__restrict__ slide_mask, const double *__restrict__ o_prev,
+                   double *__restrict__ o_out, int64_t S, int64_t N) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n_chunks = (N + 31) / 32, total = S * n_chunks;
+    const int64_t warp0 = ((int64_t)blockIdx.x * RESTORE_BLOCK + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * RESTORE_BLOCK) >> 5;
+    for (int64_t base = warp0 * 32; base < total; base += n_warps * 32) {
+        // 32 masks per warp and round, one per lane; then the warp walks the non-empty ones
+        const uint32_t mine = (base + lane < total) ? slide_mask[base + lane] : 0u;
+        uint32_t todo = __ballot_sync(0xffffffffu, mine != 0u);
+        while (todo) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint32_t m = __shfl_sync(0xffffffffu, mine, j);
+            const int64_t idx = base + j, s = idx / n_chunks, q = idx - s * n_chunks;
+            if ((m >> lane) & 1u) {
+                const int64_t off = s * 9 * N + q * 32 + lane;
+                double a[9];
+#pragma unroll
+                for (int c = 0; c < 9; ++c) a[c] = o_prev[off + c * N];
+#pragma unroll
+                for (int c = 0; c < 9; ++c) o_out[off + c * N] = clip1(a[c]);
+            }
+        }
     }
 }
 
