@@ -166,12 +166,13 @@ __device__ __forceinline__ void spin_pause(unsigned &n, int where = 0, long long
 #define DREX_SAFETY 0.9
 #endif
 __device__ __forceinline__ double plan_step(double h_prop, double remaining) {
-    // (~1 ulp divisions: the step only has to be close to remaining / n; the last step of an
-    // interval is set to what remains, exactly)
-    const double ratio = div_fast(fabs(remaining), fabs(h_prop) * DREX_STRETCH);
-    if (!(ratio > 1.0)) return remaining;  // one step reaches the end
-    if (!(ratio < 1e9)) return h_prop;     // degenerate proposal: leave it to the step-underflow test
-    return div_fast(remaining, ceil(ratio));
+    // the count n only needs float32 (it is a small integer unless the proposal is degenerate);
+    // the step itself is remaining / n in double, the last step of an interval is set to what
+    // remains, exactly
+    const float ratio = __fdividef(fabsf((float)remaining), fabsf((float)h_prop) * (float)DREX_STRETCH);
+    if (!(ratio > 1.0f)) return remaining;  // one step reaches the end
+    if (!(ratio < 1e9f)) return h_prop;     // degenerate proposal: leave it to the step-underflow test
+    return div_fast(remaining, (double)ceilf(ratio));
 }
 
 // Bogacki-Shampine 3(2)
@@ -217,6 +218,11 @@ struct SysSlot {
 struct CtaShared {
     SysSlot slot[INT_NCTX];
     uint64_t mbar[INT_WARPS];   // next-chunk prefetch
+    // warp-uniform state of the chunk loop.  It lives here because it is needed once per chunk
+    // and would otherwise sit in registers across the whole integration of a chunk, i.e. in
+    // local memory: per-thread copies whose reloads miss the (small) L1 each time
+    int ws_nxt_seq[INT_WARPS], ws_nxt_q[INT_WARPS], ws_pend_slot[INT_WARPS], ws_pend_acc[INT_WARPS];
+    int ws_cur_seq[INT_WARPS], ws_cur_q[INT_WARPS];
     int hand_seq;  // sequence number of the system currently handing out chunks
     int end_seq;   // number of systems this CTA processes (INT_MAX until the queue runs dry)
 };
@@ -334,15 +340,19 @@ __device__ __forceinline__ void store_flows(ChunkFlow *dst, int n, double val, b
 
 // Stage flows at n <= 3 times for a warp stepping a chunk of the system in `sl`: the hot case, a
 // Chebyshev table with a validated scale series (sl.s_table).  One Clenshaw recurrence per lane,
-// components and scale alike, one shared reciprocal; touches shared memory only and is not
-// inlined, so that the step loops stay small.
-__device__ __noinline__ void warp_flows_cheb(const SysSlot &sl, ChunkFlow *dst, int n, double ta,
-                                             double tb, double tc, int lane) {
+// components and scale alike, one shared reciprocal; touches shared memory only and is small
+// enough to sit inside the step loop (as a call its instructions were fetched from L2 every time).
+__device__ __forceinline__ void warp_flows_cheb(const SysSlot &sl, ChunkFlow *dst, int n, double ta,
+                                                double tb, double tc, int lane) {
     const int si = lane / 10, c = lane - 10 * si;
     const bool active = si < n;
     const double t = (si == 0) ? ta : ((si == 1) ? tb : tc);
     const double xi = fma(t - sl.t0, sl.inv_span2, -1.0);
+#ifdef DREX_EXP_NOCLENSHAW
+    const double val = active ? sl.coef[c][0] + 1e-30 * xi : 0.0;
+#else
     const double val = active ? clenshaw(sl.coef[c], sl.K, xi) : 0.0;
+#endif
     const int base = active ? 10 * si : 0;
     const double sv = __shfl_sync(0xffffffffu, val, base + 9);
     const int ct = (c < 9) ? 3 * (c % 3) + c / 3 : 0;  // transposed component
@@ -482,6 +492,9 @@ __device__ __forceinline__ void integrate_chunk(const IntegrateArgs &A, const Sy
         }
         if (cheb_flow) {
             if (need_k1) warp_flows_cheb(sl, wf + 3, 1, t, t, t, lane);
+#ifdef DREX_EXP_NOFLOWS
+            if (need_k1)
+#endif
             warp_flows_cheb(sl, wf, 3, fma(BS_A21, h, t), fma(BS_A32, h, t), t + h, lane);
         } else if (!const_flow) {
             if (need_k1) warp_flows(A, sl, wf + 3, 1, t, t, t, lane);
@@ -1022,21 +1035,24 @@ integrate_kernel(const __grid_constant__ IntegrateArgs A, const __grid_constant_
     };
 
     // deferred completion count of the last chunk this warp finished (see below)
-    int pend_slot = -1, pend_acc = 0;
+    if (lane == 0) sh.ws_pend_slot[warp] = -1;
+    __syncwarp();
     auto flush_pending = [&]() -> int {
         // returns the slot of a system this warp has to finish (it reported the last chunk), or -1
+        const int pend_slot = ld_vol(&sh.ws_pend_slot[warp]);
         if (pend_slot < 0) return -1;
         SysSlot &ps = sh.slot[pend_slot];
-        __threadfence();  // the chunk's sums and fractions are read back from L2 (ld.cg) by the finisher
+        __threadfence_block();  // (one chunk later: nothing of this warp is in flight any more)
         __syncwarp();
         unsigned long long cb = 0ull;
-        if (lane == 0) cb = atomicAdd(&ps.count_b, (unsigned long long)pend_acc | (1ull << 32));
+        if (lane == 0) {
+            cb = atomicAdd(&ps.count_b, (unsigned long long)ld_vol(&sh.ws_pend_acc[warp]) | (1ull << 32));
+            st_vol(&sh.ws_pend_slot[warp], -1);
+        }
         const int d = __shfl_sync(0xffffffffu, (int)(cb >> 32), 0);
-        const int slot = pend_slot;
-        pend_slot = -1;
         if (d != ps.n_chunks - 1) return -1;
         __threadfence_block();
-        return slot;
+        return pend_slot;
     };
 
     ChunkRef cur = grab_chunk(sh, true, lane);
@@ -1082,6 +1098,14 @@ integrate_kernel(const __grid_constant__ IntegrateArgs A, const __grid_constant_
         if (nxt.seq >= 0) prefetch(nxt);
         DREX_MARK(0)
 
+        // park the warp-uniform loop state in shared memory across the integration
+        if (lane == 0) {
+            sh.ws_cur_seq[warp] = cur.seq;
+            sh.ws_cur_q[warp] = cur.q;
+            sh.ws_nxt_seq[warp] = nxt.seq;
+            sh.ws_nxt_q[warp] = nxt.q;
+        }
+        __syncwarp();
         f0 = fmax(f0, 0.0);  // utils.py:188
         ChunkResult res;
         res.v = 0.0;
@@ -1109,34 +1133,47 @@ integrate_kernel(const __grid_constant__ IntegrateArgs A, const __grid_constant_
             else integrate_chunk<GRAIN_OLIVINE_GENERIC>(A, sl, fc, math_tab, rows, wf, lane, f0, h, res DREX_TIMER_ARGS);
         }
         DREX_MARK(7)
+        cur.seq = ld_vol(&sh.ws_cur_seq[warp]);
+        cur.q = ld_vol(&sh.ws_cur_q[warp]);
+        nxt.seq = ld_vol(&sh.ws_nxt_seq[warp]);
+        nxt.q = ld_vol(&sh.ws_nxt_q[warp]);
         const int fin_slot = flush_pending();  // the previous chunk's completion (fast by now)
         // ---- results of the chunk: clipped orientations (utils.py:187), u_g = clip(f_g) e^{v_g}
+        // (everything is derived again from the reloaded chunk reference, so that nothing but f0
+        // has to survive the integration in registers)
         {
+            SysSlot &sr = sh.slot[cur.seq % INT_NCTX];
+            const int64_t ss = sr.sys, gg = (int64_t)cur.q * 32 + lane;
+            const bool alive = gg < N;
+            const bool slip = sr.mode != 4;
             const double *fin = rows + res.row * 32 + lane;
-            double *o_out = A.o_out + s * 9 * N + g;
-            if (live) {
+            double *o_out = A.o_out + ss * 9 * N + gg;
+            if (alive) {
 #pragma unroll
                 for (int c = 0; c < 9; ++c) {
-                    const double y = (mode != 4) ? fin[c * 32] : fin[c * 32] + sl.Q[c];
+                    const double y = slip ? fin[c * 32] : fin[c * 32] + sr.Q[c];
                     o_out[c * N] = clip_int(y);
                 }
             }
-            const double u = sl.f_active ? f0 * exp_tab(res.v, math_tab) : f0;
-            if (live) A.f_out[s * N + g] = u;
-            const double part = warp_sum(live ? u : 0.0);
+            const double u = sr.f_active ? f0 * exp_tab(res.v, math_tab) : f0;
+            if (alive) A.f_out[ss * N + gg] = u;
+            const double part = warp_sum(alive ? u : 0.0);
             if (lane == 0) {
                 slot_scratch(A, cur.seq % INT_NCTX).psum[cur.q] = part;
-                if (A.h_io != nullptr && mode != 4) A.h_io[s * sl.n_chunks + cur.q] = res.h_next * sl.s_end;
-                if (cur.q == sl.n_chunks - 1) sl.rhs_last = res.n_rhs;
-                if (res.status) atomicMax(&sl.status, res.status);
-                atomicAdd(&sl.count_a, (unsigned long long)res.n_rhs | ((unsigned long long)res.n_rej << 32));
+                if (A.h_io != nullptr && slip) A.h_io[ss * sr.n_chunks + cur.q] = res.h_next * sr.s_end;
+                if (cur.q == sr.n_chunks - 1) sr.rhs_last = res.n_rhs;
+                if (res.status) atomicMax(&sr.status, res.status);
+                atomicAdd(&sr.count_a, (unsigned long long)res.n_rhs | ((unsigned long long)res.n_rej << 32));
             }
         }
         // This chunk's completion is reported when the warp finishes its NEXT chunk (or runs out
         // of work): the count must follow the stores above, and a fence right here waits a full
         // round trip to L2 for them; one chunk later they have long landed.
-        pend_slot = cur.seq % INT_NCTX;
-        pend_acc = res.n_acc;
+        if (lane == 0) {
+            sh.ws_pend_slot[warp] = cur.seq % INT_NCTX;
+            sh.ws_pend_acc[warp] = res.n_acc;
+        }
+        __syncwarp();
         DREX_MARK(4)
         if (fin_slot >= 0) finalize_system(A, sh.slot[fin_slot], slot_scratch(A, fin_slot), lane);
         DREX_MARK(5)

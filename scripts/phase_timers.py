@@ -15,7 +15,10 @@ P, N = 1250, 5000
 workload = sys.argv[1] if len(sys.argv) > 1 else "corner_flow"
 dev = torch.device("cuda", 0)
 kind, tables, t_edges = bench.make_workload(workload, P, 10, seed=1000)
-ens = drex.ParticleEnsemble(P, N, bench.PARAMS, seed=8816, device=dev)
+which = sys.argv[2] if len(sys.argv) > 2 else "both"
+phases, fabrics = {"both": ((0, 1), (0, 5)), "olivine": ((0,), (0,)), "enstatite": ((1,), (5,))}[which]
+ens = drex.ParticleEnsemble(P, N, bench.PARAMS, phases=phases, fabrics=fabrics, regimes=(4,) * len(phases),
+                            seed=8816, device=dev)
 tol = ens.tolerances()
 names = ["chunk tickets / waiting for a system", "preparing systems", "waiting for prefetched rows",
          "chunk stages", "chunk results", "finishing systems", "stage flows", "error norm + controller"]
