@@ -336,6 +336,10 @@ class ParticleEnsemble:
                     ev_in.record(s_in)
             with torch.cuda.stream(s_run):
                 sp = _lib.stream_ptr(torch)
+                # longest systems of the group first (from the previous step's counts): a group
+                # is only ~2 systems per CTA, so the order decides the tail of its launch
+                cost = self.stats[1][s0:s1].to(torch.float32) * self._weight[s0:s1]
+                order = torch.argsort(cost, descending=True, stable=True).to(torch.int32)
                 if upload:
                     s_run.wait_event(ev_in)
                     _lib.check(lib.drex_pack_soa_f64(Pp(aos), Pp(self.o[s0:s1]), n, N, sp))
@@ -346,7 +350,7 @@ class ParticleEnsemble:
                     Pp(m[3][s0:s1]), Pp(self.vol_frac[s0:s1]), Pp(mh[1][s0:s1]), Pp(mh[2][s0:s1]),
                     Pp(mh[3][s0:s1]), Pp(self.F[s0:s1]), Pp(self.o[s0:s1]), Pp(self.f[s0:s1]), None,
                     Pp(self._o_alt[s0:s1]), Pp(self.f[s0:s1]), Pp(t0), Pp(t1), int(kind), K,
-                    Pp(L_nodes), ctypes.byref(prm), ctypes.byref(tol), Pp(self.h[s0:s1]), None,
+                    Pp(L_nodes), ctypes.byref(prm), ctypes.byref(tol), Pp(self.h[s0:s1]), Pp(order),
                     Pp(self.stats[0][s0:s1]), Pp(self.stats[1][s0:s1]), Pp(self.stats[2][s0:s1]),
                     Pp(self.stats[3][s0:s1]), Pp(self.grain_evals[s0:s1]), Pp(self._ws),
                     self._ws.numel(), sp))
