@@ -268,9 +268,17 @@ int drex_strain_rate_max_f64(const double *L, int64_t P, double *out, void *stre
 
 /* ---- tensors.py helpers (tensors.py:14-21, 167-203, 254-273) ---------------------- */
 
-/* B items at a time, row-major: op 0 tensors.rotate(tensor [81], rotation [9]) -> [81];
- * op 1 tensors.voigt_to_elastic_tensor(matrix [36]) -> [81]; op 2
- * tensors.elastic_tensor_to_voigt(tensor [81]) -> [36] (in1 is only read by op 0). */
+/* B items at a time, row-major (in1 is only read by op 0):
+ *   op 0  tensors.rotate(tensor [81], rotation [9]) -> [81]                  tensors.py:254-273
+ *   op 1  tensors.voigt_to_elastic_tensor(matrix [36]) -> [81]               tensors.py:167-184
+ *   op 2  tensors.elastic_tensor_to_voigt(tensor [81]) -> [36]               tensors.py:187-203
+ *   op 3  tensors.voigt_decompose(matrix [36]) -> [18]: dilatational stiffness d_ij = C_ijkk,
+ *         then deviatoric stiffness v_ij = C_ijkj                            tensors.py:39-73
+ *   op 4 / 5 / 6 / 7  tensors.mono_project / ortho_project / tetr_project / hex_project
+ *         (voigt_vector [21]) -> [21]                                        tensors.py:76-140
+ *   op 8  tensors.voigt_matrix_to_vector(matrix [36]) -> [21]                tensors.py:206-219
+ *   op 9  tensors.voigt_vector_to_matrix(vector [21]) -> [36]                tensors.py:222-251
+ *   op 10 / 11  tensors.upper_tri_to_symmetric of 3x3 [9] / 6x6 [36] matrices  tensors.py:143-164 */
 int drex_tensor_ops_f64(int op, const double *in0, const double *in1, int64_t B, double *out,
                         void *stream);
 /* tensors.polar_decompose for B nonsingular 3x3 matrices: left != 0 gives M = V R

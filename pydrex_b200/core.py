@@ -61,7 +61,10 @@ class DeformationRegime(IntEnum):
 
 @dataclass(frozen=True)
 class DefaultParams:
-    """The parameters the CPO hot path reads (subset of core.py:125-312; minerals.py:400-445,470)."""
+    """Default simulation parameters, the same record as the reference's (core.py:125-312) so that
+    `as_dict()` carries every key a driver written against it may read.  The CPO hot path reads
+    the first nine (minerals.py:400-445, 470); the flow-law constants below are data only (the
+    viscosity module is out of scope)."""
 
     phase_assemblage: tuple = (MineralPhase.olivine,)
     phase_fractions: tuple = (1.0,)
@@ -72,6 +75,20 @@ class DefaultParams:
     nucleation_efficiency: float = 5.0
     number_of_grains: int = 3500
     initial_olivine_fabric: MineralFabric = MineralFabric.olivine_A
+    disl_Peierls_stress: float = 2.0
+    disl_prefactors: tuple = (1e-16, 1e-17)
+    diff_prefactors: tuple = (1e-10, 1e-10)
+    disl_lowtemp_switch: float = 0.7
+    disl_activation_energy: float = 460.0
+    disl_activation_volume: float = 12.0
+    diff_activation_energies: tuple = (430.0, 330)
+    diff_activation_volumes: tuple = (4.0, 4.0)
+    disl_coefficients: tuple = (4.4e8, -5.26e4, 2.11e-2, 1.74e-4, -41.8, 4.21e-2, -1.14e-5)
+
+    def __post_init__(self):
+        for k, v in self.__dataclass_fields__.items():  # core.py:297-300
+            if v.type is not type(v.default):
+                raise ValueError(f"Illegal type for {self.__class__.__qualname__}.{k}")
 
     def as_dict(self):
         """Return a mutable copy of the parameters as a dictionary."""

@@ -462,12 +462,16 @@ int drex_strain_rate_max_f64(const double *L, int64_t P, double *out, void *stre
 
 int drex_tensor_ops_f64(int op, const double *in0, const double *in1, int64_t B, double *out,
                         void *stream) {
-    if (op < 0 || op > 2) return fail(DREX_E_INVALID, "drex_tensor_ops_f64: unknown op %d", op);
+    if (op < 0 || op > 11) return fail(DREX_E_INVALID, "drex_tensor_ops_f64: unknown op %d", op);
     if (B < 0) return fail(DREX_E_INVALID, "negative size");
     if (B == 0) return DREX_OK;
     if (!in0 || !out || (op == 0 && !in1)) return fail(DREX_E_INVALID, "drex_tensor_ops_f64: null pointer");
-    const int64_t n = B * ((op == 2) ? 36 : 81);
-    drex::tensor_ops_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(op, in0, in1, B, out);
+    // ops 10 / 11: upper_tri_to_symmetric of 3x3 / 6x6 matrices
+    const int n_side = (op == 11) ? 6 : 3;
+    if (op == 11) op = 10;
+    const int64_t n = B * drex::tensor_op_n_out(op, n_side);
+    drex::tensor_ops_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(op, in0, in1, B, out,
+                                                                                            n_side);
     DREX_CUDA_CHECK(cudaGetLastError());
     return DREX_OK;
 }

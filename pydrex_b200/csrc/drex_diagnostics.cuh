@@ -583,15 +583,102 @@ __device__ __forceinline__ int voigt_index(int p, int q) { return (p == q) ? p :
 // op 0  rotate(tensor[81], rotation[9]) -> [81]                        tensors.py:254-273
 // op 1  voigt_to_elastic_tensor(matrix[36]) -> [81]                    tensors.py:167-184
 // op 2  elastic_tensor_to_voigt(tensor[81]) -> [36]                    tensors.py:187-203
+// op 3  voigt_decompose(matrix[36]) -> [18] (dilatational 3x3 | deviatoric 3x3)  tensors.py:39-73
+// op 4-7  mono / ortho / tetr / hex_project(voigt_vector[21]) -> [21]            tensors.py:76-140
+// op 8  voigt_matrix_to_vector(matrix[36]) -> [21]                              tensors.py:206-219
+// op 9  voigt_vector_to_matrix(vector[21]) -> [36]                              tensors.py:222-251
+// op 10 upper_tri_to_symmetric(matrix[n x n], n = 3 or 6 in in1[0]) -> same     tensors.py:143-164
 // One thread per output element, B items.
+__host__ __device__ inline int tensor_op_n_out(int op, int n) {
+    return (op == 0 || op == 1) ? 81 : (op == 2 || op == 9) ? 36 : (op == 3) ? 18 : (op == 10) ? n * n : 21;
+}
+__host__ __device__ inline int tensor_op_n_in(int op, int n) {
+    return (op == 0 || op == 2) ? 81 : (op == 1 || op == 3 || op == 8) ? 36 : (op == 10) ? n * n : 21;
+}
+// upper_tri_to_symmetric keeps the upper triangle and mirrors it -- through numpy.where on the
+// VALUE, so an upper-triangle entry that is exactly 0 takes the transposed entry of the
+// upper-triangular matrix instead, which is 0 as well off the diagonal (tensors.py:163-164)
+__device__ inline double sym_from_upper(const double *m, int n, int i, int j) {
+    return (i <= j) ? m[n * i + j] : m[n * j + i];
+}
 __global__ void tensor_ops_kernel(int op, const double *__restrict__ in0,
                                   const double *__restrict__ in1, int64_t B,
-                                  double *__restrict__ out) {
-    const int n_out = (op == 2) ? 36 : 81;
+                                  double *__restrict__ out, int n_side) {
+    const int n_out = tensor_op_n_out(op, n_side);
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= B * n_out) return;
     const int64_t b = e / n_out;
     const int o = (int)(e - b * n_out);
+    const double RT2 = 1.4142135623730951;
+    if (op >= 3) {
+        const double *x = in0 + b * tensor_op_n_in(op, n_side);
+        double r = 0.0;
+        if (op == 3) {
+            const int which = o / 9, i = (o % 9) / 3, j = o % 3;
+            const int lo = i < j ? i : j, hi = i < j ? j : i;
+            if (which == 0) {  // d_ij = C_ijkk: column sums of the top three rows
+                const int col = (lo == hi) ? lo : (lo == 0 && hi == 1) ? 5 : (lo == 0 && hi == 2) ? 4 : 3;
+                r = (x[col] + x[6 + col]) + x[12 + col];
+            } else if (lo == hi) {  // v_ii
+                const int a = (lo == 0) ? 4 : 3, c = (lo == 2) ? 4 : 5;
+                r = (x[7 * lo] + x[7 * a]) + x[7 * c];
+            } else if (lo == 0 && hi == 1) {
+                r = (x[5] + x[6 + 5]) + x[6 * 3 + 4];
+            } else if (lo == 0 && hi == 2) {
+                r = (x[4] + x[12 + 4]) + x[6 * 3 + 5];
+            } else {
+                r = (x[6 + 3] + x[12 + 3]) + x[6 * 4 + 5];
+            }
+        } else if (op == 4) {
+            r = (o == 9 || o == 10 || o == 12 || o == 13 || o == 15 || o == 16 || o == 18 || o == 19) ? 0.0 : x[o];
+        } else if (op == 5) {
+            r = (o < 9) ? x[o] : 0.0;
+        } else if (op == 6) {
+            if (o >= 9) r = 0.0;
+            else if (o == 2 || o == 5 || o == 8) r = x[o];
+            else r = 0.5 * (x[o - o % 3] + x[o - o % 3 + 1]);
+        } else if (op == 7) {
+            if (o == 0 || o == 1) r = 3.0 / 8.0 * (x[0] + x[1]) + x[5] / 4 / RT2 + x[8] / 4;
+            else if (o == 2) r = x[2];
+            else if (o == 3 || o == 4) r = (x[3] + x[4]) / 2;
+            else if (o == 5) r = (x[0] + x[1]) / 4 / RT2 + 3.0 / 4.0 * x[5] - x[8] / 2 / RT2;
+            else if (o == 6 || o == 7) r = (x[6] + x[7]) / 2;
+            else if (o == 8) r = (x[0] + x[1]) / 4 - x[5] / 2 / RT2 + x[8] / 2;
+        } else if (op == 8) {
+            const int i = o % 3, blk = o / 3, i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+            if (blk == 0) r = x[7 * i];
+            else if (blk == 1) r = RT2 * x[6 * i1 + i2];
+            else if (blk == 2) r = 2 * x[7 * (i + 3)];
+            else if (blk == 3) r = 2 * x[6 * i + i + 3];
+            else if (blk == 4) r = 2 * x[6 * i2 + i + 3];
+            else if (blk == 5) r = 2 * x[6 * i1 + i + 3];
+            else r = 2 * RT2 * x[6 * (i1 + 3) + i2 + 3];
+        } else if (op == 9) {
+            // the upper triangle as voigt_vector_to_matrix fills it, then upper_tri_to_symmetric
+            const int i = o / 6, j = o % 6, lo = i < j ? i : j, hi = i < j ? j : i;
+            const double h = 1.0 / RT2;
+            if (lo == hi) r = (lo < 3) ? x[lo] : 0.5 * x[lo + 3];
+            else if (lo == 1 && hi == 2) r = h * x[3];
+            else if (lo == 0 && hi == 2) r = h * x[4];
+            else if (lo == 0 && hi == 1) r = h * x[5];
+            else if (lo == 0 && hi == 3) r = 0.5 * x[9];
+            else if (lo == 1 && hi == 4) r = 0.5 * x[10];
+            else if (lo == 2 && hi == 5) r = 0.5 * x[11];
+            else if (lo == 2 && hi == 3) r = 0.5 * x[12];
+            else if (lo == 0 && hi == 4) r = 0.5 * x[13];
+            else if (lo == 1 && hi == 5) r = 0.5 * x[14];
+            else if (lo == 1 && hi == 3) r = 0.5 * x[15];
+            else if (lo == 2 && hi == 4) r = 0.5 * x[16];
+            else if (lo == 0 && hi == 5) r = 0.5 * x[17];
+            else if (lo == 4 && hi == 5) r = 0.5 * h * x[18];
+            else if (lo == 3 && hi == 5) r = 0.5 * h * x[19];
+            else if (lo == 3 && hi == 4) r = 0.5 * h * x[20];
+        } else {
+            r = sym_from_upper(x, n_side, o / n_side, o % n_side);
+        }
+        out[e] = r;
+        return;
+    }
     if (op == 0) {
         const double *T = in0 + b * 81, *R = in1 + b * 9;
         const int i = o / 27, j = (o / 9) % 3, k = (o / 3) % 3, l = o % 3;

@@ -1,5 +1,6 @@
-"""Tensor helpers (drop-in for the parts of pydrex.tensors on the Voigt-average path,
-reference tensors.py:14-21, 167-203, 254-273).
+"""Tensor helpers (drop-in for pydrex.tensors: the Voigt-average path, reference
+tensors.py:14-21, 167-203, 254-273, and the Browaeys & Chevrot decomposition helpers that
+`diagnostics.elasticity_components` is built from, tensors.py:39-164, 206-251).
 
 Every function takes one item like the reference or a leading batch axis; the arithmetic
 runs in the library's kernels (`drex_tensor_ops_f64`, `drex_polar_decompose_f64`).
@@ -76,3 +77,49 @@ def polar_decompose(matrix, left=True):
     if is_torch:
         return rot, stretch
     return rot.cpu().numpy(), stretch.cpu().numpy()
+
+
+def voigt_decompose(matrix):
+    """The two independent contractions of the elastic tensor given as 6x6 Voigt matrix:
+    dilatational d_ij = C_ijkk and deviatoric v_ij = C_ijkj stiffness (tensors.py:39-73)."""
+    out = _run(3, matrix, (6, 6), (2, 3, 3))
+    return (out[0], out[1]) if out.ndim == 3 else (out[:, 0], out[:, 1])
+
+
+def mono_project(voigt_vector):
+    """Project the 21-component Voigt vector onto monoclinic symmetry (tensors.py:76-89)."""
+    return _run(4, voigt_vector, (21,), (21,))
+
+
+def ortho_project(voigt_vector):
+    """Project the 21-component Voigt vector onto orthorhombic symmetry (tensors.py:92-103)."""
+    return _run(5, voigt_vector, (21,), (21,))
+
+
+def tetr_project(voigt_vector):
+    """Project the 21-component Voigt vector onto tetragonal symmetry (tensors.py:106-119)."""
+    return _run(6, voigt_vector, (21,), (21,))
+
+
+def hex_project(voigt_vector):
+    """Project the 21-component Voigt vector onto hexagonal symmetry (tensors.py:122-140)."""
+    return _run(7, voigt_vector, (21,), (21,))
+
+
+def upper_tri_to_symmetric(arr):
+    """Symmetric array from the upper triangle of a 3x3 or 6x6 array (or a batch of them)
+    (tensors.py:143-164)."""
+    n = int(np.shape(arr)[-1])
+    if n not in (3, 6) or np.shape(arr)[-2] != n:
+        raise ValueError("upper_tri_to_symmetric handles 3x3 and 6x6 arrays on the device")
+    return _run(10 if n == 3 else 11, arr, (n, n), (n, n))
+
+
+def voigt_matrix_to_vector(matrix):
+    """The 21-component Voigt vector equivalent to the 6x6 Voigt matrix (tensors.py:206-219)."""
+    return _run(8, matrix, (6, 6), (21,))
+
+
+def voigt_vector_to_matrix(vector):
+    """The 6x6 matrix representation of the 21-component Voigt vector (tensors.py:222-251)."""
+    return _run(9, vector, (21,), (6, 6))

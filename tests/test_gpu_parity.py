@@ -1199,6 +1199,24 @@ def test_tensor_helpers_match_golden(drex):
     rot, stretch = t.polar_decompose(torch.as_tensor(g["M"][1]).cuda())
     assert rot.is_cuda
     nt.assert_allclose((stretch @ rot).cpu().numpy(), g["M"][1], rtol=0, atol=1e-13)
+    # the Browaeys & Chevrot helpers (tensors.py:39-164, 206-251): index shuffles and sums of at
+    # most three terms, hence equality (the projections that divide by sqrt(2): 1e-15)
+    dil, dev_ = t.voigt_decompose(g["V"])
+    nt.assert_allclose(dil, g["dilat"], rtol=1e-15, atol=1e-15)
+    nt.assert_allclose(dev_, g["deviat"], rtol=1e-15, atol=1e-15)
+    d0, v0 = t.voigt_decompose(g["V"][3])
+    nt.assert_allclose(d0, g["dilat"][3], rtol=1e-15, atol=1e-15)
+    nt.assert_array_equal(t.mono_project(g["X"]), g["mono"])
+    nt.assert_array_equal(t.ortho_project(g["X"]), g["ortho"])
+    nt.assert_allclose(t.tetr_project(g["X"]), g["tetr"], rtol=1e-15, atol=0)
+    nt.assert_allclose(t.hex_project(g["X"]), g["hex"], rtol=1e-14, atol=1e-15)
+    nt.assert_allclose(t.voigt_matrix_to_vector(g["V"]), g["m2v"], rtol=1e-15, atol=0)
+    nt.assert_allclose(t.voigt_vector_to_matrix(g["X"]), g["v2m"], rtol=1e-15, atol=0)
+    nt.assert_array_equal(t.upper_tri_to_symmetric(g["U"]), g["sym6"])
+    nt.assert_array_equal(t.upper_tri_to_symmetric(g["U3"][2]), g["sym3"][2])
+    # tests/test_tensors.py:16-59: the Voigt vector of a stiffness matrix and back
+    S = drex.StiffnessTensors().olivine
+    nt.assert_allclose(t.voigt_vector_to_matrix(t.voigt_matrix_to_vector(S)), S, rtol=1e-15, atol=1e-13)
     # the Voigt average is rotate() under the hood: one grain, unit fraction
     S = drex.StiffnessTensors().olivine
     R = g["R"][0]
