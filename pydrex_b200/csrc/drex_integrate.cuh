@@ -348,11 +348,7 @@ __device__ __forceinline__ void warp_flows_cheb(const SysSlot &sl, ChunkFlow *ds
     const bool active = si < n;
     const double t = (si == 0) ? ta : ((si == 1) ? tb : tc);
     const double xi = fma(t - sl.t0, sl.inv_span2, -1.0);
-#ifdef DREX_EXP_NOCLENSHAW
-    const double val = active ? sl.coef[c][0] + 1e-30 * xi : 0.0;
-#else
     const double val = active ? clenshaw(sl.coef[c], sl.K, xi) : 0.0;
-#endif
     const int base = active ? 10 * si : 0;
     const double sv = __shfl_sync(0xffffffffu, val, base + 9);
     const int ct = (c < 9) ? 3 * (c % 3) + c / 3 : 0;  // transposed component
@@ -492,9 +488,6 @@ __device__ __forceinline__ void integrate_chunk(const IntegrateArgs &A, const Sy
         }
         if (cheb_flow) {
             if (need_k1) warp_flows_cheb(sl, wf + 3, 1, t, t, t, lane);
-#ifdef DREX_EXP_NOFLOWS
-            if (need_k1)
-#endif
             warp_flows_cheb(sl, wf, 3, fma(BS_A21, h, t), fma(BS_A32, h, t), t + h, lane);
         } else if (!const_flow) {
             if (need_k1) warp_flows(A, sl, wf + 3, 1, t, t, t, lane);
