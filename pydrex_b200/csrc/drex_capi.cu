@@ -798,6 +798,9 @@ int drex_mindex_f32(const double *o_soa, int64_t S, int64_t N, int system_a, int
         drex::mindex_quats_kernel<<<gq, 128, 0, st>>>(o_soa, N, quats, n_store, ops);
         DREX_CUDA_CHECK(cudaGetLastError());
         const int n_tiles = (int)((N + drex::MINDEX_TILE - 1) / drex::MINDEX_TILE);
+        if ((int64_t)n_tiles * (n_tiles + 1) / 2 > 65535)
+            return fail(DREX_E_INVALID, "drex_mindex_f32: textures of more than %d grains are not supported",
+                        361 * drex::MINDEX_TILE);
         dim3 gp((unsigned)S, (unsigned)((int64_t)n_tiles * (n_tiles + 1) / 2));
         if (refl) {
             drex::mindex_pairs_reflect_kernel<<<gp, drex::MINDEX_TILE, 0, st>>>(quats, N, n_tiles, tmax, thr, cnt);

@@ -96,7 +96,17 @@ __device__ __forceinline__ void grain_rhs(const double (&a)[9], const double (&D
 
     double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;  // 2 x relative slip rates by system
     double w0 = 0.0, w1 = 0.0, w2 = 0.0;            // |gamma_i|^(p/n) for i = 0..2
-    const bool all_zero = (I0 == 0.0) & (I1 == 0.0) & (I2 == 0.0) & (I3 == 0.0);
+    bool all_zero = (I0 == 0.0) & (I1 == 0.0) & (I2 == 0.0);
+    if (all_zero && !(PROBE || !olivine || !inf3)) {
+        // the shortcut I3 = I1 above assumed a symmetric D; core.derivatives takes any matrix
+        // from its caller, and the reference tests the true fourth invariant (core.py:721).
+        // Rare, so the twelve operations are only spent here.
+        double Da0[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) Da0[i] = D[3 * i] * a[0] + D[3 * i + 1] * a[1] + D[3 * i + 2] * a[2];
+        I3 = a[6] * Da0[0] + a[7] * Da0[1] + a[8] * Da0[2];
+    }
+    all_zero = all_zero & (I3 == 0.0);
     const bool default_exponents =
         (MODE == GRAIN_RUNTIME) ? (fc.default_exponents != 0) : (MODE == GRAIN_OLIVINE_DEFAULT);
 

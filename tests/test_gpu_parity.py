@@ -1286,3 +1286,46 @@ def test_large_chebyshev_table_uses_the_same_interpolant(drex):
         nt.assert_allclose(o, results[0][0], rtol=0, atol=1e-9)
         nt.assert_allclose(f, results[0][1], rtol=1e-7, atol=1e-12)
         nt.assert_allclose(F, results[0][2], rtol=0, atol=1e-10)
+
+
+def test_more_systems_than_a_grid_dimension(drex, oracle):
+    """More than 65535 systems (the limit of gridDim.y, where the layout, derivative and
+    quaternion kernels used to carry the system index): construct, integrate, read back."""
+    import torch
+
+    P, N = 33000, 8
+    ens = drex.ParticleEnsemble(P, N, TWO_PHASE, seed=3)
+    assert ens.S > 65535
+    o0 = ens.orientations().cpu().numpy()
+    L = torch.zeros((P, 3, 3), dtype=torch.float64)
+    L[:, 1, 0] = 2.0
+    ens.update(0.0, 0.02, L)
+    o1 = ens.orientations().cpu().numpy()
+    assert np.isfinite(o1).all() and np.abs(o1 - o0).max() > 1e-4
+    nt.assert_allclose(ens.fractions().sum(dim=-1).cpu().numpy(), 1.0, atol=1e-13)
+    # the last system went through the layout kernels like the first
+    gram = np.einsum("gij,glj->gil", o1[-1, -1], o1[-1, -1])
+    assert np.abs(gram - np.eye(3)).max() < 1e-3
+    C = ens.voigt_averages().cpu().numpy()
+    assert np.isfinite(C).all()
+    M = ens.misorientation_indices(drex.LatticeSystem.orthorhombic, phase_slot=0, batch=40000).cpu().numpy()
+    assert M.shape == (P,) and np.isfinite(M).all()
+    od, fd = drex.derivatives(4, 0, 0, N, o1[-1, 0], np.full(N, 1 / N), np.array([[0.0, 1, 0], [1, 0, 0], [0, 0, 0]]),
+                              np.array([[0.0, 0, 0], [2, 0, 0], [0, 0, 0]]), np.eye(3), 1.5, 3.5, 5.0, 125.0, 0.7)
+    assert np.isfinite(od).all()
+    # a strain rate that is not symmetric: the fourth invariant decides whether the grain deforms
+    # (core.py:721), like in the reference
+    for D in (np.array([[0.0, 0, 1], [0, 0, 0], [0, 0, 0]]), np.array([[0.0, 0, 0], [0, 0, 0], [1, 0, 0]]),
+              np.array([[0.0, 0, 0], [0, 0, 0], [1e-3, 0, 0.0]])):
+        o = np.stack([np.eye(3), Rotation_random_one()])
+        args = (4, 0, 0, 2, o, np.full(2, 0.5), D, D, np.eye(3), 1.5, 3.5, 5.0, 125.0, 1.0)
+        od, fd = drex.derivatives(*args)
+        od_ref, fd_ref = oracle.derivatives(*args)
+        nt.assert_allclose(od, od_ref, rtol=1e-10, atol=1e-13, equal_nan=True)
+        nt.assert_allclose(fd, fd_ref, rtol=1e-10, atol=1e-15, equal_nan=True)
+
+
+def Rotation_random_one():
+    from scipy.spatial.transform import Rotation
+
+    return Rotation.random(1, random_state=5).as_matrix()[0]
