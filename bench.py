@@ -486,7 +486,7 @@ def run_gpu(args):
     failed = int(sum_over_ranks(res["failed"]))
     g_evals = res["grain_evals"]
     evals = sum_over_ranks(g_evals)
-    internal = sum_over_ranks(res["chunk_accepts"] * N / ens.n_chunks)  # steps are per chunk of 32 grains
+    internal = sum_over_ranks(res["chunk_accepts"] * N / ens.n_chunks)  # steps are per chunk of grains
     outer = float(world * S * N * K)
     secs = total_ms * 1e-3
     value = outer / secs

@@ -172,6 +172,10 @@ typedef struct drex_tolerances {
  * grain-boundary sliding needs: S * 9 * N doubles more). */
 size_t drex_integrate_workspace_bytes(int64_t S, int64_t N, int device, int in_place);
 
+/* Grains per integration chunk (one warp's unit of work, with its own step sequence): the
+ * second dimension of h_io is ceil(N / drex_integrate_chunk_grains()). */
+int32_t drex_integrate_chunk_grains(void);
+
 /* Advance S systems from t0 to t1 (per particle), then apply grain-boundary sliding once
  * against the interval-start orientations (minerals.py:464-474, utils.apply_gbs
  * utils.py:159-180) and the final clip/renormalise (utils.extract_vars utils.py:183-190).

@@ -20,7 +20,7 @@ The algorithm
 
   So each grain carries ten unknowns (nine direction cosines and v_g) that do not see any
   other grain until the end of the interval, where one normalisation recovers the fractions.
-* Grains are integrated in chunks of 32 (one warp): every chunk walks from t0 to t1 with its
+* Grains are integrated in chunks of 32 (one warp; `chunk`): every chunk walks from t0 to t1 with its
   OWN Bogacki-Shampine 3(2) steps (FSAL), controlled by the weighted max norm of ITS grains
   with the reference's weights (minerals.py:523-524): atol + rtol |y| per component, for the
   fraction components through f_g ~ f_g(t0) exp(v_g), err_f = f_g err_v.
@@ -88,7 +88,7 @@ def integrate_F(F0, get_L, t0, t1, rtol, atol_abs, atol_rel):
 def update_orientations(orientations, fractions, regime, phase, fabric, params,
                         deformation_gradient, get_velocity_gradient, pathline,
                         rtol=1e-6, atol_abs=1e-4, atol_rel=1e-6, max_steps=100000, stats=None,
-                        h_carry=None, global_steps=False):
+                        h_carry=None, global_steps=False, chunk=CHUNK):
     """The device algorithm for ONE system (regimes 4 and 6).  Returns (F, o, f) like
     oracle.update_orientations."""
     assert regime in (4, 6)
@@ -106,8 +106,8 @@ def update_orientations(orientations, fractions, regime, phase, fabric, params,
     def get_L(t):
         return np.asarray(get_velocity_gradient(t, get_position(t)), dtype=float)
 
-    n_chunks = (N + CHUNK - 1) // CHUNK
-    chunk_of = np.arange(N) // CHUNK
+    n_chunks = (N + chunk - 1) // chunk  # the kernel's drex_integrate_chunk_grains()
+    chunk_of = np.arange(N) // chunk
 
     def flows(tc):  # per-chunk times -> per-grain (L/s, s)
         Ls, s = np.empty((n_chunks, 9)), np.empty(n_chunks)

@@ -30,7 +30,7 @@ EXPORTS = (
     "drex_fluidity_unpack_f64", "drex_fluidity_pack_f64",
     "drex_derivatives_workspace_bytes", "drex_derivatives_f64", "drex_grain_probe_f64",
     "drex_grain_helper_f64",
-    "drex_integrate_workspace_bytes", "drex_integrate_f64",
+    "drex_integrate_workspace_bytes", "drex_integrate_chunk_grains", "drex_integrate_f64",
     "drex_voigt_average_f64", "drex_elasticity_components_f64",
     "drex_axis_scatter_f64",
     "drex_flow_field_f64",
@@ -158,6 +158,8 @@ def _declare(lib):
         [vp, vp, vp, i32, i32, c.POINTER(DrexParams), i64] + [vp] * 6 + [vp]
     )
     lib.drex_grain_helper_f64.argtypes = [i32, vp, vp, vp, vp, dbl, dbl, dbl, dbl, vp, vp]
+    lib.drex_integrate_chunk_grains.restype = i32
+    lib.drex_integrate_chunk_grains.argtypes = []
     lib.drex_integrate_workspace_bytes.restype = szt
     lib.drex_integrate_workspace_bytes.argtypes = [i64, i64, i32, i32]
     lib.drex_integrate_f64.argtypes = (
@@ -203,6 +205,11 @@ def load():
                 )
             _lib = _declare(ctypes.CDLL(LIB_PATH))
     return _lib
+
+
+def chunk_grains():
+    """Grains per integration chunk (one step sequence, one carried step each)."""
+    return int(load().drex_integrate_chunk_grains())
 
 
 def last_error():

@@ -112,7 +112,9 @@ inline size_t integrate_smem_bytes() {
 }
 
 // Per-CTA scratch: the per-chunk partial sums of the systems in flight.
-inline int64_t integrate_chunk_cap(int64_t N) { return ((N + 31) / 32 + 31) / 32 * 32; }
+inline int64_t integrate_chunk_cap(int64_t N) {
+    return ((N + drex::INT_CHUNK - 1) / drex::INT_CHUNK + 31) / 32 * 32;
+}
 // One lane mask per chunk of every system: which grains slide (written by integrate_kernel, read
 // by gbs_restore_kernel).
 inline size_t integrate_mask_bytes(int64_t S, int64_t N) {
@@ -267,6 +269,8 @@ int drex_grain_helper_f64(int op, const double *in0, const double *in1, const do
     DREX_CUDA_CHECK(cudaGetLastError());
     return DREX_OK;
 }
+
+int32_t drex_integrate_chunk_grains(void) { return drex::INT_CHUNK; }
 
 size_t drex_integrate_workspace_bytes(int64_t S, int64_t N, int device, int in_place) {
     if (S <= 0 || N <= 0) return 256;

@@ -42,20 +42,32 @@
 
 namespace drex {
 
-#ifndef DREX_INT_BLOCK
-#define DREX_INT_BLOCK 512
+// A warp's unit of work is a CHUNK of 32 * INT_G grains, INT_G per lane, with 512 / INT_G threads
+// per CTA.  INT_G = 1 is the product.  INT_G = 2 (-DDREX_INT_G=2: half as many warps with 255
+// registers and two independent dependency chains each; step control, stage flows and chunk
+// bookkeeping paid once per 64 grains) is kept as a measured experiment: the right-hand side
+// alone runs at 95% of the one-grain rate that way, but the whole kernel takes 5.1 ms instead of
+// 3.7 ms per launch on the bench workload -- the sections around the stages are latency chains,
+// whose throughput is warps / latency, so halving both their count and the warps gains nothing,
+// and a 64-grain chunk takes the step its worst grain needs (5% more right-hand sides).
+#ifndef DREX_INT_G
+#define DREX_INT_G 1
 #endif
-constexpr int INT_BLOCK = DREX_INT_BLOCK;
+constexpr int INT_G = DREX_INT_G;
+constexpr int INT_CHUNK = 32 * INT_G;
+constexpr int INT_BLOCK = 512 / INT_G;
 constexpr int INT_WARPS = INT_BLOCK / 32;
 constexpr int INT_CTAS_PER_SM = 1;
 constexpr int INT_NCTX = 3;   // systems in flight per CTA
 constexpr int INT_KMAX = 33;  // L(t) tables up to this many nodes live in shared memory
-// per-warp shared-memory rows of 32 grains: 0-8 state, 9-17 FSAL slope, 18-26 new state, 27-35
-// error combination (the state and new-state rows swap roles on an accepted step), 36-45 the
+// per-warp shared-memory rows of 32 grains.  Per sub-chunk j (the j-th grain of every lane) a
+// row set of 36: 0-8 state, 9-17 FSAL slope, 18-26 new state, 27-35 error combination (the state
+// and new-state rows swap roles on an accepted step); then, per sub-chunk, the ten rows of the
 // prefetched next chunk (orientation rows 0-8 of o_in, row 9 of f_in; TMA target).  Keeping the
-// accumulators here instead of in registers is what lets 512 threads share the register file.
-constexpr int ROW_A = 0, ROW_K1 = 9, ROW_Y = 18, ROW_E = 27, ROW_PF = 36;
-constexpr int WARP_ROWS = 46;
+// accumulators here instead of in registers is what keeps the stage loop out of local memory.
+constexpr int ROW_A = 0, ROW_K1 = 9, ROW_Y = 18, ROW_E = 27, ROW_SET = 36;
+constexpr int ROW_PF = ROW_SET * INT_G, ROW_PF_SET = 10;
+constexpr int WARP_ROWS = (ROW_SET + ROW_PF_SET) * INT_G;
 constexpr int WARP_DOUBLES = WARP_ROWS * 32;
 
 struct TolArgs {
@@ -455,17 +467,19 @@ __device__ __forceinline__ uint32_t err_bits(double err, double ynew, double ato
 #endif
 
 struct ChunkResult {
-    double v, h_next;
+    double v[INT_G], h_next;
     int status, n_rhs, n_acc, n_rej, row;
 };
 
-// One chunk of 32 grains from t0 to t1: state in rows ROW_A.. of `rows` (already loaded), one
-// grain per lane.  Returns with the final orientation in rows res.row.. and v_g in res.v.
+// One chunk of 32 * INT_G grains from t0 to t1: state in rows ROW_A.. of each row set of `rows`
+// (already loaded), INT_G grains per lane.  Returns with the final orientations in rows res.row..
+// and v_g in res.v.  Everything per grain is written as a loop over j < INT_G in straight-line
+// code, so that the two dependency chains of a lane interleave.
 template <int MODE>
 __device__ __forceinline__ void integrate_chunk(const IntegrateArgs &A, const SysSlot &sl,
                                                 const FabricConsts &fc, const double *__restrict__ mt,
-                                                double *rows, ChunkFlow *wf, int lane, double f0,
-                                                double h, ChunkResult &res
+                                                double *rows, ChunkFlow *wf, int lane,
+                                                const double (&f0)[INT_G], double h, ChunkResult &res
 #ifdef DREX_PHASE_TIMERS
                                                 , long long (&ptimer)[8], long long &pmark
 #endif
@@ -476,9 +490,13 @@ __device__ __forceinline__ void integrate_chunk(const IntegrateArgs &A, const Sy
     const ChunkFlow *fl = const_flow ? &sl.cflow : wf;
     const int fstride = const_flow ? 0 : 1;
     const double rscale = sl.rscale;
-    double *sa = rows + ROW_A * 32 + lane, *sy = rows + ROW_Y * 32 + lane;
-    double *const sk = rows + ROW_K1 * 32 + lane, *const se = rows + ROW_E * 32 + lane;
-    double t = t_begin, v = 0.0, kv1 = 0.0, h_carry = h;
+    // row offsets inside a row set; the state and new-state rows swap on an accepted step
+    int off_a = ROW_A * 32 + lane, off_y = ROW_Y * 32 + lane;
+    const int off_k = ROW_K1 * 32 + lane, off_e = ROW_E * 32 + lane;
+    double t = t_begin, h_carry = h;
+    double v[INT_G], kv1[INT_G];
+#pragma unroll
+    for (int j = 0; j < INT_G; ++j) v[j] = kv1[j] = 0.0;
     int n_rhs = 0, n_acc = 0, n_rej = 0, status = 0;
     bool need_k1 = true, last_rejected = false;
     while (span != 0.0) {
@@ -494,65 +512,80 @@ __device__ __forceinline__ void integrate_chunk(const IntegrateArgs &A, const Sy
             warp_flows(A, sl, wf, 3, fma(BS_A21, h, t), fma(BS_A32, h, t), t + h, lane);
         }
         DREX_MARK(6)
-        double k[9], st[9], e, kv = 0.0, vy = 0.0, ve = 0.0;
-        if (need_k1) {
+        double k[INT_G][9], st[INT_G][9], e[INT_G], kv[INT_G], vy[INT_G], ve[INT_G];
 #pragma unroll
-            for (int c = 0; c < 9; ++c) st[c] = sa[c * 32];
-        } else {
+        for (int j = 0; j < INT_G; ++j) {
+            const double *r = rows + j * ROW_SET * 32;
+            kv[j] = vy[j] = ve[j] = 0.0;
+            if (need_k1) {
 #pragma unroll
-            for (int c = 0; c < 9; ++c) st[c] = fma(h * BS_A21, sk[c * 32], sa[c * 32]);
+                for (int c = 0; c < 9; ++c) st[j][c] = r[off_a + c * 32];
+            } else {
+#pragma unroll
+                for (int c = 0; c < 9; ++c) st[j][c] = fma(h * BS_A21, r[off_k + c * 32], r[off_a + c * 32]);
+            }
         }
         // The stages run as a ROLLED loop: one copy of the right-hand side in the hot loop keeps
         // it inside the instruction cache.  The bookkeeping between the stages differs per stage
-        // and sits behind warp-uniform branches: rows sy / se hold the partial new state
+        // and sits behind warp-uniform branches: rows y / e hold the partial new state
         // y + h (b1 k1 + b2 k2) and the partial error e1 k1 + e2 k2 after stage 2, the full ones
         // after stage 3.  Stage -1 (first step of the interval only) is the slope at t0.
 #pragma unroll 1
         for (int stg = need_k1 ? -1 : 0; stg < 3; ++stg) {
-            clip9(st);
             const ChunkFlow &sf = fl[(stg & 3) * fstride];  // -1 -> [3]: the step's start time
-            chunk_rhs<MODE>(st, sf, rscale, fc, mt, k, e);
-            kv = f_active ? sf.nks * e : 0.0;
-            if (stg < 0) {
 #pragma unroll
-                for (int c = 0; c < 9; ++c) {
-                    sk[c * 32] = k[c];
-                    st[c] = fma(h * BS_A21, k[c], sa[c * 32]);
-                }
-                kv1 = kv;
-            } else if (stg == 0) {
+            for (int j = 0; j < INT_G; ++j) clip9(st[j]);
 #pragma unroll
-                for (int c = 0; c < 9; ++c) {
-                    const double ac = sa[c * 32], kc = sk[c * 32];
-                    sy[c * 32] = fma(h * BS_B2, k[c], fma(h * BS_B1, kc, ac));
-                    se[c * 32] = fma(BS_E2, k[c], BS_E1 * kc);
-                    st[c] = fma(h * BS_A32, k[c], ac);  // stage 3 starts from y + 3h/4 k2
-                }
-                vy = fma(h * BS_B2, kv, fma(h * BS_B1, kv1, v));
-                ve = fma(BS_E2, kv, BS_E1 * kv1);
-            } else if (stg == 1) {
+            for (int j = 0; j < INT_G; ++j) chunk_rhs<MODE>(st[j], sf, rscale, fc, mt, k[j], e[j]);
 #pragma unroll
-                for (int c = 0; c < 9; ++c) {
-                    const double yn = fma(h * BS_B3, k[c], sy[c * 32]);
-                    sy[c * 32] = yn;
-                    se[c * 32] = fma(BS_E3, k[c], se[c * 32]);
-                    st[c] = yn;  // stage 4 is evaluated at the new state itself
+            for (int j = 0; j < INT_G; ++j) {
+                double *r = rows + j * ROW_SET * 32;
+                kv[j] = f_active ? sf.nks * e[j] : 0.0;
+                if (stg < 0) {
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) {
+                        r[off_k + c * 32] = k[j][c];
+                        st[j][c] = fma(h * BS_A21, k[j][c], r[off_a + c * 32]);
+                    }
+                    kv1[j] = kv[j];
+                } else if (stg == 0) {
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) {
+                        const double ac = r[off_a + c * 32], kc = r[off_k + c * 32];
+                        r[off_y + c * 32] = fma(h * BS_B2, k[j][c], fma(h * BS_B1, kc, ac));
+                        r[off_e + c * 32] = fma(BS_E2, k[j][c], BS_E1 * kc);
+                        st[j][c] = fma(h * BS_A32, k[j][c], ac);  // stage 3 starts from y + 3h/4 k2
+                    }
+                    vy[j] = fma(h * BS_B2, kv[j], fma(h * BS_B1, kv1[j], v[j]));
+                    ve[j] = fma(BS_E2, kv[j], BS_E1 * kv1[j]);
+                } else if (stg == 1) {
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) {
+                        const double yn = fma(h * BS_B3, k[j][c], r[off_y + c * 32]);
+                        r[off_y + c * 32] = yn;
+                        r[off_e + c * 32] = fma(BS_E3, k[j][c], r[off_e + c * 32]);
+                        st[j][c] = yn;  // stage 4 is evaluated at the new state itself
+                    }
+                    vy[j] = fma(h * BS_B3, kv[j], vy[j]);
+                    ve[j] = fma(BS_E3, kv[j], ve[j]);
                 }
-                vy = fma(h * BS_B3, kv, vy);
-                ve = fma(BS_E3, kv, ve);
             }
         }
         DREX_MARK(3)
         uint32_t eb = 0;
 #pragma unroll
-        for (int c = 0; c < 9; ++c) {
-            const double err = h * fma(BS_E4, k[c], se[c * 32]);
-            eb = max(eb, err_bits(err, sy[c * 32], atol_abs, relw));
-        }
-        if (f_active) {
-            // the fraction components: f_g ~ f_g(t0) e^{v_g}, err_f = f_g err_v
-            const double fe = f0 * exp_tab(vy, mt);
-            eb = max(eb, err_bits(fe * (h * fma(BS_E4, kv, ve)), fe, A.tol.atol_abs_f, relw));
+        for (int j = 0; j < INT_G; ++j) {
+            const double *r = rows + j * ROW_SET * 32;
+#pragma unroll
+            for (int c = 0; c < 9; ++c) {
+                const double err = h * fma(BS_E4, k[j][c], r[off_e + c * 32]);
+                eb = max(eb, err_bits(err, r[off_y + c * 32], atol_abs, relw));
+            }
+            if (f_active) {
+                // the fraction components: f_g ~ f_g(t0) e^{v_g}, err_f = f_g err_v
+                const double fe = f0[j] * exp_tab(vy[j], mt);
+                eb = max(eb, err_bits(fe * (h * fma(BS_E4, kv[j], ve[j])), fe, A.tol.atol_abs_f, relw));
+            }
         }
         eb = __reduce_max_sync(0xffffffffu, eb);
         n_rhs += need_k1 ? 4 : 3;
@@ -572,13 +605,17 @@ __device__ __forceinline__ void integrate_chunk(const IntegrateArgs &A, const Sy
             ++n_acc;
             last_rejected = false;
             t += h;
-            v = vy;
-            kv1 = kv;
-            double *tmp = sa;
-            sa = sy;
-            sy = tmp;
+            const int tmp = off_a;
+            off_a = off_y;
+            off_y = tmp;
 #pragma unroll
-            for (int c = 0; c < 9; ++c) sk[c * 32] = k[c];
+            for (int j = 0; j < INT_G; ++j) {
+                double *r = rows + j * ROW_SET * 32;
+                v[j] = vy[j];
+                kv1[j] = kv[j];
+#pragma unroll
+                for (int c = 0; c < 9; ++c) r[off_k + c * 32] = k[j][c];
+            }
             const double remaining = t_end - t;
             if (fabs(remaining) <= 1e-13 * fmax(fabs(t_end), fabs(span))) break;
             if (A.tol.max_step_frac > 0.0 && fabs(h_next) > A.tol.max_step_frac * fabs(span))
@@ -597,13 +634,14 @@ __device__ __forceinline__ void integrate_chunk(const IntegrateArgs &A, const Sy
         DREX_MARK(7)
     }
     DREX_MARK(7)
-    res.v = v;
+#pragma unroll
+    for (int j = 0; j < INT_G; ++j) res.v[j] = v[j];
     res.h_next = h_carry;
     res.status = status;
     res.n_rhs = n_rhs;
     res.n_acc = n_acc;
     res.n_rej = n_rej;
-    res.row = (sa == rows + ROW_A * 32 + lane) ? ROW_A : ROW_Y;
+    res.row = (off_a == ROW_A * 32 + lane) ? ROW_A : ROW_Y;
 }
 
 // ---- per-system prologue (one warp, once per system and interval) ------------------------
@@ -750,7 +788,7 @@ __device__ __noinline__ void prepare_system(const IntegrateArgs &A, const Fabric
     // grain-boundary migration active? (enstatite strain energy is identically zero,
     // core.py:674-684 loops over systems 0..2 only)
     const double kappa = (slip && phase == 0) ? rscale * A.sys_vol_frac[s] * A.gbm_mobility : 0.0;
-    const int n_chunks = (int)((A.N + 31) / 32);
+    const int n_chunks = (int)((A.N + INT_CHUNK - 1) / INT_CHUNK);
     if (lane == 0) {
         sl.busy = 1;
         sl.sys = s;
@@ -872,11 +910,11 @@ constexpr int FIN_BATCH = 8;
 __device__ __noinline__ void finalize_system(const IntegrateArgs &A, SysSlot &sl, const SlotScratch sc,
                                              int lane) {
     const int64_t N = A.N, s = sl.sys;
-    const int nq = sl.n_chunks;
+    const int nq = (int)((N + 31) / 32);  // the sweeps and the masks go by 32 grains
     double *f_out = A.f_out + s * N;
     uint32_t *mask_out = A.slide_mask + s * nq;
     double acc = 0.0;
-    for (int q = lane; q < nq; q += 32) acc += __ldcg(sc.psum + q);
+    for (int q = lane; q < sl.n_chunks; q += 32) acc += __ldcg(sc.psum + q);
     const double S1 = warp_sum(acc);
     const double floor_v = A.gbs_threshold / (double)N;
     // first sweep: S2 = sum of the fractions after sliding grains were set to chi / N
@@ -924,12 +962,12 @@ __device__ __noinline__ void finalize_system(const IntegrateArgs &A, SysSlot &sl
         const int status = max(sl.status, sl.status0);
         const unsigned long long ca = sl.count_a, cb = sl.count_b;
         const long long n_rhs = (long long)(ca & 0xffffffffull);
-        const int64_t live_last = N - (int64_t)(nq - 1) * 32;
+        const int64_t live_last = N - (int64_t)(sl.n_chunks - 1) * INT_CHUNK;
         A.status[s] = status;
         if (A.n_rhs) A.n_rhs[s] = (int32_t)n_rhs;
         if (A.n_accept) A.n_accept[s] = (int32_t)(cb & 0xffffffffull);
         if (A.n_reject) A.n_reject[s] = (int32_t)(ca >> 32);
-        if (A.grain_evals) A.grain_evals[s] = 32 * n_rhs - (32 - live_last) * (int64_t)sl.rhs_last;
+        if (A.grain_evals) A.grain_evals[s] = INT_CHUNK * n_rhs - (INT_CHUNK - live_last) * (int64_t)sl.rhs_last;
     }
     __threadfence_block();
     __syncwarp();
@@ -1015,16 +1053,16 @@ integrate_kernel(const __grid_constant__ IntegrateArgs A, const __grid_constant_
     const bool rows_aligned = ((N & 1) == 0) && ((reinterpret_cast<uintptr_t>(A.o_in) & 15) == 0) &&
                               ((reinterpret_cast<uintptr_t>(A.f_in) & 15) == 0);
     auto prefetch = [&](const ChunkRef &ch) {
-        // ten 256 B rows (nine of o_in, one of f_in) of chunk ch into rows ROW_PF..: one copy per
-        // lane, issued by ten lanes at once
+        // ten rows of INT_CHUNK grains (nine of o_in, one of f_in) of chunk ch into rows ROW_PF..,
+        // component c at row ROW_PF + c * INT_G: one copy per lane, issued by ten lanes at once
         if (!rows_aligned) return;
         const int64_t s = sh.slot[ch.seq % INT_NCTX].sys;
-        const int64_t g0 = (int64_t)ch.q * 32;
-        const uint32_t row_bytes = (uint32_t)(((N - g0 < 32) ? (N - g0) : 32) * sizeof(double));
+        const int64_t g0 = (int64_t)ch.q * INT_CHUNK;
+        const uint32_t row_bytes = (uint32_t)(((N - g0 < INT_CHUNK) ? (N - g0) : INT_CHUNK) * sizeof(double));
         if (lane == 0) mbar_expect_tx(mbar, 10 * row_bytes);
         __syncwarp();
-        if (lane < 9) bulk_g2s(rows + (ROW_PF + lane) * 32, A.o_in + (s * 9 + lane) * N + g0, row_bytes, mbar);
-        if (lane == 9) bulk_g2s(rows + (ROW_PF + 9) * 32, A.f_in + s * N + g0, row_bytes, mbar);
+        if (lane < 9) bulk_g2s(rows + (ROW_PF + lane * INT_G) * 32, A.o_in + (s * 9 + lane) * N + g0, row_bytes, mbar);
+        if (lane == 9) bulk_g2s(rows + (ROW_PF + 9 * INT_G) * 32, A.f_in + s * N + g0, row_bytes, mbar);
     };
 
     // deferred completion count of the last chunk this warp finished (see below)
@@ -1054,8 +1092,7 @@ integrate_kernel(const __grid_constant__ IntegrateArgs A, const __grid_constant_
     while (cur.seq >= 0) {
         SysSlot &sl = sh.slot[cur.seq % INT_NCTX];
         const int64_t s = sl.sys;
-        const int64_t g = (int64_t)cur.q * 32 + lane;
-        const bool live = g < N;
+        const int64_t g = (int64_t)cur.q * INT_CHUNK + lane;  // + 32 j for the lane's j-th grain
         // The warp that drew chunk `prep_at` of a system prepares the NEXT system before starting
         // on its chunk, so that the slot is ready long before the current system runs out.  (Not
         // at the time of the draw: a warp still holding an unfinished chunk must never wait for
@@ -1069,21 +1106,31 @@ integrate_kernel(const __grid_constant__ IntegrateArgs A, const __grid_constant_
         }
         DREX_MARK(1)
         // ---- this chunk's state into rows ROW_A.., then the prefetch rows are free again
-        double f0;
+        double f0[INT_G];
         if (rows_aligned) {
             mbar_wait(mbar, parity);
             parity ^= 1u;
-            const double *pf = rows + ROW_PF * 32 + lane;
 #pragma unroll
-            for (int c = 0; c < 9; ++c) rows[(ROW_A + c) * 32 + lane] = live ? pf[c * 32] : 0.0;
-            f0 = live ? pf[9 * 32] : 0.0;
+            for (int j = 0; j < INT_G; ++j) {
+                const bool live = g + 32 * j < N;
+                const double *pf = rows + (ROW_PF + j) * 32 + lane;
+                double *r = rows + (j * ROW_SET + ROW_A) * 32 + lane;
+#pragma unroll
+                for (int c = 0; c < 9; ++c) r[c * 32] = live ? pf[c * INT_G * 32] : 0.0;
+                f0[j] = live ? pf[9 * INT_G * 32] : 0.0;
+            }
             // generic-proxy reads of the prefetch rows, then an async-proxy overwrite of them
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         } else {
 #pragma unroll
-            for (int c = 0; c < 9; ++c)
-                rows[(ROW_A + c) * 32 + lane] = live ? A.o_in[(s * 9 + c) * N + g] : 0.0;
-            f0 = live ? A.f_in[s * N + g] : 0.0;
+            for (int j = 0; j < INT_G; ++j) {
+                const int64_t gj = g + 32 * j;
+                const bool live = gj < N;
+                double *r = rows + (j * ROW_SET + ROW_A) * 32 + lane;
+#pragma unroll
+                for (int c = 0; c < 9; ++c) r[c * 32] = live ? A.o_in[(s * 9 + c) * N + gj] : 0.0;
+                f0[j] = live ? A.f_in[s * N + gj] : 0.0;
+            }
         }
         __syncwarp();
         DREX_MARK(2)
@@ -1099,9 +1146,12 @@ integrate_kernel(const __grid_constant__ IntegrateArgs A, const __grid_constant_
             sh.ws_nxt_q[warp] = nxt.q;
         }
         __syncwarp();
-        f0 = fmax(f0, 0.0);  // utils.py:188
         ChunkResult res;
-        res.v = 0.0;
+#pragma unroll
+        for (int j = 0; j < INT_G; ++j) {
+            f0[j] = fmax(f0[j], 0.0);  // utils.py:188
+            res.v[j] = 0.0;
+        }
         res.h_next = 0.0;
         res.status = res.n_rhs = res.n_acc = res.n_rej = 0;
         res.row = ROW_A;
@@ -1136,21 +1186,27 @@ integrate_kernel(const __grid_constant__ IntegrateArgs A, const __grid_constant_
         // has to survive the integration in registers)
         {
             SysSlot &sr = sh.slot[cur.seq % INT_NCTX];
-            const int64_t ss = sr.sys, gg = (int64_t)cur.q * 32 + lane;
-            const bool alive = gg < N;
+            const int64_t ss = sr.sys;
             const bool slip = sr.mode != 4;
-            const double *fin = rows + res.row * 32 + lane;
-            double *o_out = A.o_out + ss * 9 * N + gg;
-            if (alive) {
+            double usum = 0.0;
 #pragma unroll
-                for (int c = 0; c < 9; ++c) {
-                    const double y = slip ? fin[c * 32] : fin[c * 32] + sr.Q[c];
-                    o_out[c * N] = clip_int(y);
+            for (int j = 0; j < INT_G; ++j) {
+                const int64_t gg = (int64_t)cur.q * INT_CHUNK + 32 * j + lane;
+                const bool alive = gg < N;
+                const double *fin = rows + (j * ROW_SET + res.row) * 32 + lane;
+                double *o_out = A.o_out + ss * 9 * N + gg;
+                if (alive) {
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) {
+                        const double y = slip ? fin[c * 32] : fin[c * 32] + sr.Q[c];
+                        o_out[c * N] = clip_int(y);
+                    }
                 }
+                const double u = sr.f_active ? f0[j] * exp_tab(res.v[j], math_tab) : f0[j];
+                if (alive) A.f_out[ss * N + gg] = u;
+                usum += alive ? u : 0.0;
             }
-            const double u = sr.f_active ? f0 * exp_tab(res.v, math_tab) : f0;
-            if (alive) A.f_out[ss * N + gg] = u;
-            const double part = warp_sum(alive ? u : 0.0);
+            const double part = warp_sum(usum);
             if (lane == 0) {
                 slot_scratch(A, cur.seq % INT_NCTX).psum[cur.q] = part;
                 if (A.h_io != nullptr && slip) A.h_io[ss * sr.n_chunks + cur.q] = res.h_next * sr.s_end;

@@ -136,8 +136,9 @@ class ParticleEnsemble:
         self._weight = torch.tensor([4.0 if ph == 0 else 1.0 for ph in self.phases],
                                     dtype=torch.float32, device=dev).repeat(P)
         self.order = torch.argsort(self._weight, descending=True, stable=True).to(i32)
-        # the integrator steps chunks of 32 grains independently: one carried step per chunk
-        self.n_chunks = (N + 31) // 32
+        # the integrator steps chunks of grains independently: one carried step per chunk
+        self.chunk_grains = _lib.chunk_grains()
+        self.n_chunks = -(-N // self.chunk_grains)
         self.h = torch.zeros((S, self.n_chunks), dtype=f64, device=dev)
         # status, n_rhs, n_accept, n_reject per system, the counters summed over its chunks
         self.stats = torch.zeros((4, S), dtype=i32, device=dev)

@@ -208,7 +208,7 @@ def _integrate_minerals(minerals, params, deformation_gradients, get_velocity_gr
     tol, explicit_first = _tolerances(kwargs, t_b - t_a, N)
     dev = torch.device("cuda", torch.cuda.current_device())
     S = len(active)
-    n_chunks = (N + 31) // 32
+    n_chunks = -(-N // _lib.chunk_grains())
     f64 = torch.float64
     o_aos = torch.as_tensor(np.stack([np.asarray(m.orientations[-1], dtype=np.float64)
                                       for m in active]).reshape(S, N, 9)).to(dev)

@@ -623,9 +623,9 @@ def test_chunk_integrator_matches_its_numpy_model(drex, oracle):
         st = {}
         F, o, f = device_model.update_orientations(
             o, f, 4, 0, 0, TWO_PHASE, F, _const(L[1]), (0.05 * k, 0.05 * (k + 1), lambda t: np.zeros(3)),
-            stats=st, h_carry=h)
+            stats=st, h_carry=h, chunk=ens.chunk_grains)
         h = st["h"]
-        live = np.minimum(32, N - 32 * np.arange(len(h)))
+        live = np.minimum(ens.chunk_grains, N - ens.chunk_grains * np.arange(len(h)))
         n_model += int((st["n_rhs"] * live).sum())
     agree = np.isclose(f_dev, f, rtol=0.2)  # same GBS decision
     assert agree.mean() > 0.995
