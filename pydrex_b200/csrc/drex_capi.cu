@@ -807,7 +807,8 @@ int drex_mindex_f32(const double *o_soa, int64_t S, int64_t N, int system_a, int
                         361 * drex::MINDEX_TILE);
         dim3 gp((unsigned)S, (unsigned)((int64_t)n_tiles * (n_tiles + 1) / 2));
         if (refl) {
-            drex::mindex_pairs_reflect_kernel<<<gp, drex::MINDEX_TILE, 0, st>>>(quats, N, n_tiles, tmax, thr, cnt);
+            drex::mindex_pairs_reflect_kernel<<<gp, drex::MINDEX_TILE, 0, st>>>(quats, N, n_tiles, tmax, thr, cnt,
+                                                                                0x8000000080000000ull);
         } else
         switch (n_ops) {
         case 1: drex::mindex_pairs_kernel<1><<<gp, drex::MINDEX_TILE, 0, st>>>(quats, N, n_tiles, tmax, thr, cnt); break;

@@ -503,53 +503,169 @@ mindex_pairs_kernel(const float4 *__restrict__ quats, int64_t N, int n_tiles, in
         if (hist[b]) atomicAdd(&counts[s * theta_max + b], (unsigned long long)hist[b]);
 }
 
+// ---- packed float32 arithmetic (sm_100: FMUL2 / FADD2 / FFMA2 on 64-bit register pairs) ------
+// Two pairs of grains per instruction.  Every lane of a packed operation is an IEEE
+// round-to-nearest float32 operation, so results are bit-identical to the scalar chain -- as
+// long as no product is contracted into the sum that follows it.  ptxas (12.9) contracts
+// mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with the explicit rounding modifiers, so the
+// products are formed as fma(a, b, -0.0f) with the -0.0f pair coming in as a kernel argument:
+// the value is exactly a * b (x + -0 = x for every x, signed zeros included), costs the same
+// one instruction, and an FFMA2 cannot be folded into the next add.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack2(float lo, float hi) {
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2_t v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b, f32x2_t neg_zero) {
+    f32x2_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(neg_zero));
+    return r;
+}
+__device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) {
+    f32x2_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t sub2(f32x2_t a, f32x2_t b) {
+    f32x2_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+struct Quat2 {
+    f32x2_t x, y, z, w;  // one component of two grains (or one grain's, duplicated) per member
+};
+__device__ __forceinline__ void absmax2(f32x2_t d, float &b0, float &b1) {
+    float lo, hi;
+    unpack2(d, lo, hi);
+    b0 = fmaxf(b0, fabsf(lo));
+    b1 = fmaxf(b1, fabsf(hi));
+}
+// absmax_sign4 for two grains at once
+__device__ __forceinline__ void absmax_sign4_x2(const Quat2 &a, const Quat2 &b, f32x2_t nz, float &b0, float &b1) {
+    const f32x2_t p0 = mul2(a.x, b.x, nz), p1 = mul2(a.y, b.y, nz);
+    const f32x2_t p2 = mul2(a.z, b.z, nz), p3 = mul2(a.w, b.w, nz);
+    const f32x2_t sp = add2(p0, p1), sm = sub2(p0, p1);
+    absmax2(add2(add2(sp, p2), p3), b0, b1);
+    absmax2(add2(sub2(sm, p2), p3), b0, b1);
+    absmax2(sub2(add2(sm, p2), p3), b0, b1);
+    absmax2(sub2(sub2(sp, p2), p3), b0, b1);
+}
+// dot4_ref for two grains at once
+__device__ __forceinline__ void absdot_x2(const Quat2 &a, const Quat2 &b, f32x2_t nz, float &b0, float &b1) {
+    const f32x2_t p0 = mul2(a.x, b.x, nz), p1 = mul2(a.y, b.y, nz);
+    const f32x2_t p2 = mul2(a.z, b.z, nz), p3 = mul2(a.w, b.w, nz);
+    absmax2(add2(add2(add2(p0, p1), p2), p3), b0, b1);
+}
+
+// The bin of mindex_bin through a table: cell c = floor(d * MINDEX_LUT) starts the count at the
+// count of the cell's upper edge (a lower bound, the count does not increase with d) and walks
+// up the thresholds from there: exact, and 0-1 steps except for the smallest angles.
+constexpr int MINDEX_LUT = 2048;
+__device__ __forceinline__ int mindex_count(float d, const float *thr, int theta_max) {
+    int lo = 0, hi = theta_max + 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (d <= thr[mid]) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+__device__ __forceinline__ int mindex_bin_lut(float d, const float *thr, const unsigned short *lut, int theta_max) {
+    int k = lut[(int)(d * (float)MINDEX_LUT)];  // d in [0, 1]: the product is exact
+    while (d <= thr[k + 1]) ++k;                // thr[theta_max + 2] = -1 ends the walk
+    if (k > theta_max) return -1;
+    return k == theta_max ? theta_max - 1 : k;
+}
+
 // K2 (monoclinic / orthorhombic): the 7 operations are identity, three "rotations" (stored
 // per grain as slots 1..3) and three diagonal sign matrices (geometry.py:133-150).  The
 // sign matrices with the identity form a group of exact float32 sign flips, so the 49
 // operator pairs collapse to 4 + 12 + 12 shared-product dots and 9 plain ones: 161 float
 // operations per pair instead of 343, with bit-identical maxima.  Slots per grain: 4.
+// A thread holds grain i (every component duplicated into a register pair) and walks the j
+// tile two grains at a time with packed arithmetic; the tile sits in shared memory as
+// [j / 2][slot][component][j % 2], 128 bytes per pair of grains, read as broadcast LDS.128.
+// The kernel is bound by instruction issue: ~115 instructions per pair this way, ~205 scalar.
 __global__ void __launch_bounds__(MINDEX_TILE)
 mindex_pairs_reflect_kernel(const float4 *__restrict__ quats, int64_t N, int n_tiles, int theta_max,
                             const float *__restrict__ thresholds,
-                            unsigned long long *__restrict__ counts) {
-    __shared__ float4 qj[MINDEX_TILE * 4];
+                            unsigned long long *__restrict__ counts, const f32x2_t neg_zero) {
+    __shared__ __align__(16) float qj[MINDEX_TILE * 16];
     __shared__ unsigned int hist[MAX_THETA];
-    __shared__ float thr[MAX_THETA + 2];
+    __shared__ float thr[MAX_THETA + 3];
+    __shared__ unsigned short lut[MINDEX_LUT + 2];
     const int64_t s = blockIdx.x;  // textures in grid.x, tile pairs in grid.y
     int ti, tj;
     mindex_tile(blockIdx.y, n_tiles, ti, tj);
     const int tid = threadIdx.x;
     for (int b = tid; b < theta_max; b += MINDEX_TILE) hist[b] = 0u;
     for (int b = tid; b < theta_max + 2; b += MINDEX_TILE) thr[b] = thresholds[b];
+    if (tid == 0) thr[theta_max + 2] = -1.0f;
     const float4 *base = quats + s * N * 4;
     const int64_t j0 = (int64_t)tj * MINDEX_TILE;
     const int nj = (int)min((int64_t)MINDEX_TILE, N - j0);
-    for (int e = tid; e < nj * 4; e += MINDEX_TILE) qj[e] = base[j0 * 4 + e];
-    const int64_t i = (int64_t)ti * MINDEX_TILE + tid;
-    float4 q1 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = q1, v2 = q1, v3 = q1;
-    if (i < N) {
-        q1 = base[i * 4 + 0];
-        v1 = base[i * 4 + 1];
-        v2 = base[i * 4 + 2];
-        v3 = base[i * 4 + 3];
+    for (int e = tid; e < MINDEX_TILE * 4; e += MINDEX_TILE) {
+        const int j = e >> 2, slot = e & 3;
+        const float4 v = (j < nj) ? base[j0 * 4 + e] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float *dst = qj + (j >> 1) * 32 + slot * 8 + (j & 1);
+        dst[0] = v.x;
+        dst[2] = v.y;
+        dst[4] = v.z;
+        dst[6] = v.w;
     }
+    const int64_t i = (int64_t)ti * MINDEX_TILE + tid;
+    Quat2 qi[4];
+    {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float4 v = (i < N) ? base[i * 4 + k] : z;
+            qi[k].x = pack2(v.x, v.x);
+            qi[k].y = pack2(v.y, v.y);
+            qi[k].z = pack2(v.z, v.z);
+            qi[k].w = pack2(v.w, v.w);
+        }
+    }
+    __syncthreads();  // thr is complete
+    for (int c = tid; c <= MINDEX_LUT; c += MINDEX_TILE)
+        lut[c] = (unsigned short)mindex_count((float)(c + 1) * (1.0f / (float)MINDEX_LUT), thr, theta_max);
     __syncthreads();
     if (i < N) {
         const int jstart = (ti == tj) ? tid + 1 : 0;
-        for (int jj = jstart; jj < nj; ++jj) {
-            const float4 q2 = qj[jj * 4 + 0], u1 = qj[jj * 4 + 1], u2 = qj[jj * 4 + 2], u3 = qj[jj * 4 + 3];
-            float best = absmax_sign4(q1, q2, 0.0f);  // {I, R} x {I, R}
-            best = absmax_sign4(q1, u1, best);         // {I, R} q1 . rotations of q2
-            best = absmax_sign4(q1, u2, best);
-            best = absmax_sign4(q1, u3, best);
-            best = absmax_sign4(v1, q2, best);         // rotations of q1 . {I, R} q2
-            best = absmax_sign4(v2, q2, best);
-            best = absmax_sign4(v3, q2, best);
-            best = fmaxf(best, fmaxf(fmaxf(fabsf(dot4_ref(v1, u1)), fabsf(dot4_ref(v1, u2))), fabsf(dot4_ref(v1, u3))));
-            best = fmaxf(best, fmaxf(fmaxf(fabsf(dot4_ref(v2, u1)), fabsf(dot4_ref(v2, u2))), fabsf(dot4_ref(v2, u3))));
-            best = fmaxf(best, fmaxf(fmaxf(fabsf(dot4_ref(v3, u1)), fabsf(dot4_ref(v3, u2))), fabsf(dot4_ref(v3, u3))));
-            const int bin = mindex_bin(fminf(best, 1.0f), thr, theta_max);
-            if (bin >= 0) atomicAdd(&hist[bin], 1u);
+        const ulonglong2 *tile = reinterpret_cast<const ulonglong2 *>(qj);
+        for (int jp = jstart >> 1; 2 * jp < nj; ++jp) {
+            Quat2 qb[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const ulonglong2 xy = tile[jp * 8 + 2 * k], zw = tile[jp * 8 + 2 * k + 1];
+                qb[k].x = xy.x;
+                qb[k].y = xy.y;
+                qb[k].z = zw.x;
+                qb[k].w = zw.y;
+            }
+            float b0 = 0.0f, b1 = 0.0f;
+            absmax_sign4_x2(qi[0], qb[0], neg_zero, b0, b1);  // {I, R} x {I, R}
+#pragma unroll
+            for (int k = 1; k < 4; ++k) {
+                absmax_sign4_x2(qi[0], qb[k], neg_zero, b0, b1);  // {I, R} q1 . rotations of q2
+                absmax_sign4_x2(qi[k], qb[0], neg_zero, b0, b1);  // rotations of q1 . {I, R} q2
+            }
+#pragma unroll
+            for (int a = 1; a < 4; ++a)
+#pragma unroll
+                for (int b = 1; b < 4; ++b) absdot_x2(qi[a], qb[b], neg_zero, b0, b1);
+            const int j = 2 * jp;
+            if (j >= jstart) {
+                const int bin = mindex_bin_lut(fminf(b0, 1.0f), thr, lut, theta_max);
+                if (bin >= 0) atomicAdd(&hist[bin], 1u);
+            }
+            if (j + 1 < nj) {  // (j + 1 >= jstart always: the walk starts at the pair of jstart)
+                const int bin = mindex_bin_lut(fminf(b1, 1.0f), thr, lut, theta_max);
+                if (bin >= 0) atomicAdd(&hist[bin], 1u);
+            }
         }
     }
     __syncthreads();

@@ -32,6 +32,21 @@ for _ in range(5):
 torch.cuda.synchronize()
 ms = (time.perf_counter() - t0) / 5 * 1e3
 print(f"D2H 0.9 GB in one copy: {ms:.2f} ms = {d.numel() * 8 / ms / 1e6:.1f} GB/s")
+# the same bytes as update_host moves out, cut the same way (8 groups x 3 copies), copies only
+s_out = torch.cuda.Stream(device=dev)
+per = -(-P // 8) * 2
+for rep in range(3):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    with torch.cuda.stream(s_out):
+        for c in range(8):
+            s0, s1 = c * per, min(S, (c + 1) * per)
+            h_o[s0:s1].copy_(d[s0:s1], non_blocking=True)
+            h_f[s0:s1].copy_(ens.f[s0:s1], non_blocking=True)
+            h_F[s0:s1].copy_(ens.F[s0:s1], non_blocking=True)
+    s_out.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3
+print(f"D2H of the whole state in 24 copies on a side stream: {ms:.2f} ms")
 for n_chunks in (2, 3, 4, 8):
     for k in range(6, 8):
         ens.update_host(h_o, h_f, h_F, h_lo[k], h_hi[k], h_L[k], kind, n_chunks=n_chunks)

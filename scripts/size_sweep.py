@@ -26,7 +26,7 @@ for N in (500, 1000, 2000, 3000, 5000, 5120, 8000, 10000, 20000):
         torch.cuda.synchronize()
         if k >= 4:
             ms.append(e0.elapsed_time(e1))
-            evals += int(ens.stats[1].sum()) * N
+            evals += int(ens.grain_evals.sum())
     bad = int((ens.stats[0] != 0).sum())
     print(f"N={N:6d} P={P:6d}: {np.mean(ms):6.2f} ms/step, {evals / (sum(ms) * 1e-3):.3e} grain-evals/s, "
           f"{P * 2 * N * len(ms) / (sum(ms) * 1e-3):.3e} grain-steps/s, failed {bad}")

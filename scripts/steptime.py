@@ -28,4 +28,5 @@ for variant in ('full', 'noorder'):
         t1 = time.perf_counter()
         torch.cuda.synchronize()
         print(variant, k, 'gpu ms %.2f' % e0.elapsed_time(e1), 'cpu ms %.2f' % ((t1 - t0) * 1e3),
-              'rhs/sys %.2f' % ens.stats[1].float().mean().item(), 'maxrhs', int(ens.stats[1].max()))
+              'rhs/grain %.2f' % (float(ens.grain_evals.sum()) / (ens.S * ens.N)),
+              'max rhs/grain of a system %.1f' % (float(ens.grain_evals.max()) / ens.N))
