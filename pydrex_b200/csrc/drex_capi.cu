@@ -751,7 +751,7 @@ static size_t mindex_ws_layout(int64_t S, int64_t N, int n_store, int tmax, size
     *off_theory = quats + counts;
     size_t theory = align_up((size_t)tmax * sizeof(double), 256);
     *off_thr = quats + counts + theory;
-    return quats + counts + theory + align_up((size_t)(tmax + 2) * sizeof(float), 256);
+    return quats + counts + theory + align_up(sizeof(drex::MindexBins), 256);
 }
 
 // monoclinic / orthorhombic: identity + 3 rotations stored, 3 sign-flip reflections implied
@@ -791,12 +791,18 @@ int drex_mindex_f32(const double *o_soa, int64_t S, int64_t N, int system_a, int
     float4 *quats = (float4 *)workspace;
     unsigned long long *cnt = (unsigned long long *)((char *)workspace + off_counts);
     double *theory = (double *)((char *)workspace + off_theory);
-    float *thr = (float *)((char *)workspace + off_thr);
-    float thr_host[drex::MAX_THETA + 2];
-    mindex_thresholds(tmax, thr_host);
+    drex::MindexBins *bins = (drex::MindexBins *)((char *)workspace + off_thr);
+    const float *thr = bins->thr;  // (device address; first member)
+    drex::MindexBins bins_host;
+    memset(&bins_host, 0, sizeof(bins_host));
+    mindex_thresholds(tmax, bins_host.thr);
+    bins_host.thr[tmax + 2] = -1.0f;  // ends the walk up the thresholds
+    for (int c = 0; c <= drex::MINDEX_LUT; ++c)
+        bins_host.lut[c] = (unsigned short)drex::mindex_count((float)(c + 1) * (1.0f / (float)drex::MINDEX_LUT),
+                                                              bins_host.thr, tmax);
     DREX_CUDA_CHECK(cudaMemsetAsync(cnt, 0, (size_t)S * tmax * sizeof(unsigned long long), st));
     DREX_CUDA_CHECK(cudaMemcpyAsync(theory, theory_host, tmax * sizeof(double), cudaMemcpyHostToDevice, st));
-    DREX_CUDA_CHECK(cudaMemcpyAsync(thr, thr_host, (tmax + 2) * sizeof(float), cudaMemcpyHostToDevice, st));
+    DREX_CUDA_CHECK(cudaMemcpyAsync(bins, &bins_host, sizeof(bins_host), cudaMemcpyHostToDevice, st));
     if (N > 0) {
         dim3 gq((unsigned)S, (unsigned)((N + 127) / 128));
         drex::mindex_quats_kernel<<<gq, 128, 0, st>>>(o_soa, N, quats, n_store, ops);
@@ -807,8 +813,15 @@ int drex_mindex_f32(const double *o_soa, int64_t S, int64_t N, int system_a, int
                         361 * drex::MINDEX_TILE);
         dim3 gp((unsigned)S, (unsigned)((int64_t)n_tiles * (n_tiles + 1) / 2));
         if (refl) {
-            drex::mindex_pairs_reflect_kernel<<<gp, drex::MINDEX_TILE, 0, st>>>(quats, N, n_tiles, tmax, thr, cnt,
-                                                                                0x8000000080000000ull);
+            // all 49 dots (cross-check) or only the products that can matter (see the kernels)
+            const char *full = getenv("DREX_MINDEX_FULL");
+            const unsigned long long neg_zero2 = 0x8000000080000000ull;  // (-0.0f, -0.0f)
+            if (full && full[0] == '1')
+                drex::mindex_pairs_reflect_kernel<<<gp, drex::MINDEX_TILE, 0, st>>>(quats, N, n_tiles, tmax, bins,
+                                                                                    cnt, neg_zero2);
+            else
+                drex::mindex_pairs_reflect_live_kernel<<<gp, drex::MINDEX_TILE, 0, st>>>(quats, N, n_tiles, tmax,
+                                                                                         bins, cnt, neg_zero2);
         } else
         switch (n_ops) {
         case 1: drex::mindex_pairs_kernel<1><<<gp, drex::MINDEX_TILE, 0, st>>>(quats, N, n_tiles, tmax, thr, cnt); break;

@@ -562,10 +562,16 @@ __device__ __forceinline__ void absdot_x2(const Quat2 &a, const Quat2 &b, f32x2_
 }
 
 // The bin of mindex_bin through a table: cell c = floor(d * MINDEX_LUT) starts the count at the
-// count of the cell's upper edge (a lower bound, the count does not increase with d) and walks
-// up the thresholds from there: exact, and 0-1 steps except for the smallest angles.
+// count of the cell's upper edge (a lower bound: the count does not increase with d) and walks
+// up the thresholds from there: exact, and 0-1 steps except for the smallest angles.  The host
+// builds the table next to the thresholds (drex_mindex_f32); a CTA copies both to shared memory.
 constexpr int MINDEX_LUT = 2048;
-__device__ __forceinline__ int mindex_count(float d, const float *thr, int theta_max) {
+struct MindexBins {
+    float thr[MAX_THETA + 4];              // thr[theta_max + 2] = -1 ends the walk
+    unsigned short lut[MINDEX_LUT + 8];    // lut[c] = count((c + 1) / MINDEX_LUT), c = 0..MINDEX_LUT
+};
+static_assert(sizeof(MindexBins) % 16 == 0, "copied as uint4");
+__host__ __device__ inline int mindex_count(float d, const float *thr, int theta_max) {
     int lo = 0, hi = theta_max + 1;
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
@@ -573,9 +579,15 @@ __device__ __forceinline__ int mindex_count(float d, const float *thr, int theta
     }
     return lo;
 }
-__device__ __forceinline__ int mindex_bin_lut(float d, const float *thr, const unsigned short *lut, int theta_max) {
-    int k = lut[(int)(d * (float)MINDEX_LUT)];  // d in [0, 1]: the product is exact
-    while (d <= thr[k + 1]) ++k;                // thr[theta_max + 2] = -1 ends the walk
+__device__ __forceinline__ void mindex_load_bins(MindexBins &dst, const MindexBins *__restrict__ src, int tid,
+                                                 int nthreads) {
+    const uint4 *a = reinterpret_cast<const uint4 *>(src);
+    uint4 *b = reinterpret_cast<uint4 *>(&dst);
+    for (int i = tid; i < (int)(sizeof(MindexBins) / 16); i += nthreads) b[i] = a[i];
+}
+__device__ __forceinline__ int mindex_bin_lut(float d, const MindexBins &bins, int theta_max) {
+    int k = bins.lut[(int)(d * (float)MINDEX_LUT)];  // d in [0, 1]: the product is exact
+    while (d <= bins.thr[k + 1]) ++k;
     if (k > theta_max) return -1;
     return k == theta_max ? theta_max - 1 : k;
 }
@@ -591,19 +603,17 @@ __device__ __forceinline__ int mindex_bin_lut(float d, const float *thr, const u
 // The kernel is bound by instruction issue: ~115 instructions per pair this way, ~205 scalar.
 __global__ void __launch_bounds__(MINDEX_TILE)
 mindex_pairs_reflect_kernel(const float4 *__restrict__ quats, int64_t N, int n_tiles, int theta_max,
-                            const float *__restrict__ thresholds,
+                            const MindexBins *__restrict__ bins_global,
                             unsigned long long *__restrict__ counts, const f32x2_t neg_zero) {
     __shared__ __align__(16) float qj[MINDEX_TILE * 16];
     __shared__ unsigned int hist[MAX_THETA];
-    __shared__ float thr[MAX_THETA + 3];
-    __shared__ unsigned short lut[MINDEX_LUT + 2];
+    __shared__ __align__(16) MindexBins bins;
     const int64_t s = blockIdx.x;  // textures in grid.x, tile pairs in grid.y
     int ti, tj;
     mindex_tile(blockIdx.y, n_tiles, ti, tj);
     const int tid = threadIdx.x;
     for (int b = tid; b < theta_max; b += MINDEX_TILE) hist[b] = 0u;
-    for (int b = tid; b < theta_max + 2; b += MINDEX_TILE) thr[b] = thresholds[b];
-    if (tid == 0) thr[theta_max + 2] = -1.0f;
+    mindex_load_bins(bins, bins_global, tid, MINDEX_TILE);
     const float4 *base = quats + s * N * 4;
     const int64_t j0 = (int64_t)tj * MINDEX_TILE;
     const int nj = (int)min((int64_t)MINDEX_TILE, N - j0);
@@ -629,9 +639,6 @@ mindex_pairs_reflect_kernel(const float4 *__restrict__ quats, int64_t N, int n_t
             qi[k].w = pack2(v.w, v.w);
         }
     }
-    __syncthreads();  // thr is complete
-    for (int c = tid; c <= MINDEX_LUT; c += MINDEX_TILE)
-        lut[c] = (unsigned short)mindex_count((float)(c + 1) * (1.0f / (float)MINDEX_LUT), thr, theta_max);
     __syncthreads();
     if (i < N) {
         const int jstart = (ti == tj) ? tid + 1 : 0;
@@ -659,11 +666,122 @@ mindex_pairs_reflect_kernel(const float4 *__restrict__ quats, int64_t N, int n_t
                 for (int b = 1; b < 4; ++b) absdot_x2(qi[a], qb[b], neg_zero, b0, b1);
             const int j = 2 * jp;
             if (j >= jstart) {
-                const int bin = mindex_bin_lut(fminf(b0, 1.0f), thr, lut, theta_max);
+                const int bin = mindex_bin_lut(fminf(b0, 1.0f), bins, theta_max);
                 if (bin >= 0) atomicAdd(&hist[bin], 1u);
             }
             if (j + 1 < nj) {  // (j + 1 >= jstart always: the walk starts at the pair of jstart)
-                const int bin = mindex_bin_lut(fminf(b1, 1.0f), thr, lut, theta_max);
+                const int bin = mindex_bin_lut(fminf(b1, 1.0f), bins, theta_max);
+                if (bin >= 0) atomicAdd(&hist[bin], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int b = tid; b < theta_max; b += MINDEX_TILE)
+        if (hist[b]) atomicAdd(&counts[s * theta_max + b], (unsigned long long)hist[b]);
+}
+
+// K2 (monoclinic / orthorhombic), the product kernel: only the products that can matter.
+// The three stored "rotations" are the reference's quat_product (utils.py:365-371, no cross term)
+// with the quaternions of the half turns about z, y, x, whose scalar part is cos(pi/2) =
+// 6.1e-17 in double: slot 1 is (6e-17 x, 6e-17 y, w + 6e-17 z, -z + 6e-17 w) and likewise
+// slot 2 = (~0, w', ~0, -y'), slot 3 = (w', ~0, ~0, -x'): two components of order 1 ("live")
+// and two of order 1e-17.  In a dot ((p0 + p1) + p2) + p3 the products with a 1e-17 factor
+// vanish in the rounding of the first live product they meet (they are below half an ulp of
+// anything larger than 2e-9), so
+//   {I, R} q1 . slot k of q2, and slot k of q1 . {I, R} q2:  |pa + pb| and |pb - pa| over the two
+//                                                            live components (the four sign
+//                                                            variants are these two, twice);
+//   slot a . slot a:  pa + pb over the two live components;
+//   slot a . slot b, a != b:  only the scalar parts are live in both: |w_a| |w_b|;
+// and the {I, R} q1 . {I, R} q2 block as in the kernel above: 25 products and 25 sums per pair
+// instead of 64 and 97.  The maxima are those of the full evaluation unless the WINNING dot
+// (always >= cos(60 deg)) contains a live product below 2e-9 and sits within 1e-16 of a
+// float32 rounding boundary -- once in ~1e17 pairs; mindex_pairs_reflect_kernel (all 49 dots,
+// DREX_MINDEX_FULL=1) is the cross-check and tests/test_gpu_parity.py compares the histograms
+// of the two kernels for equality.  Tile in shared memory: [j / 2][10 components][j % 2].
+__global__ void __launch_bounds__(MINDEX_TILE)
+mindex_pairs_reflect_live_kernel(const float4 *__restrict__ quats, int64_t N, int n_tiles, int theta_max,
+                                 const MindexBins *__restrict__ bins_global,
+                                 unsigned long long *__restrict__ counts, const f32x2_t neg_zero) {
+    __shared__ __align__(16) float qj[(MINDEX_TILE / 2) * 20];
+    __shared__ unsigned int hist[MAX_THETA];
+    __shared__ __align__(16) MindexBins bins;
+    const int64_t s = blockIdx.x;
+    int ti, tj;
+    mindex_tile(blockIdx.y, n_tiles, ti, tj);
+    const int tid = threadIdx.x;
+    for (int b = tid; b < theta_max; b += MINDEX_TILE) hist[b] = 0u;
+    mindex_load_bins(bins, bins_global, tid, MINDEX_TILE);
+    const float4 *base = quats + s * N * 4;
+    const int64_t j0 = (int64_t)tj * MINDEX_TILE;
+    const int nj = (int)min((int64_t)MINDEX_TILE, N - j0);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    {
+        const bool have = tid < nj;
+        const float4 q = have ? base[(j0 + tid) * 4 + 0] : zero4, u1 = have ? base[(j0 + tid) * 4 + 1] : zero4;
+        const float4 u2 = have ? base[(j0 + tid) * 4 + 2] : zero4, u3 = have ? base[(j0 + tid) * 4 + 3] : zero4;
+        float *dst = qj + (tid >> 1) * 20 + (tid & 1);
+        dst[0] = q.x;   dst[2] = q.y;   dst[4] = q.z;   dst[6] = q.w;
+        dst[8] = u1.z;  dst[10] = u1.w; dst[12] = u2.y; dst[14] = u2.w;
+        dst[16] = u3.x; dst[18] = u3.w;
+    }
+    const int64_t i = (int64_t)ti * MINDEX_TILE + tid;
+    const bool live_i = i < N;
+    const float4 q1 = live_i ? base[i * 4 + 0] : zero4, v1 = live_i ? base[i * 4 + 1] : zero4;
+    const float4 v2 = live_i ? base[i * 4 + 2] : zero4, v3 = live_i ? base[i * 4 + 3] : zero4;
+    Quat2 qi;
+    qi.x = pack2(q1.x, q1.x);
+    qi.y = pack2(q1.y, q1.y);
+    qi.z = pack2(q1.z, q1.z);
+    qi.w = pack2(q1.w, q1.w);
+    const f32x2_t a1z = pack2(v1.z, v1.z), a1w = pack2(v1.w, v1.w);
+    const f32x2_t a2y = pack2(v2.y, v2.y), a2w = pack2(v2.w, v2.w);
+    const f32x2_t a3x = pack2(v3.x, v3.x), a3w = pack2(v3.w, v3.w);
+    // slot a . slot b for a != b: max over a of |w_a| |w_b| = (max over a != b of |w_a|) |w_b|
+    const float m1s = fmaxf(fabsf(v2.w), fabsf(v3.w)), m2s = fmaxf(fabsf(v1.w), fabsf(v3.w));
+    const float m3s = fmaxf(fabsf(v1.w), fabsf(v2.w));
+    const f32x2_t m1 = pack2(m1s, m1s), m2 = pack2(m2s, m2s), m3 = pack2(m3s, m3s);
+    __syncthreads();
+    if (live_i) {
+        const int jstart = (ti == tj) ? tid + 1 : 0;
+        const ulonglong2 *tile = reinterpret_cast<const ulonglong2 *>(qj);
+        for (int jp = jstart >> 1; 2 * jp < nj; ++jp) {
+            const ulonglong2 xy = tile[jp * 5 + 0], zw = tile[jp * 5 + 1], s1 = tile[jp * 5 + 2];
+            const ulonglong2 s2 = tile[jp * 5 + 3], s3 = tile[jp * 5 + 4];
+            Quat2 qb;
+            qb.x = xy.x;
+            qb.y = xy.y;
+            qb.z = zw.x;
+            qb.w = zw.y;
+            float b0 = 0.0f, b1 = 0.0f;
+            absmax_sign4_x2(qi, qb, neg_zero, b0, b1);  // {I, R} q1 . {I, R} q2
+            // two live components: |pa + pb|, |pb - pa|
+#define DREX_LIVE2(A0, B0, A1, B1)                                          \
+    {                                                                        \
+        const f32x2_t pa_ = mul2(A0, B0, neg_zero), pb_ = mul2(A1, B1, neg_zero); \
+        absmax2(add2(pa_, pb_), b0, b1);                                     \
+        absmax2(sub2(pb_, pa_), b0, b1);                                     \
+    }
+            DREX_LIVE2(qi.z, s1.x, qi.w, s1.y)  // {I, R} q1 . slot 1 of q2
+            DREX_LIVE2(qi.y, s2.x, qi.w, s2.y)  //             slot 2
+            DREX_LIVE2(qi.x, s3.x, qi.w, s3.y)  //             slot 3
+            DREX_LIVE2(a1z, qb.z, a1w, qb.w)    // slot 1 of q1 . {I, R} q2
+            DREX_LIVE2(a2y, qb.y, a2w, qb.w)
+            DREX_LIVE2(a3x, qb.x, a3w, qb.w)
+#undef DREX_LIVE2
+            absmax2(add2(mul2(a1z, s1.x, neg_zero), mul2(a1w, s1.y, neg_zero)), b0, b1);  // slot a . slot a
+            absmax2(add2(mul2(a2y, s2.x, neg_zero), mul2(a2w, s2.y, neg_zero)), b0, b1);
+            absmax2(add2(mul2(a3x, s3.x, neg_zero), mul2(a3w, s3.y, neg_zero)), b0, b1);
+            absmax2(mul2(m1, s1.y, neg_zero), b0, b1);  // slot a . slot b, a != b
+            absmax2(mul2(m2, s2.y, neg_zero), b0, b1);
+            absmax2(mul2(m3, s3.y, neg_zero), b0, b1);
+            const int j = 2 * jp;
+            if (j >= jstart) {
+                const int bin = mindex_bin_lut(fminf(b0, 1.0f), bins, theta_max);
+                if (bin >= 0) atomicAdd(&hist[bin], 1u);
+            }
+            if (j + 1 < nj) {
+                const int bin = mindex_bin_lut(fminf(b1, 1.0f), bins, theta_max);
                 if (bin >= 0) atomicAdd(&hist[bin], 1u);
             }
         }

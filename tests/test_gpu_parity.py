@@ -419,6 +419,35 @@ def test_misorientation_known_answers(drex):
             drex.misorientations_random(10, 11, system))
 
 
+def test_misorientation_pair_kernels_agree(drex, monkeypatch):
+    """The product pair kernel (only the products that can matter, packed float32) against the
+    kernel that evaluates all 49 operator pairs (DREX_MINDEX_FULL=1): identical histograms,
+    count for count, for random, strongly textured, single-orientation and axis-aligned
+    textures of odd and even sizes, both 7-operation lattice systems."""
+    from scipy.spatial.transform import Rotation
+
+    rng = np.random.default_rng(11)
+    textures = [Rotation.random(2500, random_state=1).as_matrix(),
+                Rotation.from_rotvec(0.3 * rng.normal(size=(777, 3))).as_matrix(),
+                Rotation.from_rotvec(0.02 * rng.normal(size=(1001, 3))).as_matrix(),
+                Rotation.from_rotvec(1e-7 * rng.normal(size=(300, 3))).as_matrix(),
+                np.tile(np.eye(3), (129, 1, 1)),
+                # half turns and quarter turns about the axes: exact zeros in the quaternions
+                Rotation.from_euler("zyx", 90.0 * rng.integers(0, 4, size=(256, 3)), degrees=True).as_matrix(),
+                (Rotation.from_rotvec([0.0, 0.0, 0.7]) * Rotation.from_rotvec(
+                    np.c_[np.zeros(500), np.zeros(500), rng.normal(size=500)])).as_matrix()]
+    for system in (drex.LatticeSystem.orthorhombic, drex.LatticeSystem.monoclinic):
+        for o in textures:
+            npairs = len(o) * (len(o) - 1) // 2
+            monkeypatch.delenv("DREX_MINDEX_FULL", raising=False)
+            h_live, _ = drex.misorientation_hist(o, system)
+            monkeypatch.setenv("DREX_MINDEX_FULL", "1")
+            h_full, _ = drex.misorientation_hist(o, system)
+            monkeypatch.delenv("DREX_MINDEX_FULL", raising=False)
+            c_live, c_full = np.round(h_live * npairs), np.round(h_full * npairs)
+            assert np.array_equal(c_live, c_full), (system, len(o), np.abs(c_live - c_full).max())
+
+
 def test_random_theory_matches_golden(drex, golden_diagnostics):
     g = golden_diagnostics
     for name in SYSTEMS:
