@@ -298,12 +298,21 @@ int drex_polar_decompose_f64(const double *matrices, int64_t B, int left, double
  * (the reference's layout), f: [S][N], uniforms: [S][n_samples] in [0,1) -- the caller draws
  * them (numpy.random.default_rng(seed).random((S, n_samples)) reproduces the reference's
  * stream).  out_o: [S][n_samples][3][3], out_f: [S][n_samples].  Workspace is only needed
- * above 8192 grains per texture (query first; 0 otherwise). */
+ * above 11000 grains per texture (query first; 0 otherwise). */
 size_t drex_resample_workspace_bytes(int64_t S, int64_t N);
 int drex_resample_orientations_f64(const double *o_aos, const double *f, const double *uniforms,
                                    int64_t S, int64_t N, int64_t n_samples, double *out_o,
                                    double *out_f, void *workspace, size_t workspace_bytes,
                                    void *stream);
+
+/* The uniform variates of stats.resample_orientations on the device (stats.py:49, 59):
+ * out[t][0..n) = numpy.random.default_rng(seeds[t]).random(offsets[t] + n)[offsets[t]:], bit for
+ * bit (SeedSequence hashing of the seed's 32-bit words, PCG64, 53-bit doubles).  seeds: [T]
+ * non-negative integers below 2^64; offsets: [T] or NULL (all 0): cut ONE seeded stream into
+ * per-texture pieces with seeds[t] = seed, offsets[t] = t * n, as the reference's loop over
+ * textures draws them.  Device pointers. */
+int drex_numpy_uniform_f64(const uint64_t *seeds, const uint64_t *offsets, int64_t T, int64_t n,
+                           double *out, void *stream);
 
 /* ---- diagnostics.misorientation_index (diagnostics.py:332-367) -------------------- */
 

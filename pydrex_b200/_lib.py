@@ -42,7 +42,7 @@ EXPORTS = (
     "drex_tensor_ops_f64",
     "drex_polar_decompose_f64",
     "drex_resample_workspace_bytes",
-    "drex_resample_orientations_f64",
+    "drex_resample_orientations_f64", "drex_numpy_uniform_f64",
     "drex_mindex_workspace_bytes", "drex_mindex_theory_host", "drex_mindex_f32",
     "drex_misorientations_random_host",
     "drex_fp64_peak_probe",
@@ -183,6 +183,7 @@ def _declare(lib):
     lib.drex_resample_workspace_bytes.restype = szt
     lib.drex_resample_workspace_bytes.argtypes = [i64, i64]
     lib.drex_resample_orientations_f64.argtypes = [vp, vp, vp, i64, i64, i64, vp, vp, vp, szt, vp]
+    lib.drex_numpy_uniform_f64.argtypes = [vp, vp, i64, i64, vp, vp]
     lib.drex_mindex_workspace_bytes.restype = szt
     lib.drex_mindex_workspace_bytes.argtypes = [i64, i64, i32, i32]
     lib.drex_mindex_theory_host.argtypes = [i32, i32, c.POINTER(c.c_double)]

@@ -495,8 +495,7 @@ int drex_polar_decompose_f64(const double *matrices, int64_t B, int left, double
 
 size_t drex_resample_workspace_bytes(int64_t S, int64_t N) {
     if (S <= 0 || N <= 0) return 0;
-    const int64_t npad = drex::resample_npad(N);
-    return npad <= drex::RESAMPLE_SMEM_NPAD_MAX ? 0 : (size_t)S * (size_t)npad * 20;
+    return N <= drex::RESAMPLE_SMEM_N_MAX ? 0 : (size_t)S * (size_t)drex::resample_ws_stride(N);
 }
 
 int drex_resample_orientations_f64(const double *o_aos, const double *f, const double *uniforms,
@@ -514,12 +513,23 @@ int drex_resample_orientations_f64(const double *o_aos, const double *f, const d
         return fail(DREX_E_WORKSPACE, "drex_resample_orientations_f64: workspace too small (%zu < %zu)",
                     workspace_bytes, need);
     const int64_t npad = drex::resample_npad(N);
-    const size_t smem = need ? 0 : (size_t)npad * 20;
+    const size_t smem = need ? 0 : (size_t)N * 20;
     if (smem > 48 * 1024)
         DREX_CUDA_CHECK(cudaFuncSetAttribute(drex::resample_kernel,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     drex::resample_kernel<<<(unsigned)S, drex::RESAMPLE_THREADS, smem, (cudaStream_t)stream>>>(
         o_aos, f, uniforms, N, npad, n_samples, out_o, out_f, (unsigned char *)workspace);
+    DREX_CUDA_CHECK(cudaGetLastError());
+    return DREX_OK;
+}
+
+int drex_numpy_uniform_f64(const uint64_t *seeds, const uint64_t *offsets, int64_t T, int64_t n,
+                           double *out, void *stream) {
+    if (T < 0 || n < 0) return fail(DREX_E_INVALID, "negative size");
+    if (T == 0 || n == 0) return DREX_OK;
+    if (!seeds || !out) return fail(DREX_E_INVALID, "drex_numpy_uniform_f64: null pointer");
+    drex::numpy_uniform_kernel<<<(unsigned)((T + 63) / 64), 64, 0, (cudaStream_t)stream>>>(seeds, offsets, T, n,
+                                                                                        out);
     DREX_CUDA_CHECK(cudaGetLastError());
     return DREX_OK;
 }

@@ -19,6 +19,7 @@ import numpy as np
 from . import _lib
 from . import core as _core
 from . import exceptions as _err
+from . import stats as _stats
 from .minerals import StiffnessTensors
 
 
@@ -405,9 +406,7 @@ class ParticleEnsemble:
         n_samples = self.N if n_samples is None else int(n_samples)
         if seeds is None:
             seeds = [None] * self.P
-        uniforms = np.stack([np.random.default_rng(seed=seeds[i]).random(n_samples)
-                             for i in range(lo, hi)]) if n else np.empty((0, n_samples))
-        uniforms = torch.as_tensor(uniforms).to(self.device)
+        uniforms = _stats.numpy_uniforms([seeds[i] for i in range(lo, hi)], n_samples)
         o_soa = self.o.reshape(self.P, self.n_phases, 9, self.N)[lo:hi, phase_slot].contiguous()
         f = self.f.reshape(self.P, self.n_phases, self.N)[lo:hi, phase_slot].contiguous()
         o_aos = torch.empty((n, self.N, 3, 3), dtype=torch.float64, device=self.device)

@@ -8,6 +8,36 @@ from . import _lib
 from . import geometry as _geo
 
 
+def _plain_seed(seed):
+    return isinstance(seed, (int, np.integer)) and not isinstance(seed, bool) and 0 <= int(seed) < 2**64
+
+
+def numpy_uniforms(seeds, n, offsets=None):
+    """`numpy.random.default_rng(seed).random(n)` for every seed, as a [T, n] float64 tensor on
+    the current CUDA device -- generated there, bit for bit numpy's stream
+    (`drex_numpy_uniform_f64`: SeedSequence + PCG64).  `offsets[t]` variates of stream t are
+    skipped first.  Seeds that are not plain integers in [0, 2**64) (None, sequences,
+    SeedSequence objects) are drawn by numpy on the host instead."""
+    torch = _lib.require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    seeds = list(seeds)
+    T, n = len(seeds), int(n)
+    if not all(_plain_seed(s) for s in seeds):
+        offsets = [0] * T if offsets is None else offsets
+        rows = [np.random.default_rng(seed=s).random(int(k) + n)[int(k):] for s, k in zip(seeds, offsets)]
+        return torch.as_tensor(np.stack(rows) if T else np.empty((0, n))).to(dev)
+    out = torch.empty((T, n), dtype=torch.float64, device=dev)
+    if T == 0 or n == 0:
+        return out
+    d_seeds = torch.as_tensor(np.array([int(s) for s in seeds], dtype=np.uint64).view(np.int64)).to(dev)
+    d_off = None
+    if offsets is not None:
+        d_off = torch.as_tensor(np.array([int(k) for k in offsets], dtype=np.uint64).view(np.int64)).to(dev)
+    _lib.check(_lib.load().drex_numpy_uniform_f64(_lib.ptr(d_seeds), _lib.ptr(d_off), T, n, _lib.ptr(out),
+                                                  _lib.stream_ptr(torch)))
+    return out
+
+
 def resample_orientations(orientations, fractions, n_samples=None, seed=None):
     """Return new samples from `orientations` weighted by the volume distribution
     (stats.py:14-64).
@@ -19,8 +49,9 @@ def resample_orientations(orientations, fractions, n_samples=None, seed=None):
 
     Returns the Nx`n_samples`x3x3 orientations and associated grain volumes.  numpy in,
     numpy out; torch CUDA tensors in, torch CUDA tensors out.  The uniform variates are
-    numpy's `default_rng(seed).random` stream, drawn texture by texture like the reference;
-    sorting, running sum, search and gather run on the device.  Grains with EQUAL fractions
+    numpy's `default_rng(seed).random` stream, drawn texture by texture like the reference
+    (generated on the device for an integer seed, `numpy_uniforms`); sorting, running sum,
+    search and gather run on the device.  Grains with EQUAL fractions
     are ordered by index (numpy.argsort(kind="stable")); the reference's default argsort
     leaves that order to the numpy build, see csrc/drex_resample.cuh.
     """
@@ -47,8 +78,11 @@ def resample_orientations(orientations, fractions, n_samples=None, seed=None):
     if n_samples is None:
         n_samples = N
     n_samples = int(n_samples)
-    rng = np.random.default_rng(seed=seed)
-    uniforms = torch.as_tensor(rng.random((T, n_samples))).to(dev)
+    if _plain_seed(seed):  # one seeded stream, cut into per-texture pieces on the device
+        uniforms = numpy_uniforms([seed] * T, n_samples, offsets=[i * n_samples for i in range(T)])
+    else:
+        rng = np.random.default_rng(seed=seed)
+        uniforms = torch.as_tensor(rng.random((T, n_samples))).to(dev)
 
     def to_dev(x):
         if not type(x).__module__.startswith("torch"):

@@ -448,6 +448,26 @@ def test_misorientation_pair_kernels_agree(drex, monkeypatch):
             assert np.array_equal(c_live, c_full), (system, len(o), np.abs(c_live - c_full).max())
 
 
+def test_device_uniform_variates_are_numpys_stream(drex):
+    """drex_numpy_uniform_f64 against numpy.random.default_rng(seed).random(n), bit for bit:
+    one- and two-word seeds, the edges of both, skipped variates (one stream cut into pieces)."""
+    from pydrex_b200 import stats
+
+    seeds = [0, 1, 2, 8816, 123456789, 2**31, 2**32 - 1, 2**32, 2**32 + 5, 2**63 + 12345, 2**64 - 1]
+    got = stats.numpy_uniforms(seeds, 257).cpu().numpy()
+    for s, row in zip(seeds, got):
+        assert np.array_equal(row, np.random.default_rng(s).random(257)), s
+    offsets = [0, 1, 2, 3, 1000, 4097, 65536, 10**6 + 1, 2**20, 7, 12345]
+    got = stats.numpy_uniforms(seeds, 31, offsets=offsets).cpu().numpy()
+    for s, k, row in zip(seeds, offsets, got):
+        assert np.array_equal(row, np.random.default_rng(s).random(k + 31)[k:]), (s, k)
+    # seeds numpy accepts but the device kernel does not take: drawn by numpy itself
+    got = stats.numpy_uniforms([[1, 2, 3], 2**70], 5).cpu().numpy()
+    assert np.array_equal(got[0], np.random.default_rng([1, 2, 3]).random(5))
+    assert np.array_equal(got[1], np.random.default_rng(2**70).random(5))
+    assert stats.numpy_uniforms([], 5).shape == (0, 5)
+
+
 def test_random_theory_matches_golden(drex, golden_diagnostics):
     g = golden_diagnostics
     for name in SYSTEMS:
@@ -960,9 +980,9 @@ def test_resample_orientations_match_golden(drex, golden_resample, golden_integr
         assert np.array_equal(ro[t][untied], g["e_o"][t][untied])
 
 
-@pytest.mark.parametrize("n_grains,n_samples", [(1, 5), (2, 7), (5000, 1000), (8192, 8192), (9001, 500)])
+@pytest.mark.parametrize("n_grains,n_samples", [(1, 5), (2, 7), (3, 9), (5000, 1000), (8192, 8192), (9001, 500), (11000, 64), (11001, 64), (13337, 100)])
 def test_resample_orientations_match_oracle(drex, oracle, n_grains, n_samples):
-    """Sizes around the shared-memory / workspace switch (8192 grains), heavy ties (GBS-like
+    """Sizes around powers of two and the shared-memory / workspace switch (11000 grains), heavy ties (GBS-like
     floor) and a non-normalised fraction row; bit-exact against the oracle."""
     from scipy.spatial.transform import Rotation
 
