@@ -227,7 +227,8 @@ int drex_derivatives_f64(const double *o_soa, const double *f, const double *D, 
     A.S = S; A.N = N;
     const drex::FabricTable T = make_fabric_table(*params);
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid((unsigned)S, (unsigned)((N + drex::DERIV_BLOCK - 1) / drex::DERIV_BLOCK));
+    const int64_t per_block = (int64_t)drex::DERIV_BLOCK * drex::DERIV_TILES;
+    dim3 grid((unsigned)S, (unsigned)((N + per_block - 1) / per_block));
     drex::derivatives_grain_kernel<<<grid, drex::DERIV_BLOCK, 0, st>>>(A, T);
     DREX_CUDA_CHECK(cudaGetLastError());
     drex::derivatives_gbm_kernel<<<(unsigned)S, drex::GBM_BLOCK, 0, st>>>(A);

@@ -70,43 +70,61 @@ struct DerivArgs {
     int64_t S, N;
 };
 
+// A block walks DERIV_TILES consecutive 128-grain tiles of one system: the math tables are loaded
+// once, and the nine loads of the next tile are issued before the current tile is computed, so
+// that the memory latency of a tile hides behind the arithmetic of the one before it (one tile
+// per block spent 36 % of its stall samples waiting for those loads).
+constexpr int DERIV_TILES = 4;
 __global__ void __launch_bounds__(DERIV_BLOCK)
 derivatives_grain_kernel(const DerivArgs A, const __grid_constant__ FabricTable T) {
     __shared__ __align__(16) double mt[MATH_TABLE_DOUBLES];
-    load_math_tables(mt);
-    __syncthreads();
     const int64_t s = blockIdx.x;  // systems in grid.x: no 65535 limit
-    const int64_t g = (int64_t)blockIdx.y * DERIV_BLOCK + threadIdx.x;
-    if (g >= A.N) return;
+    const int64_t N = A.N;
+    int64_t g = (int64_t)blockIdx.y * (DERIV_BLOCK * DERIV_TILES) + threadIdx.x;
     const int regime = A.regime[s];
-    const double *o = A.o + s * 9 * A.N + g;
-    double *dst = A.d_o + s * 9 * A.N + g;
-    if (regime == 0 || regime == 7) {  // identity "derivative" (core.py:386-391,467-472)
+    const double *o = A.o + s * 9 * N;
+    double *dst = A.d_o + s * 9 * N;
+    if (regime == 0 || regime == 7 || regime == 1) {
+        // identity "derivative" (core.py:386-391,467-472); regime 1: every grain gets the spin
+        // argument (core.py:392-405)
+        for (int t = 0; t < DERIV_TILES && g < N; ++t, g += DERIV_BLOCK) {
 #pragma unroll
-        for (int c = 0; c < 9; ++c) dst[c * A.N] = (c % 4 == 0) ? 1.0 : 0.0;
-        A.energy[s * A.N + g] = 0.0;
-        return;
-    }
-    if (regime == 1) {  // every grain gets the spin argument (core.py:392-405)
-#pragma unroll
-        for (int c = 0; c < 9; ++c) dst[c * A.N] = A.spin[s * 9 + c];
-        A.energy[s * A.N + g] = 0.0;
+            for (int c = 0; c < 9; ++c)
+                dst[c * N + g] = (regime == 1) ? A.spin[s * 9 + c] : ((c % 4 == 0) ? 1.0 : 0.0);
+            A.energy[s * N + g] = 0.0;
+        }
         return;
     }
     double a[9], D[9], L[9];
+    if (g < N) {
+#pragma unroll
+        for (int c = 0; c < 9; ++c) a[c] = o[c * N + g];
+    }
+    load_math_tables(mt);
 #pragma unroll
     for (int c = 0; c < 9; ++c) {
-        a[c] = o[c * A.N];
         D[c] = A.D[s * 9 + c];
         L[c] = A.L[s * 9 + c];
     }
     const FabricConsts &fc = T.fab[A.fabric[s]];
-    GrainOut out;
-    grain_rhs<false>(a, D, L, fc, mt, out, nullptr);
     const double scale = (regime == 6) ? 0.3 : 1.0;  // core.py:459
+    __syncthreads();
+#pragma unroll 1
+    for (int t = 0; t < DERIV_TILES && g < N; ++t, g += DERIV_BLOCK) {
+        double an[9];
+        const int64_t gn = g + DERIV_BLOCK;
+        if (t + 1 < DERIV_TILES && gn < N) {
 #pragma unroll
-    for (int c = 0; c < 9; ++c) dst[c * A.N] = (regime == 6) ? scale * out.da[c] : out.da[c];
-    A.energy[s * A.N + g] = out.energy;
+            for (int c = 0; c < 9; ++c) an[c] = o[c * N + gn];
+        }
+        GrainOut out;
+        grain_rhs<false>(a, D, L, fc, mt, out, nullptr);
+#pragma unroll
+        for (int c = 0; c < 9; ++c) dst[c * N + g] = (regime == 6) ? scale * out.da[c] : out.da[c];
+        A.energy[s * N + g] = out.energy;
+#pragma unroll
+        for (int c = 0; c < 9; ++c) a[c] = an[c];
+    }
 }
 
 constexpr int GBM_BLOCK = 512;
