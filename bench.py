@@ -573,7 +573,8 @@ def run_gpu(args):
         "rejected_chunk_steps": res["chunk_rejects"],
         "failed_systems": failed,
         "parity_check": parity,
-        "gpu_launches": 2 * K,
+        # per step: integrate_kernel, gbs_restore_kernel, next_order_kernel
+        "gpu_launches": 3 * K,
         "e2e": e2e,
         "roofline": {
             "kernel": "drex::integrate_kernel", "bound": "fp64",
@@ -655,7 +656,7 @@ def run_e2e(args, drex, _lib, torch, dev, kind, tables, t_edges, barrier, max_ov
         raise RuntimeError("e2e arm: integration failed")
     return {"value": world * S * N * K / (ms * 1e-3), "unit": "grain-steps/s",
             "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "ms_per_step": ms / K, "gpu_launches_per_step": 3 * n_chunks,
+            "ms_per_step": ms / K, "gpu_launches_per_step": 4 * n_chunks,  # per group: next_order, integrate, gbs_restore, unpack_soa
             "state_upload_bytes_once": int(state),
             "api": "ParticleEnsemble.update_host",
             "note": "per step: this step's L tables and interval bounds from pinned host memory in, "

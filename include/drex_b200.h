@@ -215,6 +215,14 @@ int32_t drex_integrate_chunk_grains(void);
  * grain_evals [S]   int64 output (may be NULL): per-grain right-hand sides actually evaluated,
  *                   i.e. sum over chunks of (evaluations x grains in the chunk)
  */
+/* The `order` argument for the NEXT call from this call's counts: systems sorted by measured cost,
+ * most expensive first (cost = grain_evals[s] x 4 for olivine, x 1 for enstatite: the relative
+ * price of their right-hand sides), ties by index.  One small launch (S <= 16384; larger S:
+ * DREX_E_UNSUPPORTED, sort on the caller's side).  Stream-ordered like everything else, so the
+ * array the previous call read can be overwritten in place. */
+int drex_integrate_next_order(const int64_t *grain_evals, const int32_t *sys_phase, int64_t S,
+                              int32_t *order, void *stream);
+
 int drex_integrate_f64(int64_t S, int64_t P, int64_t N, const int32_t *sys_particle,
                        const int32_t *sys_phase, const int32_t *sys_fabric,
                        const int32_t *sys_regime, const double *sys_vol_frac,

@@ -31,6 +31,7 @@ EXPORTS = (
     "drex_derivatives_workspace_bytes", "drex_derivatives_f64", "drex_grain_probe_f64",
     "drex_grain_helper_f64",
     "drex_integrate_workspace_bytes", "drex_integrate_chunk_grains", "drex_integrate_f64",
+    "drex_integrate_next_order",
     "drex_voigt_average_f64", "drex_elasticity_components_f64",
     "drex_axis_scatter_f64",
     "drex_flow_field_f64",
@@ -158,6 +159,7 @@ def _declare(lib):
         [vp, vp, vp, i32, i32, c.POINTER(DrexParams), i64] + [vp] * 6 + [vp]
     )
     lib.drex_grain_helper_f64.argtypes = [i32, vp, vp, vp, vp, dbl, dbl, dbl, dbl, vp, vp]
+    lib.drex_integrate_next_order.argtypes = [vp, vp, i64, vp, vp]
     lib.drex_integrate_chunk_grains.restype = i32
     lib.drex_integrate_chunk_grains.argtypes = []
     lib.drex_integrate_workspace_bytes.restype = szt

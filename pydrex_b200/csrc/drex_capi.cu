@@ -285,6 +285,23 @@ size_t drex_integrate_workspace_bytes(int64_t S, int64_t N, int device, int in_p
     return need;
 }
 
+int drex_integrate_next_order(const int64_t *grain_evals, const int32_t *sys_phase, int64_t S,
+                              int32_t *order, void *stream) {
+    if (S < 0) return fail(DREX_E_INVALID, "negative size");
+    if (S == 0) return DREX_OK;
+    if (!grain_evals || !sys_phase || !order) return fail(DREX_E_INVALID, "drex_integrate_next_order: null pointer");
+    if (S > drex::ORDER_MAX)
+        return fail(DREX_E_UNSUPPORTED, "drex_integrate_next_order: more than %d systems", drex::ORDER_MAX);
+    const size_t smem = (size_t)S * sizeof(unsigned long long);
+    if (smem > 48 * 1024)
+        DREX_CUDA_CHECK(cudaFuncSetAttribute(drex::next_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem));
+    drex::next_order_kernel<<<1, drex::ORDER_THREADS, smem, (cudaStream_t)stream>>>(grain_evals, sys_phase, (int)S,
+                                                                                    order);
+    DREX_CUDA_CHECK(cudaGetLastError());
+    return DREX_OK;
+}
+
 int drex_integrate_f64(int64_t S, int64_t P, int64_t N, const int32_t *sys_particle,
                        const int32_t *sys_phase, const int32_t *sys_fabric,
                        const int32_t *sys_regime, const double *sys_vol_frac,

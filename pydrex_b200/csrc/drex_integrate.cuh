@@ -1283,4 +1283,40 @@ gbs_restore_kernel(const uint32_t *__restrict__ slide_mask, const double *__rest
     }
 }
 
+// Work-queue order of the next launch: systems by measured cost, most expensive first, ties by
+// index.  One CTA sorts 64-bit keys (complement of the cost | index) with the all-ascending
+// bitonic network over exactly S entries (virtual padding stays at the end and is never touched).
+constexpr int ORDER_THREADS = 1024;
+constexpr int ORDER_MAX = 16384;
+__global__ void __launch_bounds__(ORDER_THREADS)
+next_order_kernel(const int64_t *__restrict__ grain_evals, const int32_t *__restrict__ sys_phase, int n,
+                  int32_t *__restrict__ order) {
+    extern __shared__ __align__(16) unsigned long long order_keys[];
+    for (int i = threadIdx.x; i < n; i += ORDER_THREADS) {
+        unsigned long long cost = (unsigned long long)grain_evals[i] * (sys_phase[i] == 0 ? 4ull : 1ull);
+        if (cost >> 49) cost = (1ull << 49) - 1;
+        order_keys[i] = ((~cost & ((1ull << 49) - 1)) << 14) | (unsigned long long)i;
+    }
+    __syncthreads();
+    int npad = 2;
+    while (npad < n) npad <<= 1;
+    for (int k = 2; k <= npad; k <<= 1) {
+        for (int j = k; j > 0; j = (j == k) ? (k >> 2) : (j >> 1)) {
+            // first step of a merge: mirror image inside the block of k; then strides k/4, k/8, ...
+            for (int i = threadIdx.x; i < n; i += ORDER_THREADS) {
+                const int p = (j == k) ? (i ^ (k - 1)) : (i ^ j);
+                if (p > i && p < n) {
+                    const unsigned long long a = order_keys[i], b = order_keys[p];
+                    if (b < a) {
+                        order_keys[i] = b;
+                        order_keys[p] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < n; i += ORDER_THREADS) order[i] = (int32_t)(order_keys[i] & 0x3fffull);
+}
+
 }  // namespace drex

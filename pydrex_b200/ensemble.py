@@ -226,8 +226,7 @@ class ParticleEnsemble:
             Pp(self._ws), self._ws.numel(), _lib.stream_ptr(torch)))
         self.o, self._o_alt = self._o_alt, self.o
         # next launch: systems that needed the most right-hand sides go first
-        cost = self.stats[1].to(torch.float32) * self._weight
-        self.order = torch.argsort(cost, descending=True, stable=True).to(torch.int32)
+        self._next_order(0, self.S, self.order)
         if check:
             stats = self.stats.cpu().numpy()
             bad = np.nonzero(stats[0])[0]
@@ -239,6 +238,19 @@ class ParticleEnsemble:
             self.total_rhs += int(self.grain_evals.sum().item())
             self.total_steps += int(stats[2].sum())
         return self.stats[0]
+
+    def _next_order(self, s0, s1, out):
+        """Work-queue order of systems [s0, s1) for their next launch (indices relative to s0):
+        most expensive first by the measured right-hand sides of the last one."""
+        lib, torch = _lib.load(), self._torch
+        n = s1 - s0
+        if n <= 16384:
+            _lib.check(lib.drex_integrate_next_order(
+                _lib.ptr(self.grain_evals[s0:s1]), _lib.ptr(self.meta[1][s0:s1]), n, _lib.ptr(out),
+                _lib.stream_ptr(torch)))
+        else:
+            cost = self.grain_evals[s0:s1].to(torch.float32) * self._weight[s0:s1]
+            out.copy_(torch.argsort(cost, descending=True, stable=True).to(torch.int32))
 
     def _workspace(self):
         """Workspace and second orientation buffer of the integrator, allocated on first use."""
@@ -290,6 +302,7 @@ class ParticleEnsemble:
                 "streams": [torch.cuda.Stream(device=dev) for _ in range(3)],
                 "aos_in": [torch.empty((per, N, 9), dtype=f64, device=dev) for _ in range(2)],
                 "aos_out": [torch.empty((per, N, 9), dtype=f64, device=dev) for _ in range(2)],
+                "order": [torch.empty(per, dtype=torch.int32, device=dev) for _ in range(2)],
             }
         s_in, s_run, s_out = self._pipe["streams"]
         main = torch.cuda.current_stream(dev)
@@ -340,8 +353,8 @@ class ParticleEnsemble:
                 sp = _lib.stream_ptr(torch)
                 # longest systems of the group first (from the previous step's counts): a group
                 # is only ~2 systems per CTA, so the order decides the tail of its launch
-                cost = self.stats[1][s0:s1].to(torch.float32) * self._weight[s0:s1]
-                order = torch.argsort(cost, descending=True, stable=True).to(torch.int32)
+                order = self._pipe["order"][c % 2][:n]
+                self._next_order(s0, s1, order)  # from the previous step's counts
                 if upload:
                     s_run.wait_event(ev_in)
                     _lib.check(lib.drex_pack_soa_f64(Pp(aos), Pp(self.o[s0:s1]), n, N, sp))

@@ -1337,6 +1337,28 @@ def test_large_chebyshev_table_uses_the_same_interpolant(drex):
         nt.assert_allclose(F, results[0][2], rtol=0, atol=1e-10)
 
 
+def test_next_order_sorts_by_measured_cost(drex):
+    """drex_integrate_next_order: most expensive system first (olivine right-hand sides count
+    four times enstatite ones), ties by index; sizes that are not powers of two."""
+    import torch
+
+    from pydrex_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    for S in (1, 2, 3, 100, 2500, 4097, 16384):
+        evals = rng.integers(0, 50, size=S).astype(np.int64) * 5000  # many ties
+        phase = rng.integers(0, 2, size=S).astype(np.int32)
+        d_e, d_p = torch.as_tensor(evals).cuda(), torch.as_tensor(phase).cuda()
+        order = torch.empty(S, dtype=torch.int32, device="cuda")
+        _lib.check(lib.drex_integrate_next_order(_lib.ptr(d_e), _lib.ptr(d_p), S, _lib.ptr(order),
+                                                 _lib.stream_ptr(torch)))
+        cost = evals * np.where(phase == 0, 4, 1)
+        assert np.array_equal(order.cpu().numpy(), np.argsort(-cost, kind="stable")), S
+    assert lib.drex_integrate_next_order(_lib.ptr(d_e), _lib.ptr(d_p), 16385, _lib.ptr(order),
+                                         _lib.stream_ptr(torch)) < 0
+
+
 def test_more_systems_than_a_grid_dimension(drex, oracle):
     """More than 65535 systems (the limit of gridDim.y, where the layout, derivative and
     quaternion kernels used to carry the system index): construct, integrate, read back."""
