@@ -55,7 +55,10 @@ namespace drex {
 #endif
 constexpr int INT_G = DREX_INT_G;
 constexpr int INT_CHUNK = 32 * INT_G;
-constexpr int INT_BLOCK = 512 / INT_G;
+#ifndef DREX_INT_BLOCK
+#define DREX_INT_BLOCK (512 / DREX_INT_G)
+#endif
+constexpr int INT_BLOCK = DREX_INT_BLOCK;
 constexpr int INT_WARPS = INT_BLOCK / 32;
 constexpr int INT_CTAS_PER_SM = 1;
 constexpr int INT_NCTX = 3;   // systems in flight per CTA
