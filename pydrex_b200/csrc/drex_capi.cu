@@ -108,7 +108,7 @@ int integrate_slots(int device) {
 
 // Dynamic shared memory of the integrator: the per-warp state / prefetch rows and stage flows.
 inline size_t integrate_smem_bytes() {
-    return (size_t)drex::INT_WARPS * (drex::WARP_DOUBLES * sizeof(double) + 4 * sizeof(drex::ChunkFlow));
+    return (size_t)drex::INT_WARPS * (drex::WARP_DOUBLES * sizeof(double) + 3 * sizeof(drex::ChunkFlow));
 }
 
 // Per-CTA scratch: the per-chunk partial sums of the systems in flight.

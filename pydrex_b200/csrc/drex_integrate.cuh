@@ -208,14 +208,31 @@ struct ChunkFlow {
     double nks;     // -(0.3 if frictional) vf M* s: dv/dt = nks E
 };
 
+// Stage flows shared between the chunks of a system.  The step planner cuts what is left of the
+// interval into equal steps, so most chunks of a system walk the SAME (t, h) pairs -- and the
+// flows at t + h/2, t + 3h/4, t + h are the same for all of them.  The first warp that needs a
+// pair computes the flows into an entry, the others read them: bit-identical to computing them
+// (same function, same arguments), without the Clenshaw recurrences (19 % of the warps' time on
+// the corner-flow workload when every warp evaluated its own).  `key` is claimed with one
+// compare-and-swap (0 = free), `ready` is set after the data; an entry is never evicted.
+constexpr int FLOW_CACHE = 6;
+struct FlowEntry {
+    unsigned long long key;
+    double t, h;
+    ChunkFlow f[3];
+};
+
 // One system in flight (shared memory).  Written by the preparing warp before `ticket` is
-// published and read-only afterwards, except the counters at the end.
+// published and read-only afterwards, except the counters and the flow cache.
 struct SysSlot {
     double t0, t1, kappa, rscale;
     double s_begin, s_end;         // strain-rate scale at t0 and t1 (step sizes are carried as strain)
     double inv_span2;              // 2 / (t1 - t0), 0 for an empty interval
     double Q[9];                   // regimes 0/1/7: orientation increment common to all grains
     ChunkFlow cflow;               // the flow when L is constant over the interval
+    ChunkFlow flow_t0;             // otherwise: the flow at t0 (first right-hand side of every chunk)
+    FlowEntry fcache[FLOW_CACHE];
+    int fc_ready[FLOW_CACHE];
     double Ltab[INT_KMAX * 9];     // this particle's L(t) node table (K <= INT_KMAX)
     double coef[10][INT_KMAX];     // Chebyshev coefficients of L (0-8) and of the strain-rate scale (9)
     double ctab[2 * INT_KMAX];     // cos(pi m / (K - 1))
@@ -398,6 +415,56 @@ __device__ __noinline__ void warp_flows(const IntegrateArgs &A, const SysSlot &s
     store_flows(dst, n, val, false, sl.kappa, lane);
 }
 
+// The flows of the three stage times of a step (t + h/2, t + 3h/4, t + h): from the system's cache
+// when another chunk has taken the same step before, else computed -- into a free cache entry when
+// the step is one the planner produced (`cacheable`: a retry after a rejection has a step size of
+// its own and would only use up an entry), into the warp's private buffer otherwise.
+__device__ __forceinline__ const ChunkFlow *stage_flows(const IntegrateArgs &A, SysSlot &sl, ChunkFlow *wf,
+                                                        double t, double h, bool cacheable, bool cheb,
+                                                        int lane) {
+    const double ta = fma(BS_A21, h, t), tb = fma(BS_A32, h, t), tc = t + h;
+    const unsigned long long key =
+        (((unsigned long long)__double_as_longlong(t) * 0x9E3779B97F4A7C15ull) ^
+         (unsigned long long)__double_as_longlong(h)) | 1ull;  // never 0 (= free); t and h are compared too
+    const bool in = lane < FLOW_CACHE;
+    const unsigned long long tag = in ? ld_vol64(&sl.fcache[lane].key) : 0ull;
+    const unsigned match = __ballot_sync(0xffffffffu, in && tag == key);
+    ChunkFlow *dst = wf;
+    int claimed = -1;
+    if (match) {
+        const int e = __ffs(match) - 1;
+        if (ld_vol(&sl.fc_ready[e]) == 2) {
+            __threadfence_block();  // the entry's data was written before `ready`
+            if (sl.fcache[e].t == t && sl.fcache[e].h == h) return sl.fcache[e].f;
+        }
+        // (still being filled by another warp, or a different step with the same key: private copy)
+    } else if (cacheable) {
+        const unsigned empty = __ballot_sync(0xffffffffu, in && tag == 0ull);
+        if (empty) {
+            const int e = __ffs(empty) - 1;
+            unsigned long long old = 1ull;
+            if (lane == 0) old = atomicCAS(&sl.fcache[e].key, 0ull, key);
+            old = __shfl_sync(0xffffffffu, old, 0);
+            if (old == 0ull) {
+                claimed = e;
+                dst = sl.fcache[e].f;
+            }
+        }
+    }
+    if (cheb) warp_flows_cheb(sl, dst, 3, ta, tb, tc, lane);
+    else warp_flows(A, sl, dst, 3, ta, tb, tc, lane);
+    if (claimed >= 0) {
+        if (lane == 0) {
+            sl.fcache[claimed].t = t;
+            sl.fcache[claimed].h = h;
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) st_vol(&sl.fc_ready[claimed], 2);
+    }
+    return dst;
+}
+
 // Clip to [-1, 1] (utils.py:187) on the integer pipe: the FP64 pipe is the bottleneck and
 // the clip almost never fires.  |x| >= 1 (including inf/NaN) becomes +-1 exactly; a NaN
 // state is still caught by the error test through the unclipped new state.
@@ -479,7 +546,7 @@ struct ChunkResult {
 // and v_g in res.v.  Everything per grain is written as a loop over j < INT_G in straight-line
 // code, so that the two dependency chains of a lane interleave.
 template <int MODE>
-__device__ __forceinline__ void integrate_chunk(const IntegrateArgs &A, const SysSlot &sl,
+__device__ __forceinline__ void integrate_chunk(const IntegrateArgs &A, SysSlot &sl,
                                                 const FabricConsts &fc, const double *__restrict__ mt,
                                                 double *rows, ChunkFlow *wf, int lane,
                                                 const double (&f0)[INT_G], double h, ChunkResult &res
@@ -490,7 +557,8 @@ __device__ __forceinline__ void integrate_chunk(const IntegrateArgs &A, const Sy
     const double t_begin = sl.t0, t_end = sl.t1, span = t_end - t_begin;
     const double relw = A.tol.atol_rel + A.tol.rtol, atol_abs = A.tol.atol_abs;
     const bool f_active = sl.f_active != 0, const_flow = sl.const_flow != 0, cheb_flow = sl.s_table != 0;
-    const ChunkFlow *fl = const_flow ? &sl.cflow : wf;
+    // flows of stages 0..2 (f3: the step's) and of stage -1 (fm1: the interval's start)
+    const ChunkFlow *f3 = &sl.cflow, *fm1 = const_flow ? &sl.cflow : &sl.flow_t0;
     const int fstride = const_flow ? 0 : 1;
     const double rscale = sl.rscale;
     // row offsets inside a row set; the state and new-state rows swap on an accepted step
@@ -507,13 +575,7 @@ __device__ __forceinline__ void integrate_chunk(const IntegrateArgs &A, const Sy
             status = 1;  // DREX_STATUS_MAX_STEPS
             break;
         }
-        if (cheb_flow) {
-            if (need_k1) warp_flows_cheb(sl, wf + 3, 1, t, t, t, lane);
-            warp_flows_cheb(sl, wf, 3, fma(BS_A21, h, t), fma(BS_A32, h, t), t + h, lane);
-        } else if (!const_flow) {
-            if (need_k1) warp_flows(A, sl, wf + 3, 1, t, t, t, lane);
-            warp_flows(A, sl, wf, 3, fma(BS_A21, h, t), fma(BS_A32, h, t), t + h, lane);
-        }
+        if (!const_flow) f3 = stage_flows(A, sl, wf, t, h, !last_rejected, cheb_flow, lane);
         DREX_MARK(6)
         double k[INT_G][9], st[INT_G][9], e[INT_G], kv[INT_G], vy[INT_G], ve[INT_G];
 #pragma unroll
@@ -535,7 +597,7 @@ __device__ __forceinline__ void integrate_chunk(const IntegrateArgs &A, const Sy
         // after stage 3.  Stage -1 (first step of the interval only) is the slope at t0.
 #pragma unroll 1
         for (int stg = need_k1 ? -1 : 0; stg < 3; ++stg) {
-            const ChunkFlow &sf = fl[(stg & 3) * fstride];  // -1 -> [3]: the step's start time
+            const ChunkFlow &sf = (stg < 0) ? *fm1 : f3[stg * fstride];
 #pragma unroll
             for (int j = 0; j < INT_G; ++j) clip9(st[j]);
 #pragma unroll
@@ -882,6 +944,14 @@ __device__ __noinline__ void prepare_system(const IntegrateArgs &A, const Fabric
         if (lane == 1) sl.s_end = se;
         __syncwarp();
     }
+    if (!sl.const_flow) {
+        if (sl.s_table) warp_flows_cheb(sl, &sl.flow_t0, 1, sl.t0, sl.t0, sl.t0, lane);
+        else warp_flows(A, sl, &sl.flow_t0, 1, sl.t0, sl.t0, sl.t0, lane);
+    }
+    if (lane < FLOW_CACHE) {
+        sl.fcache[lane].key = 0ull;
+        sl.fc_ready[lane] = 0;
+    }
     const int status0 = integrate_gradient(A, sl, lane);
     if (lane == 0) sl.status0 = status0;
     __threadfence_block();
@@ -1030,7 +1100,7 @@ integrate_kernel(const __grid_constant__ IntegrateArgs A, const __grid_constant_
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
     const int64_t N = A.N;
     double *rows = dyn_smem + warp * WARP_DOUBLES;
-    ChunkFlow *wf = reinterpret_cast<ChunkFlow *>(dyn_smem + INT_WARPS * WARP_DOUBLES) + 4 * warp;
+    ChunkFlow *wf = reinterpret_cast<ChunkFlow *>(dyn_smem + INT_WARPS * WARP_DOUBLES) + 3 * warp;
     uint64_t *mbar = &sh.mbar[warp];
     uint32_t parity = 0;
     if (lane == 0) mbar_init(mbar, 1);
