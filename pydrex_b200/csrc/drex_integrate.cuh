@@ -215,7 +215,7 @@ struct ChunkFlow {
 // (same function, same arguments), without the Clenshaw recurrences (19 % of the warps' time on
 // the corner-flow workload when every warp evaluated its own).  `key` is claimed with one
 // compare-and-swap (0 = free), `ready` is set after the data; an entry is never evicted.
-constexpr int FLOW_CACHE = 6;
+constexpr int FLOW_CACHE = 6;  // 4 and 8 measure the same
 struct FlowEntry {
     unsigned long long key;
     double t, h;
@@ -1123,8 +1123,12 @@ integrate_kernel(const __grid_constant__ IntegrateArgs A, const __grid_constant_
     DREX_MARK(1)
 
     // TMA needs 16-byte aligned rows: N even and aligned bases; otherwise plain loads
+#ifdef DREX_NO_TMA_PREFETCH
+    const bool rows_aligned = false;
+#else
     const bool rows_aligned = ((N & 1) == 0) && ((reinterpret_cast<uintptr_t>(A.o_in) & 15) == 0) &&
                               ((reinterpret_cast<uintptr_t>(A.f_in) & 15) == 0);
+#endif
     auto prefetch = [&](const ChunkRef &ch) {
         // ten rows of INT_CHUNK grains (nine of o_in, one of f_in) of chunk ch into rows ROW_PF..,
         // component c at row ROW_PF + c * INT_G: one copy per lane, issued by ten lanes at once
