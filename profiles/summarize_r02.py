@@ -32,10 +32,12 @@ WANT = [
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "shared-memory bank conflicts"),
 ]
 kernels = ["integrate_kernel", "gbs_restore_kernel", "derivatives_grain_kernel", "derivatives_gbm_kernel",
-           "voigt_average_kernel", "mindex_pairs_reflect_kernel", "mindex_quats_kernel", "pathlines_kernel",
+           "voigt_average_kernel", "mindex_pairs_reflect_live_kernel", "mindex_pairs_reflect_kernel",
+           "mindex_quats_kernel", "pathlines_kernel",
            "resample_kernel", "pack_soa_kernel", "fp64_peak_kernel"]
 lines = ["ncu --set full --clock-control none, one launch per kernel, bench size (1250 particles x 2 phases x",
-         "5000 grains; M-index: 64 textures of 5000 grains); command: scripts/profile_all.sh", ""]
+         "5000 grains; M-index: 64 textures of 5000 grains); commands: scripts/profile_all.sh, scripts/final_run.sh",
+         "(mindex_pairs_reflect_kernel is the all-49-dots cross-check kernel, DREX_MINDEX_FULL=1)", ""]
 traffic = None
 for k in kernels:
     path = os.path.join(OUT, f"r02_{k}_raw.csv")
@@ -101,7 +103,10 @@ if os.path.exists(src):
             text += f"  executed ~{10 ** b:9.0f} times: {st:5d} static instructions, {100 * n / tot_n:5.1f}% of executed, {100 * s / tot_s:5.1f}% of stall samples\n"
     open(os.path.join(HERE, "r02_integrate_kernel_summary.txt"), "w").write(text)
 
-raw = os.path.join(OUT, "r02_launches_raw.csv")
+# launch list of the bench command itself (scripts/final_run.sh); else of scripts/profile_kernels.py
+raw = os.path.join(OUT, "r02_bench_launches_raw.csv")
+if not os.path.exists(raw):
+    raw = os.path.join(OUT, "r02_launches_raw.csv")
 if os.path.exists(raw):
     out = subprocess.run([sys.executable, os.path.join(HERE, "summarize_launches.py"), raw],
                          capture_output=True, text=True).stdout
