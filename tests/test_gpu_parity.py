@@ -69,6 +69,28 @@ def test_derivatives_match_oracle_random(drex, oracle, phase, fabric):
         nt.assert_allclose(fd, fd_ref, rtol=1e-10, atol=1e-15)
 
 
+def test_derivatives_match_oracle_million_grains(drex, oracle):
+    """1.2e6 Haar-random olivine grains in one call (default exponents, frictional-yielding
+    regime for the 0.3 factors) and 6e5 enstatite grains: every grain to 1e-10."""
+    from scipy.spatial.transform import Rotation
+
+    for phase, fabric, regime, N in ((0, 0, 6, 1_200_000), (1, 5, 4, 600_000)):
+        rng = np.random.default_rng(7 + phase)
+        o = Rotation.random(N, random_state=40 + phase).as_matrix()
+        f = rng.random(N)
+        f /= f.sum()
+        L = rng.normal(size=(3, 3))
+        L -= np.eye(3) * np.trace(L) / 3
+        D = (L + L.T) / 2
+        s = np.abs(np.linalg.eigvalsh(D)).max()
+        L, D = L / s, D / s
+        od, fd = drex.derivatives(regime, phase, fabric, N, o, f, D, L, np.eye(3), 1.5, 3.5, 5.0, 125.0, 0.7)
+        od_ref, fd_ref = oracle.derivatives(regime, phase, fabric, N, o, f, D, L, np.eye(3), 1.5, 3.5, 5.0,
+                                            125.0, 0.7)
+        nt.assert_allclose(od, od_ref, rtol=1e-10, atol=1e-13)
+        nt.assert_allclose(fd, fd_ref, rtol=1e-10, atol=1e-15 / 100)
+
+
 def test_derivatives_integer_inputs_and_errors(drex):
     # the reference tests pass int64 arrays (tests/test_core.py:43-44)
     o = np.eye(3, dtype=np.int64)[None]
