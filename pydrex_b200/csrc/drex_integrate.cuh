@@ -71,7 +71,9 @@ constexpr int INT_KMAX = 33;  // L(t) tables up to this many nodes live in share
 constexpr int ROW_A = 0, ROW_K1 = 9, ROW_Y = 18, ROW_E = 27, ROW_SET = 36;
 constexpr int ROW_PF = ROW_SET * INT_G, ROW_PF_SET = 10;
 constexpr int WARP_ROWS = (ROW_SET + ROW_PF_SET) * INT_G;
-constexpr int WARP_DOUBLES = WARP_ROWS * 32;
+// (+ 2 doubles: the chunk's rejected-step counter, bumped with a fire-and-forget shared-memory
+// reduction; as a register it lived on the stack and every step waited for its reload)
+constexpr int WARP_DOUBLES = WARP_ROWS * 32 + 2;
 
 struct TolArgs {
     double rtol, atol_abs, atol_rel, atol_abs_F, atol_abs_f, first_step_frac, max_step_frac;
@@ -568,10 +570,14 @@ __device__ __forceinline__ void integrate_chunk(const IntegrateArgs &A, SysSlot 
     double v[INT_G], kv1[INT_G];
 #pragma unroll
     for (int j = 0; j < INT_G; ++j) v[j] = kv1[j] = 0.0;
-    int n_rhs = 0, n_acc = 0, n_rej = 0, status = 0;
+    // attempts left (the only step counter in a register: right-hand sides and accepted steps
+    // follow from attempts and rejections) and the rejection counter in shared memory
+    int left = A.tol.max_steps, status = 0;
+    int *n_rej_smem = reinterpret_cast<int *>(rows + WARP_ROWS * 32);
+    if (lane == 0) *n_rej_smem = 0;
     bool need_k1 = true, last_rejected = false;
     while (span != 0.0) {
-        if (n_acc + n_rej >= A.tol.max_steps) {
+        if (left <= 0) {
             status = 1;  // DREX_STATUS_MAX_STEPS
             break;
         }
@@ -653,11 +659,12 @@ __device__ __forceinline__ void integrate_chunk(const IntegrateArgs &A, SysSlot 
             }
         }
         eb = __reduce_max_sync(0xffffffffu, eb);
-        n_rhs += need_k1 ? 4 : 3;
+        --left;
         need_k1 = false;
         const float emax = __uint_as_float(eb);
         if (!(emax < INFINITY)) {
             status = 3;  // DREX_STATUS_NOT_FINITE
+            if (lane == 0) atomicAdd(n_rej_smem, 1);  // (not an accepted step)
             break;
         }
         const bool accept = emax <= 1.0f;
@@ -667,7 +674,6 @@ __device__ __forceinline__ void integrate_chunk(const IntegrateArgs &A, SysSlot 
         double h_next = h * (double)facf;
         h_carry = h_next;
         if (accept) {
-            ++n_acc;
             last_rejected = false;
             t += h;
             const int tmp = off_a;
@@ -688,7 +694,7 @@ __device__ __forceinline__ void integrate_chunk(const IntegrateArgs &A, SysSlot 
             if (fabs(h_next) >= fabs(remaining) * (1.0 - 1e-10)) h_next = remaining;
             else if (DREX_STRETCH > 1.0) h_next = plan_step(h_next, remaining);
         } else {
-            ++n_rej;
+            if (lane == 0) atomicAdd(n_rej_smem, 1);
             last_rejected = true;
             if (fabs(h_next) <= 1e-14 * fmax(fabs(t), fabs(span))) {
                 status = 2;  // DREX_STATUS_STEP_UNDERFLOW
@@ -703,8 +709,10 @@ __device__ __forceinline__ void integrate_chunk(const IntegrateArgs &A, SysSlot 
     for (int j = 0; j < INT_G; ++j) res.v[j] = v[j];
     res.h_next = h_carry;
     res.status = status;
-    res.n_rhs = n_rhs;
-    res.n_acc = n_acc;
+    __syncwarp();
+    const int attempts = A.tol.max_steps - left, n_rej = *n_rej_smem;
+    res.n_rhs = attempts ? 3 * attempts + 1 : 0;  // the first attempt evaluates the slope at t0 as well
+    res.n_acc = attempts - n_rej;
     res.n_rej = n_rej;
     res.row = (off_a == ROW_A * 32 + lane) ? ROW_A : ROW_Y;
 }
