@@ -71,9 +71,7 @@ constexpr int INT_KMAX = 33;  // L(t) tables up to this many nodes live in share
 constexpr int ROW_A = 0, ROW_K1 = 9, ROW_Y = 18, ROW_E = 27, ROW_SET = 36;
 constexpr int ROW_PF = ROW_SET * INT_G, ROW_PF_SET = 10;
 constexpr int WARP_ROWS = (ROW_SET + ROW_PF_SET) * INT_G;
-// (+ 2 doubles: the chunk's rejected-step counter, bumped with a fire-and-forget shared-memory
-// reduction; as a register it lived on the stack and every step waited for its reload)
-constexpr int WARP_DOUBLES = WARP_ROWS * 32 + 2;
+constexpr int WARP_DOUBLES = WARP_ROWS * 32;
 
 struct TolArgs {
     double rtol, atol_abs, atol_rel, atol_abs_F, atol_abs_f, first_step_frac, max_step_frac;
@@ -115,6 +113,12 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
                  "r"(bytes)
                  : "memory");
 }
+// Spins before a wait is declared stuck (~1 s at 64 ns per spin).  A profiler that instruments the
+// kernel instruction by instruction (ncu's source counters) slows it down a hundredfold; build with
+// a larger value for such captures.
+#ifndef DREX_WATCHDOG_LOG2
+#define DREX_WATCHDOG_LOG2 24
+#endif
 __device__ __noinline__ void watchdog_fire(int where, long long a, long long b, long long c);
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int where = 100) {
     uint32_t done = 0;
@@ -128,7 +132,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int wh
             : "=r"(done)
             : "r"(addr), "r"(parity)
             : "memory");
-        if (!done && ++tries > (1u << 22)) watchdog_fire(where, parity, 0, 0);
+        if (!done && ++tries > (1u << (DREX_WATCHDOG_LOG2 - 2))) watchdog_fire(where, parity, 0, 0);
     }
 }
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_global, uint32_t bytes,
@@ -167,7 +171,7 @@ __device__ __noinline__ void watchdog_fire(int where, long long a, long long b, 
 __device__ __forceinline__ void spin_pause(unsigned &n, int where = 0, long long a = 0, long long b = 0,
                                            long long c = 0) {
     __nanosleep(64);
-    if (++n > (1u << 24)) watchdog_fire(where, a, b, c);
+    if (++n > (1u << DREX_WATCHDOG_LOG2)) watchdog_fire(where, a, b, c);
 }
 
 // Step planning: the rest of the interval is cut into n EQUAL steps, n the smallest count
@@ -217,7 +221,8 @@ struct ChunkFlow {
 // (same function, same arguments), without the Clenshaw recurrences (19 % of the warps' time on
 // the corner-flow workload when every warp evaluated its own).  `key` is claimed with one
 // compare-and-swap (0 = free), `ready` is set after the data; an entry is never evicted.
-constexpr int FLOW_CACHE = 6;  // 4 and 8 measure the same
+constexpr int FLOW_CACHE = 4;  // 6 and 8 measure the same; ncu's source-level instrumentation needs
+                               // ~5.6 KB of the CTA's shared memory for itself, which 6 entries did not leave
 struct FlowEntry {
     unsigned long long key;
     double t, h;
@@ -570,11 +575,12 @@ __device__ __forceinline__ void integrate_chunk(const IntegrateArgs &A, SysSlot 
     double v[INT_G], kv1[INT_G];
 #pragma unroll
     for (int j = 0; j < INT_G; ++j) v[j] = kv1[j] = 0.0;
-    // attempts left (the only step counter in a register: right-hand sides and accepted steps
-    // follow from attempts and rejections) and the rejection counter in shared memory
+    // attempts left and rejections: right-hand sides and accepted steps follow from them.  (With
+    // three counters ptxas kept them on the stack and every step waited for their reloads.  The
+    // rejections as a counter in shared memory measured the same, but ncu's source-level
+    // instrumentation could not run that kernel.)
     int left = A.tol.max_steps, status = 0;
-    int *n_rej_smem = reinterpret_cast<int *>(rows + WARP_ROWS * 32);
-    if (lane == 0) *n_rej_smem = 0;
+    int n_rej = 0;
     bool need_k1 = true, last_rejected = false;
     while (span != 0.0) {
         if (left <= 0) {
@@ -664,7 +670,7 @@ __device__ __forceinline__ void integrate_chunk(const IntegrateArgs &A, SysSlot 
         const float emax = __uint_as_float(eb);
         if (!(emax < INFINITY)) {
             status = 3;  // DREX_STATUS_NOT_FINITE
-            if (lane == 0) atomicAdd(n_rej_smem, 1);  // (not an accepted step)
+            ++n_rej;
             break;
         }
         const bool accept = emax <= 1.0f;
@@ -694,7 +700,7 @@ __device__ __forceinline__ void integrate_chunk(const IntegrateArgs &A, SysSlot 
             if (fabs(h_next) >= fabs(remaining) * (1.0 - 1e-10)) h_next = remaining;
             else if (DREX_STRETCH > 1.0) h_next = plan_step(h_next, remaining);
         } else {
-            if (lane == 0) atomicAdd(n_rej_smem, 1);
+            ++n_rej;
             last_rejected = true;
             if (fabs(h_next) <= 1e-14 * fmax(fabs(t), fabs(span))) {
                 status = 2;  // DREX_STATUS_STEP_UNDERFLOW
@@ -709,8 +715,7 @@ __device__ __forceinline__ void integrate_chunk(const IntegrateArgs &A, SysSlot 
     for (int j = 0; j < INT_G; ++j) res.v[j] = v[j];
     res.h_next = h_carry;
     res.status = status;
-    __syncwarp();
-    const int attempts = A.tol.max_steps - left, n_rej = *n_rej_smem;
+    const int attempts = A.tol.max_steps - left;
     res.n_rhs = attempts ? 3 * attempts + 1 : 0;  // the first attempt evaluates the slope at t0 as well
     res.n_acc = attempts - n_rej;
     res.n_rej = n_rej;
