@@ -11,7 +11,7 @@ import bench
 import pydrex_b200 as drex
 
 dev = torch.device("cuda", 0)
-for N in (100, 500, 1000, 2000, 5000, 10000, 20000, 50000):
+for N in [int(x) for x in os.environ.get("SWEEP_N", "100,500,1000,2000,5000,10000,20000,50000").split(",")]:
     P = max(148, int(6.25e6 / N))
     kind, tables, t_edges = bench.make_workload("simple_shear", P, 9, seed=1000)
     ens = drex.ParticleEnsemble(P, N, bench.PARAMS, seed=8816, device=dev)
