@@ -75,7 +75,9 @@ struct DerivArgs {
 // that the memory latency of a tile hides behind the arithmetic of the one before it (one tile
 // per block spent 36 % of its stall samples waiting for those loads).
 constexpr int DERIV_TILES = 4;
-__global__ void __launch_bounds__(DERIV_BLOCK)
+// (eight CTAs per SM, 64 registers with a little spilling: the kernel is bound by memory latency,
+// 32 resident warps beat 16 with everything in registers by 6 %)
+__global__ void __launch_bounds__(DERIV_BLOCK, 8)
 derivatives_grain_kernel(const DerivArgs A, const __grid_constant__ FabricTable T) {
     __shared__ __align__(16) double mt[MATH_TABLE_DOUBLES];
     const int64_t s = blockIdx.x;  // systems in grid.x: no 65535 limit
