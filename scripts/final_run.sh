@@ -8,7 +8,7 @@ timeout 900 python bench.py > gpurun_out/final_bench.json 2> gpurun_out/final_be
 timeout 900 python bench.py --impl reference > gpurun_out/final_ref.json 2> gpurun_out/final_ref.err; echo "reference arm rc=$?"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_bench_launches_raw.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-parity-check > gpurun_out/final_ncu_bench.log 2>&1; echo "launch list rc=$?"
-for k in integrate_kernel mindex_pairs_reflect_live_kernel derivatives_grain_kernel resample_kernel; do
+for k in integrate_kernel derivatives_grain_kernel voigt_average_kernel; do
     skip=0
     [ $k = integrate_kernel ] && skip=6
     timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s $skip -c 1 -f \
